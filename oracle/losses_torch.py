@@ -1,0 +1,122 @@
+"""torch-CPU restatement of the reference's TensorFlow loss graph.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED by the
+reference (TensorFlow cannot run here and the reference ships no tests): this
+file follows src/utils.py:302-311,343-360 and src/networks.py:797-870 op for
+op, in the reference's materialising form ([N,N,D] difference tensor), and is
+pinned only by the hand-checked known-answer tests of SURVEY.md Appendix B
+(tests/test_oracle_kat.py).  Gradients come from torch autograd through the
+same ops; ``amax``/``amin`` split the gradient evenly among ties exactly like
+TF's ``_MinOrMaxGrad``.
+
+dtype: pass float32 tensors for the parity target, float64 for the tolerance
+arbiter.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def all_diffs_tf(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """src/utils.py:302-311."""
+    return a.unsqueeze(1) - b.unsqueeze(0)
+
+
+def cdist_tf(diff: torch.Tensor, metric: str = "squaredeuclidean") -> torch.Tensor:
+    """src/utils.py:343-360."""
+    if metric == "squaredeuclidean":
+        return diff.square().sum(-1)
+    if metric == "euclidean":
+        return (diff.square().sum(-1) + 1e-12).sqrt()
+    if metric == "l1":
+        return diff.abs().sum(-1)
+    raise NotImplementedError(metric)
+
+
+def _masks(pids: torch.Tensor):
+    same = pids.unsqueeze(1) == pids.unsqueeze(0)          # networks.py:802-803
+    neg = ~same                                            # :804
+    pos = same ^ torch.eye(pids.shape[0], dtype=torch.bool)  # :805-806
+    return same, neg, pos
+
+
+def _weights(pids, neg, dtype, weighted):
+    n = pids.shape[0]
+    fg = (pids != 0).to(dtype)                             # networks.py:821
+    if weighted:
+        w = neg.to(dtype).sum(1) * fg                      # :824-825
+        w = w / w.sum()                                    # :826
+    else:
+        w = torch.full((n,), 1.0 / n, dtype=dtype)         # :828
+    return w, fg
+
+
+def _softplus(x):
+    return torch.clamp(x, min=0) + torch.log1p(torch.exp(-x.abs()))
+
+
+def batch_hard(dists: torch.Tensor, pids: torch.Tensor, margin, weighted: bool = True):
+    """src/networks.py:797-833.  Returns the reference 6-tuple
+    (loss, num_active, diff, weights, furthest_positive, closest_negative).
+
+    Empty negative set: reduce_min over an empty boolean_mask gives the reducer's
+    initial value; we state it as +inf (TF>=1.13) -- the loss term is 0 either way.
+    ``weighted=False`` makes the reference raise NameError at :831 (foreground_mask
+    undefined); we define num_active with the same foreground mask instead.
+    """
+    dt = dists.dtype
+    _, neg, pos = _masks(pids)
+    fp = (dists * pos.to(dt)).amax(dim=1)                                  # :808
+    inf = torch.full_like(dists, float("inf"))
+    cn = torch.where(neg, dists, inf).amin(dim=1)                          # :809-810
+    x = fp - cn                                                            # :812
+    if margin == "soft":
+        diff = _softplus(x)                                                # :814
+    else:
+        diff = torch.clamp(x + float(margin), min=0.0)                     # :816
+    w, fg = _weights(pids, neg, dt, weighted)
+    loss = (diff * w).sum()                                                # :830
+    num_active = ((diff * fg) > 1e-5).to(dt).sum() / fg.sum()              # :831
+    return loss, num_active, diff, w, fp, cn
+
+
+def lifted_loss(dists: torch.Tensor, pids: torch.Tensor, margin, weighted: bool = True):
+    """src/networks.py:835-870 (the author's variant).  num_active is the constant 1.0."""
+    dt = dists.dtype
+    _, neg, pos = _masks(pids)
+    fp = torch.logsumexp(dists * pos.to(dt), dim=1)                        # :846 -- over ALL N columns
+    ninf = torch.full_like(dists, float("-inf"))
+    has_neg = neg.any(dim=1)
+    masked = torch.where(neg, float(margin) - dists, ninf)                 # :847-848
+    # rows without negatives: logsumexp(empty) = -inf and contributes no gradient
+    safe = torch.where(has_neg.unsqueeze(1), masked, torch.zeros_like(masked))
+    cn = torch.where(has_neg, torch.logsumexp(safe, dim=1), torch.full_like(fp, float("-inf")))
+    diff = torch.clamp(torch.where(has_neg, fp + cn, torch.zeros_like(fp)), min=0.0)  # :850-852
+    w, _ = _weights(pids, neg, dt, weighted)
+    loss = (diff * w).sum()                                                # :866
+    return loss, 1.0, diff, w, fp, cn
+
+
+def mined_indices(dists: torch.Tensor, pids: torch.Tensor):
+    """Hardest-positive / hardest-negative column per row, first index among ties.
+    Rows without positives (negatives) get -1."""
+    _, neg, pos = _masks(pids)
+    dt = dists.dtype
+    pv = torch.where(pos, dists, torch.full_like(dists, -1.0))
+    pos_idx = pv.argmax(dim=1)
+    pos_idx = torch.where(pos.any(1), pos_idx, torch.full_like(pos_idx, -1))
+    nv = torch.where(neg, dists, torch.full_like(dists, float("inf")))
+    neg_idx = nv.argmin(dim=1)
+    neg_idx = torch.where(neg.any(1), neg_idx, torch.full_like(neg_idx, -1))
+    return pos_idx, neg_idx
+
+
+def loss_and_grad(kind: str, emb: torch.Tensor, pids: torch.Tensor, margin, weighted=True):
+    """Forward + backward through the materialising graph, as the reference trains
+    (src/base_model_batchhard.py:115-124, src/base_model_lifted.py:115-119)."""
+    e = emb.detach().clone().requires_grad_(True)
+    d = cdist_tf(all_diffs_tf(e, e))
+    fn = batch_hard if kind == "batch_hard" else lifted_loss
+    out = fn(d, pids.to(e.dtype), margin, weighted)
+    out[0].backward()
+    return out, e.grad.detach(), d.detach()

@@ -1,0 +1,52 @@
+"""Known-answer tests for the TF-half restatement (hand-checked)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses_torch as L
+
+E = torch.tensor([[0, 0], [1, 0], [0, 2], [3, 0]], dtype=torch.float64)
+
+KATS = [
+    ("batch_hard", [1, 1, 2, 2], 0.2, 4.6, [[0, 1], [1, 0], [-3, 1], [2, -2]]),
+    ("batch_hard", [1, 1, 2, 2], "soft", 4.524355377,
+     [[-0.0474258732, 1.0473024786], [1.0947283518, 0], [-2.9996298163, 0.9524507322], [1.9523273377, -1.9997532108]]),
+    ("lifted", [1, 1, 2, 2], 1.0, 5.079997649,
+     [[0.0100392764, 0.7310585786], [0.8588364384, 0.2689414214], [-2.8655089465, 0.9999864381], [1.9966332317, -1.9999864381]]),
+    ("batch_hard", [0, 1, 1, 2], "soft", 1.531039002,
+     [[0.5611507372, 0.8354955184], [0.4485812620, -1.9577969928], [-0.9788984964, 1.1223014743], [-0.0308335028, 0]]),
+]
+
+
+@pytest.mark.parametrize("kind,pids,margin,loss,grad", KATS)
+def test_kat(kind, pids, margin, loss, grad):
+    out, g, d = L.loss_and_grad(kind, E, torch.tensor(pids, dtype=torch.float64), margin)
+    assert float(out[0].detach()) == pytest.approx(loss, abs=1e-8)
+    assert np.allclose(g.numpy(), np.array(grad), atol=1e-8)
+
+
+def test_kat_details():
+    pids = torch.tensor([1., 1., 2., 2.], dtype=torch.float64)
+    out, _, d = L.loss_and_grad("batch_hard", E, pids, 0.2)
+    assert d.tolist()[0] == [0, 1, 4, 9]
+    assert out[4].tolist() == [1, 1, 13, 13] and out[5].tolist() == [4, 4, 4, 4]
+    assert out[2].tolist() == pytest.approx([0, 0, 9.2, 9.2])
+    p, n = L.mined_indices(d, pids)
+    assert p.tolist() == [1, 0, 3, 2] and n.tolist() == [2, 3, 0, 1]
+    out, _, _ = L.loss_and_grad("batch_hard", E, torch.tensor([0., 1., 1., 2.], dtype=torch.float64), "soft")
+    assert out[3].tolist() == pytest.approx([0, 2 / 7, 2 / 7, 3 / 7])
+    assert out[4].tolist() == [0, 5, 5, 0] and out[5].tolist() == [1, 1, 4, 4]
+
+
+def test_edge_semantics():
+    # single class: no negatives -> loss terms 0, weights 0/0 (undefined input, App. A.2) ; weighted=False is finite
+    pids = torch.ones(4, dtype=torch.float64)
+    out, g, _ = L.loss_and_grad("batch_hard", E, pids, 0.2, weighted=False)
+    assert float(out[0].detach()) == 0.0 and torch.isinf(out[5]).all() and (g == 0).all()
+    out, g, _ = L.loss_and_grad("lifted", E, pids, 1.0, weighted=False)
+    assert float(out[0].detach()) == 0.0 and (g == 0).all()
+    # exact ties split the gradient evenly (TF _MinOrMaxGrad)
+    E2 = torch.tensor([[0., 0.], [1., 0.], [-1., 0.], [0., 5.]], dtype=torch.float64)
+    out, g, _ = L.loss_and_grad("batch_hard", E2, torch.tensor([1., 1., 1., 2.], dtype=torch.float64), 0.2, weighted=False)
+    # row 0 has two furthest positives at distance 1 -> each gets half
+    assert g[0, 0] == pytest.approx(0.0)
