@@ -1,0 +1,98 @@
+/* mmsim -- C-ABI of the B200-native metric-learning hot path (libmmsim.so).
+ *
+ * The reference (johndpope/multimodal_similarity) has no FFI: its boundary is the Python signature of a few
+ * leaf functions in src/utils.py and src/networks.py.  Each entry point below replaces one of them; the Python
+ * package `multimodal_similarity_b200` mirrors the reference signatures on top of this ABI with ctypes
+ * (INTEGRATION.md shows the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative MMSIM_ERR_* code; mmsim_last_error() gives the
+ *     thread-local message of the last failure on the calling thread
+ *   - all data pointers are DEVICE pointers, row-major contiguous; the caller owns every buffer; the library
+ *     never allocates device memory: workspaces are sized by the *_workspace_bytes functions and passed in
+ *     (1024-byte aligned; cudaMalloc / torch allocations are)
+ *   - all work is enqueued on the caller's stream and returns asynchronously; no host synchronisation inside
+ *   - there is no CPU fallback: without a CUDA device of compute capability 10.0 the calls fail
+ */
+#ifndef MMSIM_H_
+#define MMSIM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mmsim_stream_t; /* == cudaStream_t */
+
+#if defined(__GNUC__)
+#define MMSIM_API __attribute__((visibility("default")))
+#else
+#define MMSIM_API
+#endif
+
+#define MMSIM_OK 0
+#define MMSIM_ERR_ARG (-1)
+#define MMSIM_ERR_WORKSPACE (-2)
+#define MMSIM_ERR_CUDA (-3)
+#define MMSIM_ERR_UNSUPPORTED (-4)
+
+#define MMSIM_METRIC_SQEUCLIDEAN 0 /* src/utils.py:335 */
+#define MMSIM_METRIC_EUCLIDEAN 1   /* src/utils.py:337  sqrt(sum + 1e-12) */
+#define MMSIM_METRIC_L1 2          /* src/utils.py:339 */
+
+#define MMSIM_LOSS_BATCH_HARD 0 /* src/networks.py:797-833 */
+#define MMSIM_LOSS_LIFTED 1     /* src/networks.py:835-870 */
+
+#define MMSIM_KNN_MAX_K 112 /* k (+1 with exclude_self) <= 112 on the tcgen05 path */
+
+MMSIM_API int mmsim_version(void);
+MMSIM_API const char* mmsim_last_error(void);
+
+/* out[i*ld + j] = dist(A[i,:], B[j,:]) -- replaces utils.cdist(utils.all_diffs(a, b), metric)
+ * (src/utils.py:313-341; the TF twins :302-311,343-360 compute the same values).  fp32, evaluated in NumPy's
+ * summation order: bit-identical to the reference's host path. */
+MMSIM_API int mmsim_sqdist_f32(const float* A, int64_t M, const float* B, int64_t N, int64_t D, int metric, float* out,
+                     int64_t ld, mmsim_stream_t stream);
+
+/* Fused loss forward + backward -- replaces
+ *   dists = cdist_tf(all_diffs_tf(E, E)); batch_hard(dists, pids, margin, weighted)   (kind 0)
+ *   dists = ...                         ; lifted_loss(dists, pids, margin, weighted)  (kind 1)
+ * (src/base_model_batchhard.py:115-124, src/base_model_lifted.py:115-119) and the gradient w.r.t. E that TF
+ * autodiff derives.  pids are float32 labels (label_ph is float32 in the reference), 0 = background.
+ * soft != 0 selects margin == "soft" (softplus) for batch_hard; otherwise `margin` is the numeric margin.
+ * Outputs follow the reference's return tuple: loss[1], num_active[1], diff[N], weights[N],
+ * furthest_positive[N], closest_negative[N]; plus the mined column indices pos_idx[N], neg_idx[N]
+ * (-1 when the row has no positive / negative; lifted writes -1).  dE[N*D] may be NULL (forward only). */
+MMSIM_API int mmsim_loss_workspace_bytes(int64_t N, int64_t D, size_t* bytes);
+MMSIM_API int mmsim_loss_f32(int kind, const float* E, const float* pids, int64_t N, int64_t D, int soft, float margin,
+                   int weighted, float* loss, float* num_active, float* diff, float* weights, float* furthest_positive,
+                   float* closest_negative, int32_t* pos_idx, int32_t* neg_idx, float* dE, void* ws, size_t ws_bytes,
+                   mmsim_stream_t stream);
+
+/* k nearest gallery rows of every query by the reference's retrieval distance
+ *   dist = np.linalg.norm(q - G, axis=1); idx = np.argsort(dist)[:k]        (src/utils.py:73-74)
+ * out_dist[nq*k] are the reference's float32 distances bit for bit, out_idx[nq*k] the row indices inside G
+ * (a shard holds < 2^31 rows), ordered by (distance, index); -1 / +inf pad when G has fewer than k rows.
+ * exclude_self != 0 drops gallery row (self_offset + i) for query i: the leave-one-out of utils.evaluate
+ * (src/utils.py:115,172) without the np.delete copy; indices stay in G's numbering.
+ * status[8] (device int32): [0] queries that needed the exact fallback, [1] fallback overflow (result invalid),
+ * [2] more uncertified queries than the fallback handles (result invalid).  D <= 256. */
+MMSIM_API int mmsim_knn_workspace_bytes(int64_t nq, int64_t ng, int64_t D, int k, size_t* bytes);
+MMSIM_API int mmsim_knn_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
+                  int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
+                  mmsim_stream_t stream);
+
+/* Merge `parts` shard-local results (as produced by mmsim_knn_f32 on each gallery shard and gathered with one
+ * NCCL all-gather) into the global top-k ordered by (distance, global index).  Part p's [nq][k] block starts at
+ * dist_parts + p * part_stride (same for idx_parts; part_stride in elements, >= nq*k, so a packed
+ * [parts][2][nq][k] gather buffer can be merged in place); global index = idx_base[p] + local index.
+ * parts * k <= 4096. */
+MMSIM_API int mmsim_knn_merge(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride, const int64_t* idx_base,
+                    int parts, int64_t nq, int k, float* out_dist, int64_t* out_idx, mmsim_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMSIM_H_ */

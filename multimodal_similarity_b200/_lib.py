@@ -1,0 +1,73 @@
+"""ctypes binding of libmmsim.so (include/mmsim.h).  No CPU fallback: a missing library or device is an error."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmsim.so")
+
+METRICS = {"squaredeuclidean": 0, "euclidean": 1, "l1": 2}
+LOSS_BATCH_HARD, LOSS_LIFTED = 0, 1
+KNN_MAX_K = 112
+
+# name -> (restype, argtypes); mirrors include/mmsim.h one to one (tests/test_abi.py checks the header against this)
+SIGNATURES = {
+    "mmsim_version": (c_int, []),
+    "mmsim_last_error": (c_char_p, []),
+    "mmsim_sqdist_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "mmsim_loss_workspace_bytes": (c_int, [c_int64, c_int64, POINTER(c_size_t)]),
+    "mmsim_loss_f32": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mmsim_knn_workspace_bytes": (c_int, [c_int64, c_int64, c_int64, c_int, POINTER(c_size_t)]),
+    "mmsim_knn_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int64,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mmsim_knn_merge": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+}
+
+
+class MmsimError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libmmsim.so (building it first if the sources are newer and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        try:
+            from .build import build
+            build()
+        except Exception as e:  # noqa: BLE001
+            raise MmsimError(
+                f"libmmsim.so is missing and could not be built ({e}); run `python -m multimodal_similarity_b200.build`. "
+                "There is no CPU fallback.") from e
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().mmsim_last_error()
+        raise MmsimError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def require_cuda(torch):
+    if not torch.cuda.is_available():
+        raise MmsimError("multimodal_similarity_b200 needs a CUDA device (sm_100a); there is no CPU fallback")

@@ -1,0 +1,77 @@
+// extern "C" surface of libmmsim.so (declared in include/mmsim.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/mmsim.h"
+#include "common.cuh"
+#include "knn.h"
+#include "loss.h"
+#include "merge.h"
+#include "sqdist.h"
+
+namespace mmsim {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace mmsim
+
+using namespace mmsim;
+
+extern "C" {
+
+MMSIM_API int mmsim_version(void) { return 100; }  // 0.1.0
+
+MMSIM_API const char* mmsim_last_error(void) { return g_err; }
+
+MMSIM_API int mmsim_sqdist_f32(const float* A, int64_t M, const float* B, int64_t N, int64_t D, int metric, float* out, int64_t ld,
+                     mmsim_stream_t stream) {
+  return sqdist::run(A, M, B, N, D, metric, out, ld, reinterpret_cast<cudaStream_t>(stream));
+}
+
+MMSIM_API int mmsim_loss_workspace_bytes(int64_t N, int64_t D, size_t* bytes) {
+  MMSIM_REQUIRE(bytes, MMSIM_ERR_ARG, "loss_workspace_bytes: null output");
+  MMSIM_REQUIRE(N >= 1 && N <= 1024 && D >= 1 && D <= 512, MMSIM_ERR_UNSUPPORTED,
+                "loss: N=%lld (1..1024), D=%lld (1..512) unsupported", (long long)N, (long long)D);
+  *bytes = loss::make_layout(N, D).total_bytes;
+  return MMSIM_OK;
+}
+
+MMSIM_API int mmsim_loss_f32(int kind, const float* E, const float* pids, int64_t N, int64_t D, int soft, float margin, int weighted,
+                   float* loss_out, float* num_active, float* diff, float* weights, float* furthest_positive,
+                   float* closest_negative, int32_t* pos_idx, int32_t* neg_idx, float* dE, void* ws, size_t ws_bytes,
+                   mmsim_stream_t stream) {
+  return loss::run(kind, E, pids, N, D, soft, margin, weighted, loss_out, num_active, diff, weights, furthest_positive,
+                   closest_negative, pos_idx, neg_idx, dE, ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+MMSIM_API int mmsim_knn_workspace_bytes(int64_t nq, int64_t ng, int64_t D, int k, size_t* bytes) {
+  MMSIM_REQUIRE(bytes, MMSIM_ERR_ARG, "knn_workspace_bytes: null output");
+  MMSIM_REQUIRE(nq > 0 && ng > 0 && D > 0 && D <= 256 && k >= 1, MMSIM_ERR_ARG, "knn_workspace_bytes: bad sizes");
+  // the layout is sized for the largest grid any device could use, so the answer does not depend on the device
+  size_t worst = 0;
+  for (int sms = 1; sms <= 192; ++sms) worst = std::max(worst, knn::make_plan(nq, ng, D, k, sms).total_bytes);
+  *bytes = worst;
+  return MMSIM_OK;
+}
+
+MMSIM_API int mmsim_knn_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
+                  int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
+                  mmsim_stream_t stream) {
+  return knn::run(Q, nq, G, ng, D, k, exclude_self, self_offset, out_dist, out_idx, status, ws, ws_bytes,
+                  reinterpret_cast<cudaStream_t>(stream));
+}
+
+MMSIM_API int mmsim_knn_merge(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride, const int64_t* idx_base,
+                    int parts, int64_t nq, int k, float* out_dist, int64_t* out_idx, mmsim_stream_t stream) {
+  return merge::run(dist_parts, idx_parts, part_stride, idx_base, parts, nq, k, out_dist, out_idx,
+                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

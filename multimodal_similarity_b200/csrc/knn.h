@@ -1,0 +1,29 @@
+// Internal declarations shared by the kNN translation units and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace mmsim {
+namespace knn {
+
+constexpr int KP = 128;  // approximate candidates kept per (query, gallery split); k <= KP - 16
+
+// Launch geometry + workspace layout of one mmsim_knn_f32 call (pure function of the problem size).
+struct Plan {
+  int Dp, katoms;             // padded feature width (multiple of 64) and number of 64-wide K atoms
+  int n_qblocks, n_tiles;     // 128-query blocks, 256-row gallery tiles
+  int n_splits, tiles_per_split, grid;
+  int unc_cap;                // max uncertified queries handled by the exact fallback
+  size_t off_qh, off_gh, off_gnorm, off_qnorm, off_qerr, off_stats, off_cand_key, off_cand_idx;
+  size_t off_unc_query, off_unc_bound, off_fb_count, off_fb_dist, off_fb_idx;
+  size_t total_bytes;
+};
+
+Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms);
+
+int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
+        float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace knn
+}  // namespace mmsim

@@ -1,0 +1,550 @@
+// K2/K3: batch-hard and lifted-structured loss, forward + backward in ONE cooperative launch.
+//
+// Reference semantics:
+//   dists = cdist_tf(all_diffs_tf(E, E))                       src/utils.py:302-311,343-360
+//   batch_hard(dists, pids, margin, weighted)                  src/networks.py:797-833
+//   lifted_loss(dists, pids, margin, weighted)                 src/networks.py:835-870
+// and the gradient TF autodiff produces for them.  The reference materialises [N,N,D]; here the N x N
+// matrix lives only in registers:
+//   phase 1  every CTA owns a TI x TJ tile of pairs: squared distances in difference form (the reference's
+//            arithmetic, D_ii == 0 exactly), label masks, and the tile's contribution to each row reduction
+//            (hardest positive / hardest negative with index and tie count, or online-logsumexp partials)
+//   barrier  one grid-wide barrier (cooperative launch => all CTAs co-resident)
+//   phase 2  row owners (one warp per row) combine the partials in a fixed order, write the reference's
+//            per-row outputs and the batch-hard sparse gradient; tile CTAs of the lifted loss reuse the
+//            distances still sitting in their registers for the dense gradient (G + G^T)(e_i - e_j)
+//   last CTA sums the per-row loss terms in a fixed order (deterministic loss value).
+// dE is accumulated with fp32 atomics (order-dependent in the last bits only).
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "common.cuh"
+#include "loss.h"
+
+namespace mmsim {
+namespace loss {
+
+constexpr int THREADS = 128;
+
+struct Params {
+  const float* E;
+  const float* pids;
+  int N, D, kind, soft, weighted;
+  float margin;
+  float *loss, *num_active, *diff, *w, *fp, *cn;
+  int *pos_idx, *neg_idx;
+  float* dE;
+  // workspace
+  float *p_a, *p_b, *p_c, *p_d;   // partial tables [NBJ][Npad]
+  int *p_ia, *p_ib, *p_ca, *p_cb; // partial index / tie-count tables
+  int* same_cnt;                  // [N] number of same-label columns (incl. self), integer atomics
+  float* row_loss;                // [N] l_i * w_i
+  float* row_active;              // [N]
+  unsigned int* sync;             // [0] barrier counter, [1] done counter
+  int NBI, NBJ, Npad;
+};
+
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+
+// hardest-positive style (max, smallest index among ties, tie count)
+struct Arg {
+  float v;
+  int i, c;
+};
+__device__ __forceinline__ Arg arg_max(Arg a, Arg b) {
+  if (a.v > b.v) return a;
+  if (b.v > a.v) return b;
+  return Arg{a.v, min(a.i, b.i) < 0 ? max(a.i, b.i) : min(a.i, b.i), a.c + b.c};
+}
+__device__ __forceinline__ Arg arg_min(Arg a, Arg b) {
+  if (a.v < b.v) return a;
+  if (b.v < a.v) return b;
+  return Arg{a.v, min(a.i, b.i) < 0 ? max(a.i, b.i) : min(a.i, b.i), a.c + b.c};
+}
+struct Lse {
+  float m, s;
+};
+__device__ __forceinline__ Lse lse_add(Lse a, float x) {
+  if (x <= a.m) {
+    a.s += expf(x - a.m);
+  } else {
+    a.s = a.s * expf(a.m - x) + 1.f;  // a.m == -inf -> exp(-inf) = 0
+    a.m = x;
+  }
+  return a;
+}
+__device__ __forceinline__ Lse lse_merge(Lse a, Lse b) {
+  const float m = fmaxf(a.m, b.m);
+  if (m == -kInf) return Lse{-kInf, 0.f};
+  return Lse{m, a.s * expf(a.m - m) + b.s * expf(b.m - m)};
+}
+__device__ __forceinline__ float lse_value(Lse a) { return a.s > 0.f ? a.m + logf(a.s) : -kInf; }
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int expected) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= expected) break;
+      if (clock64() - t0 > 4000000000LL) {
+        printf("mmsim: loss grid barrier timed out\n");
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// distance of row i to row j in the tile kernel's arithmetic (sequential fmaf over d) -- used by the tie path so
+// that equality tests against the mined extreme reproduce bit for bit
+__device__ float seq_sqdist(const float* __restrict__ a, const float* __restrict__ b, int D) {
+  float acc = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float x = a[d] - b[d];
+    acc = fmaf(x, x, acc);
+  }
+  return acc;
+}
+
+template <int MI, int MJ>
+__global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
+  constexpr int TI = 8 * MI, TJ = 16 * MJ;
+  extern __shared__ __align__(16) float sm[];
+  const int N = p.N, D = p.D;
+  const int D4 = (D + 3) & ~3;
+  const int DP = D4 + 4;
+  float* Ei = sm;                 // [TI][DP]
+  float* Ej = Ei + TI * DP;       // [TJ][DP]
+  float* pid_i = Ej + TJ * DP;    // [TI]
+  float* pid_j = pid_i + TI;      // [TJ]
+  float* st = pid_j + TJ;         // lifted: per-row stats for TI + TJ rows: fp, cn, coef -> 3 * (TI + TJ)
+  float* Ss = st + 3 * (TI + TJ); // lifted: S tile [TI][TJ + 1]
+  __shared__ int s_red[THREADS / 32];
+  __shared__ int s_W;
+  __shared__ int s_last;
+
+  const int t = threadIdx.x;
+  const int bi = blockIdx.x / p.NBJ, bj = blockIdx.x % p.NBJ;
+  const int i0 = bi * TI, j0 = bj * TJ;
+  const int ti = t >> 4, tj = t & 15;
+  const unsigned int G = gridDim.x;
+
+  // ---- zero this CTA's slice of dE (ordered before phase 2 by the grid barrier)
+  if (p.dE) {
+    const int64_t total = int64_t(N) * D;
+    for (int64_t x = int64_t(blockIdx.x) * THREADS + t; x < total; x += int64_t(G) * THREADS) p.dE[x] = 0.f;
+  }
+
+  // ---- stage the two row panels (coalesced, zero padded)
+  for (int x = t; x < TI * D4; x += THREADS) {
+    const int r = x / D4, c = x - r * D4;
+    Ei[r * DP + c] = (i0 + r < N && c < D) ? p.E[size_t(i0 + r) * D + c] : 0.f;
+  }
+  for (int x = t; x < TJ * D4; x += THREADS) {
+    const int r = x / D4, c = x - r * D4;
+    Ej[r * DP + c] = (j0 + r < N && c < D) ? p.E[size_t(j0 + r) * D + c] : 0.f;
+  }
+  if (t < TI) pid_i[t] = i0 + t < N ? p.pids[i0 + t] : 0.f;
+  if (t < TJ) pid_j[t] = j0 + t < N ? p.pids[j0 + t] : 0.f;
+  __syncthreads();
+
+  // ---- phase 1a: MI x MJ squared distances per thread, difference form
+  float acc[MI][MJ];
+#pragma unroll
+  for (int a = 0; a < MI; ++a)
+#pragma unroll
+    for (int b = 0; b < MJ; ++b) acc[a][b] = 0.f;
+  for (int d = 0; d < D4; d += 4) {
+    float4 av[MI], bv[MJ];
+#pragma unroll
+    for (int a = 0; a < MI; ++a) av[a] = *reinterpret_cast<const float4*>(Ei + (ti + 8 * a) * DP + d);
+#pragma unroll
+    for (int b = 0; b < MJ; ++b) bv[b] = *reinterpret_cast<const float4*>(Ej + (tj + 16 * b) * DP + d);
+#pragma unroll
+    for (int a = 0; a < MI; ++a)
+#pragma unroll
+      for (int b = 0; b < MJ; ++b) {
+        float x;
+        x = av[a].x - bv[b].x; acc[a][b] = fmaf(x, x, acc[a][b]);
+        x = av[a].y - bv[b].y; acc[a][b] = fmaf(x, x, acc[a][b]);
+        x = av[a].z - bv[b].z; acc[a][b] = fmaf(x, x, acc[a][b]);
+        x = av[a].w - bv[b].w; acc[a][b] = fmaf(x, x, acc[a][b]);
+      }
+  }
+
+  // ---- phase 1b: masked row reductions over this tile's columns
+#pragma unroll
+  for (int a = 0; a < MI; ++a) {
+    const int li = ti + 8 * a, i = i0 + li;
+    const float pi = pid_i[li];
+    int same = 0;
+    Arg hp{-1.f, -1, 0}, hn{kInf, -1, 0};
+    Lse lp{-kInf, 0.f}, ln{-kInf, 0.f};
+#pragma unroll
+    for (int b = 0; b < MJ; ++b) {
+      const int lj = tj + 16 * b, j = j0 + lj;
+      if (j >= N || i >= N) continue;
+      const bool same_id = pid_j[lj] == pi;
+      const bool pos = same_id && (i != j);
+      const float dist = acc[a][b];
+      same += same_id ? 1 : 0;
+      if (p.kind == 0) {
+        if (pos) hp = arg_max(hp, Arg{dist, j, 1});
+        if (!same_id) hn = arg_min(hn, Arg{dist, j, 1});
+      } else {
+        lp = lse_add(lp, pos ? dist : 0.f);              // over ALL columns (networks.py:846)
+        if (!same_id) ln = lse_add(ln, p.margin - dist);  // negatives only (:847-848)
+      }
+    }
+    // reduce over the 16 threads that share this row (xor offsets < 16 stay inside the half-warp)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      same += __shfl_xor_sync(0xffffffffu, same, o);
+      if (p.kind == 0) {
+        Arg o1{__shfl_xor_sync(0xffffffffu, hp.v, o), __shfl_xor_sync(0xffffffffu, hp.i, o), __shfl_xor_sync(0xffffffffu, hp.c, o)};
+        Arg o2{__shfl_xor_sync(0xffffffffu, hn.v, o), __shfl_xor_sync(0xffffffffu, hn.i, o), __shfl_xor_sync(0xffffffffu, hn.c, o)};
+        hp = arg_max(hp, o1);
+        hn = arg_min(hn, o2);
+      } else {
+        Lse o1{__shfl_xor_sync(0xffffffffu, lp.m, o), __shfl_xor_sync(0xffffffffu, lp.s, o)};
+        Lse o2{__shfl_xor_sync(0xffffffffu, ln.m, o), __shfl_xor_sync(0xffffffffu, ln.s, o)};
+        lp = lse_merge(lp, o1);
+        ln = lse_merge(ln, o2);
+      }
+    }
+    if (tj == 0 && i < N) {
+      const int slot = bj * p.Npad + i;
+      if (p.kind == 0) {
+        p.p_a[slot] = hp.v; p.p_ia[slot] = hp.i; p.p_ca[slot] = hp.c;
+        p.p_b[slot] = hn.v; p.p_ib[slot] = hn.i; p.p_cb[slot] = hn.c;
+      } else {
+        p.p_a[slot] = lp.m; p.p_b[slot] = lp.s;
+        p.p_c[slot] = ln.m; p.p_d[slot] = ln.s;
+      }
+      if (same) atomicAdd(&p.same_cnt[i], same);
+    }
+  }
+
+  grid_barrier(&p.sync[0], G);
+
+  // ---- phase 2a: W = sum_i (#negatives_i) * [pid_i != 0], exact in integers (every CTA, fixed order)
+  {
+    int part = 0;
+    for (int i = t; i < N; i += THREADS) part += (__ldcg(&p.pids[i]) != 0.f) ? (N - __ldcg(&p.same_cnt[i])) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((t & 31) == 0) s_red[t >> 5] = part;
+    __syncthreads();
+    if (t == 0) {
+      int tot = 0;
+      for (int x = 0; x < THREADS / 32; ++x) tot += s_red[x];
+      s_W = tot;
+    }
+    __syncthreads();
+  }
+  const float Wf = float(s_W);
+  const float invN = 1.0f / float(N);
+  auto weight_of = [&](int i) -> float {
+    if (!p.weighted) return invN;
+    const float wn = (__ldcg(&p.pids[i]) != 0.f) ? float(N - __ldcg(&p.same_cnt[i])) : 0.f;
+    return wn / Wf;
+  };
+
+  // ---- phase 2b: row owners -- one warp per row, fixed combine order over the NBJ partials
+  {
+    const int warp = t >> 5, lane = t & 31;
+    for (int i = blockIdx.x * (THREADS / 32) + warp; i < N; i += G * (THREADS / 32)) {
+      const float wi = weight_of(i);
+      const float fg = __ldcg(&p.pids[i]) != 0.f ? 1.f : 0.f;
+      if (p.kind == 0) {
+        Arg hp{-1.f, -1, 0}, hn{kInf, -1, 0};
+        if (lane < p.NBJ) {
+          const int slot = lane * p.Npad + i;
+          hp = Arg{__ldcg(&p.p_a[slot]), __ldcg(&p.p_ia[slot]), __ldcg(&p.p_ca[slot])};
+          hn = Arg{__ldcg(&p.p_b[slot]), __ldcg(&p.p_ib[slot]), __ldcg(&p.p_cb[slot])};
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          Arg o1{__shfl_xor_sync(0xffffffffu, hp.v, o), __shfl_xor_sync(0xffffffffu, hp.i, o), __shfl_xor_sync(0xffffffffu, hp.c, o)};
+          Arg o2{__shfl_xor_sync(0xffffffffu, hn.v, o), __shfl_xor_sync(0xffffffffu, hn.i, o), __shfl_xor_sync(0xffffffffu, hn.c, o)};
+          hp = arg_max(hp, o1);
+          hn = arg_min(hn, o2);
+        }
+        const float fp = fmaxf(hp.v, 0.f);  // max_j(D_ij * pos_ij) >= 0: masked zeros take part (networks.py:808)
+        const float cn = hn.v;              // +inf when the row has no negatives
+        const float x = fp - cn;
+        float l, dl;
+        if (p.soft) {
+          l = softplus_f(x);
+          dl = 1.f / (1.f + expf(-x));
+        } else {
+          l = fmaxf(x + p.margin, 0.f);
+          dl = (x + p.margin >= 0.f) ? 1.f : 0.f;
+        }
+        if (hn.i < 0) { l = 0.f; dl = 0.f; }  // empty negative set: the term is exactly 0
+        if (lane == 0) {
+          p.diff[i] = l; p.w[i] = wi; p.fp[i] = fp; p.cn[i] = cn;
+          p.pos_idx[i] = hp.i; p.neg_idx[i] = hn.i;
+          p.row_loss[i] = l * wi;
+          p.row_active[i] = (l * fg > 1e-5f) ? 1.f : 0.f;
+        }
+        // sparse gradient: dL/dD_ip = +c/|P|, dL/dD_in = -c/|N| ; dD_ij/de_i = 2(e_i - e_j)
+        const float c = wi * dl;
+        if (p.dE && c != 0.f) {
+          const float* ei = p.E + size_t(i) * D;
+          const bool use_pos = hp.i >= 0 && fp > 0.f;  // fp == 0: every tied entry has zero derivative
+          if (hp.c <= 1 && hn.c <= 1) {
+            const float* ep = p.E + size_t(use_pos ? hp.i : i) * D;
+            const float* en = p.E + size_t(hn.i) * D;
+            for (int d = lane; d < D; d += 32) {
+              const float vi = ei[d], vp = ep[d], vn = en[d];
+              float gi = -2.f * c * (vi - vn);
+              if (use_pos) {
+                gi += 2.f * c * (vi - vp);
+                atomicAdd(&p.dE[size_t(hp.i) * D + d], 2.f * c * (vp - vi));
+              }
+              atomicAdd(&p.dE[size_t(i) * D + d], gi);
+              atomicAdd(&p.dE[size_t(hn.i) * D + d], 2.f * c * (vi - vn));
+            }
+          } else {
+            // exact ties: TF splits the gradient evenly over the tied entries (math_grad._MinOrMaxGrad)
+            for (int j = 0; j < N; ++j) {
+              if (j == i) continue;
+              const bool same_id = __ldcg(&p.pids[j]) == __ldcg(&p.pids[i]);
+              float dist = 0.f;
+              if (lane == 0) dist = seq_sqdist(ei, p.E + size_t(j) * D, D);
+              dist = __shfl_sync(0xffffffffu, dist, 0);
+              float g = 0.f;
+              if (same_id && use_pos && dist == fp) g = c / float(hp.c);
+              if (!same_id && dist == cn) g = -c / float(hn.c);
+              if (g != 0.f) {
+                const float* ej = p.E + size_t(j) * D;
+                for (int d = lane; d < D; d += 32) {
+                  const float dv = 2.f * g * (ei[d] - ej[d]);
+                  atomicAdd(&p.dE[size_t(i) * D + d], dv);
+                  atomicAdd(&p.dE[size_t(j) * D + d], -dv);
+                }
+              }
+            }
+          }
+        }
+      } else {
+        Lse lp{-kInf, 0.f}, ln{-kInf, 0.f};
+        if (lane == 0) {
+          for (int b = 0; b < p.NBJ; ++b) {  // sequential: the tile CTAs below combine in the same order
+            const int slot = b * p.Npad + i;
+            lp = lse_merge(lp, Lse{__ldcg(&p.p_a[slot]), __ldcg(&p.p_b[slot])});
+            ln = lse_merge(ln, Lse{__ldcg(&p.p_c[slot]), __ldcg(&p.p_d[slot])});
+          }
+          const float fp = lse_value(lp), cn = lse_value(ln);
+          const float l = (cn > -kInf) ? fmaxf(fp + cn, 0.f) : 0.f;
+          p.diff[i] = l; p.w[i] = wi; p.fp[i] = fp; p.cn[i] = cn;
+          p.pos_idx[i] = -1; p.neg_idx[i] = -1;
+          p.row_loss[i] = l * wi;
+          p.row_active[i] = 1.f;
+        }
+      }
+    }
+  }
+
+  // ---- phase 2c (lifted): dense gradient from the distances still held in registers
+  if (p.kind == 1 && p.dE) {
+    // stats of the TI rows (as anchors) and the TJ rows (as anchors of the transposed entries)
+    for (int r = t; r < TI + TJ; r += THREADS) {
+      const int i = r < TI ? i0 + r : j0 + (r - TI);
+      float fp = 0.f, cn = -kInf, coef = 0.f;
+      if (i < N) {
+        Lse lp{-kInf, 0.f}, ln{-kInf, 0.f};
+        for (int b = 0; b < p.NBJ; ++b) {
+          const int slot = b * p.Npad + i;
+          lp = lse_merge(lp, Lse{__ldcg(&p.p_a[slot]), __ldcg(&p.p_b[slot])});
+          ln = lse_merge(ln, Lse{__ldcg(&p.p_c[slot]), __ldcg(&p.p_d[slot])});
+        }
+        fp = lse_value(lp);
+        cn = lse_value(ln);
+        coef = (cn > -kInf && fp + cn >= 0.f) ? weight_of(i) : 0.f;  // w_i * [l_i active]
+      }
+      st[r] = fp;
+      st[(TI + TJ) + r] = cn;
+      st[2 * (TI + TJ) + r] = coef;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < MI; ++a) {
+      const int li = ti + 8 * a, i = i0 + li;
+#pragma unroll
+      for (int b = 0; b < MJ; ++b) {
+        const int lj = tj + 16 * b, j = j0 + lj;
+        float s = 0.f;
+        if (i < N && j < N && i != j) {
+          const bool same_id = pid_j[lj] == pid_i[li];
+          const float dist = acc[a][b];
+          const float ci = st[2 * (TI + TJ) + li], cj = st[2 * (TI + TJ) + TI + lj];
+          if (same_id) {
+            // G_ij = c_i exp(D_ij - fp_i), G_ji = c_j exp(D_ij - fp_j)
+            if (ci != 0.f) s += ci * expf(dist - st[li]);
+            if (cj != 0.f) s += cj * expf(dist - st[TI + lj]);
+          } else {
+            if (ci != 0.f) s -= ci * expf(p.margin - dist - st[(TI + TJ) + li]);
+            if (cj != 0.f) s -= cj * expf(p.margin - dist - st[(TI + TJ) + TI + lj]);
+          }
+        }
+        Ss[li * (TJ + 1) + lj] = s;
+      }
+    }
+    __syncthreads();
+    // dE[i][d] += 2 * sum_j S_ij (e_i[d] - e_j[d])
+    for (int x = t; x < TI * D; x += THREADS) {
+      const int li = x / D, d = x - li * D;
+      if (i0 + li >= N) continue;
+      const float eid = Ei[li * DP + d];
+      float o = 0.f;
+#pragma unroll 8
+      for (int lj = 0; lj < TJ; ++lj) o = fmaf(Ss[li * (TJ + 1) + lj], eid - Ej[lj * DP + d], o);
+      if (o != 0.f) atomicAdd(&p.dE[size_t(i0 + li) * D + d], 2.f * o);
+    }
+  }
+
+  // ---- last CTA: deterministic sum of the per-row terms
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&p.sync[1], 1u) == G - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    __shared__ float s_l[THREADS], s_a[THREADS], s_f[THREADS];
+    float l = 0.f, a = 0.f, f = 0.f;
+    for (int i = t; i < N; i += THREADS) {
+      l += __ldcg(&p.row_loss[i]);
+      a += __ldcg(&p.row_active[i]);
+      f += __ldcg(&p.pids[i]) != 0.f ? 1.f : 0.f;
+    }
+    s_l[t] = l; s_a[t] = a; s_f[t] = f;
+    __syncthreads();
+    for (int o = THREADS / 2; o > 0; o >>= 1) {
+      if (t < o) { s_l[t] += s_l[t + o]; s_a[t] += s_a[t + o]; s_f[t] += s_f[t + o]; }
+      __syncthreads();
+    }
+    if (t == 0) {
+      *p.loss = s_l[0];
+      *p.num_active = p.kind == 0 ? s_a[0] / s_f[0] : 1.0f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+// Tile shapes (MI, MJ) -> TI = 8 MI rows x TJ = 16 MJ columns per CTA, smallest first.
+static const int kShapes[3][2] = {{2, 2}, {4, 4}, {8, 8}};
+
+static size_t smem_for(int TI, int TJ, int64_t D) {
+  const int D4 = int((D + 3) & ~int64_t(3));
+  return size_t(TI + TJ) * (D4 + 4) * 4 + size_t(TI + TJ) * 4 + size_t(3) * (TI + TJ) * 4 + size_t(TI) * (TJ + 1) * 4;
+}
+
+static const void* kernel_for(int shape) {
+  switch (shape) {
+    case 0: return reinterpret_cast<const void*>(loss_kernel<2, 2>);
+    case 1: return reinterpret_cast<const void*>(loss_kernel<4, 4>);
+    default: return reinterpret_cast<const void*>(loss_kernel<8, 8>);
+  }
+}
+
+// Pick the smallest tile whose grid fits co-resident on the device (a cooperative launch requires it).
+static int pick_shape(int64_t N, int64_t D) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      num_sms = 0;
+  }
+  for (int s = 0; s < 3; ++s) {
+    const int TI = 8 * kShapes[s][0], TJ = 16 * kShapes[s][1];
+    const size_t smem = smem_for(TI, TJ, D);
+    if (smem > 200 * 1024) continue;
+    const int64_t grid = ((N + TI - 1) / TI) * ((N + TJ - 1) / TJ);
+    int per_sm = 0;
+    if (num_sms > 0) {
+      cudaFuncSetAttribute(kernel_for(s), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_for(s), THREADS, smem) != cudaSuccess) per_sm = 0;
+    } else {
+      per_sm = int((227 * 1024) / (smem + 1024));  // no device (layout queries on a CPU box): assume 148 SMs
+    }
+    const int64_t cap = int64_t(per_sm) * (num_sms > 0 ? num_sms : 148);
+    if (grid <= cap) return s;
+  }
+  return -1;
+}
+
+Layout make_layout(int64_t N, int64_t D) {
+  Layout L{};
+  L.shape = pick_shape(N, D);
+  const int s = L.shape < 0 ? 2 : L.shape;
+  L.TI = 8 * kShapes[s][0];
+  L.TJ = 16 * kShapes[s][1];
+  L.NBI = int((N + L.TI - 1) / L.TI);
+  L.NBJ = int((N + L.TJ - 1) / L.TJ);
+  L.Npad = int(align_up(size_t(N), 32));
+  const size_t tab = size_t((N + 31) / 32) * L.Npad * 4;  // sized for the smallest TJ so the size is device independent
+  size_t off = 0;
+  auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
+  L.off_sync = take(256);
+  L.off_same = take(size_t(N) * 4);
+  L.zero_bytes = off;  // [sync | same_cnt] must be zeroed before every launch
+  for (int x = 0; x < 8; ++x) L.off_tab[x] = take(tab);
+  L.off_row_loss = take(size_t(N) * 4);
+  L.off_row_active = take(size_t(N) * 4);
+  L.total_bytes = off;
+  L.smem_bytes = smem_for(L.TI, L.TJ, D);
+  return L;
+}
+
+int run(int kind, const float* E, const float* pids, int64_t N, int64_t D, int soft, float margin, int weighted,
+        float* loss, float* num_active, float* diff, float* w, float* fp, float* cn, int* pos_idx, int* neg_idx,
+        float* dE, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  MMSIM_REQUIRE(E && pids && loss && num_active && diff && w && fp && cn && pos_idx && neg_idx && ws, MMSIM_ERR_ARG,
+                "loss: null pointer argument");
+  MMSIM_REQUIRE(kind == 0 || kind == 1, MMSIM_ERR_ARG, "loss: kind must be 0 (batch_hard) or 1 (lifted)");
+  MMSIM_REQUIRE(N >= 1 && N <= 1024, MMSIM_ERR_UNSUPPORTED, "loss: batch size N=%lld unsupported (1..1024)", (long long)N);
+  MMSIM_REQUIRE(D >= 1 && D <= 512, MMSIM_ERR_UNSUPPORTED, "loss: embedding width D=%lld unsupported (1..512)", (long long)D);
+  MMSIM_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, MMSIM_ERR_WORKSPACE, "loss: workspace must be 256-byte aligned");
+  const Layout L = make_layout(N, D);
+  MMSIM_REQUIRE(L.shape >= 0, MMSIM_ERR_UNSUPPORTED, "loss: N=%lld, D=%lld does not fit a co-resident grid on this device",
+                (long long)N, (long long)D);
+  MMSIM_REQUIRE(ws_bytes >= L.total_bytes, MMSIM_ERR_WORKSPACE, "loss: workspace too small (%zu < %zu)", ws_bytes, L.total_bytes);
+
+  uint8_t* b = static_cast<uint8_t*>(ws);
+  Params p{};
+  p.E = E; p.pids = pids; p.N = int(N); p.D = int(D); p.kind = kind; p.soft = soft; p.weighted = weighted; p.margin = margin;
+  p.loss = loss; p.num_active = num_active; p.diff = diff; p.w = w; p.fp = fp; p.cn = cn;
+  p.pos_idx = pos_idx; p.neg_idx = neg_idx; p.dE = dE;
+  p.sync = reinterpret_cast<unsigned int*>(b + L.off_sync);
+  p.same_cnt = reinterpret_cast<int*>(b + L.off_same);
+  p.p_a = reinterpret_cast<float*>(b + L.off_tab[0]); p.p_b = reinterpret_cast<float*>(b + L.off_tab[1]);
+  p.p_c = reinterpret_cast<float*>(b + L.off_tab[2]); p.p_d = reinterpret_cast<float*>(b + L.off_tab[3]);
+  p.p_ia = reinterpret_cast<int*>(b + L.off_tab[4]); p.p_ib = reinterpret_cast<int*>(b + L.off_tab[5]);
+  p.p_ca = reinterpret_cast<int*>(b + L.off_tab[6]); p.p_cb = reinterpret_cast<int*>(b + L.off_tab[7]);
+  p.row_loss = reinterpret_cast<float*>(b + L.off_row_loss);
+  p.row_active = reinterpret_cast<float*>(b + L.off_row_active);
+  p.NBI = L.NBI; p.NBJ = L.NBJ; p.Npad = L.Npad;
+
+  MMSIM_CUDA_CHECK(cudaMemsetAsync(b, 0, L.zero_bytes, stream));
+  void* args[] = {const_cast<Params*>(&p)};
+  const dim3 grid(unsigned(L.NBI * L.NBJ)), block(THREADS);
+  const void* fn = kernel_for(L.shape);
+  MMSIM_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L.smem_bytes)));
+  MMSIM_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, grid, block, args, L.smem_bytes, stream));
+  return MMSIM_OK;
+}
+
+}  // namespace loss
+}  // namespace mmsim

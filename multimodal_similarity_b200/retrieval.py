@@ -1,0 +1,157 @@
+"""Query x gallery retrieval -- drop-ins for the reference's evaluation path (src/utils.py:55-266).
+
+``retrieve`` is the GPU form of the per-query ``retrieve_one`` loop: distances are the reference's float32
+``np.linalg.norm(q - G, axis=1)`` bit for bit, neighbours are ordered by (distance, index).  The tcgen05 kernel
+only *filters*; every returned distance is recomputed in the reference arithmetic and the result is certified
+(or recomputed exactly), see csrc/knn_tc.cu.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._util import is_numpy_like, stream_handle, to_cuda_f32, workspace
+
+RECALL_KS = (1, 2, 4, 8, 16, 32)  # src/utils.py:190-197
+
+
+def late_fusion(*modalities):
+    """Feature concatenation of independently normalised modalities (src/evaluate_late_fusion.py:115,
+    src/evaluate_hallucination.py:59): d^2_fused = sum of the per-modality d^2."""
+    if all(is_numpy_like(m) for m in modalities):
+        return np.concatenate([np.asarray(m, dtype=np.float32) for m in modalities], axis=1)
+    dev = next(m.device for m in modalities if torch.is_tensor(m) and m.is_cuda)
+    return torch.cat([to_cuda_f32(m, dev) for m in modalities], dim=1)
+
+
+def knn_raw(q: torch.Tensor, g: torch.Tensor, k: int, exclude_self: bool = False, self_offset: int = 0):
+    """Low-level call: CUDA float32 tensors in, (dist [Q,k] f32, idx [Q,k] i32 shard-local, status [8] i32) out.
+    Asynchronous on the current stream; ``status`` is checked by the callers that hand results to the user."""
+    lib = _lib.load()
+    nq, d = q.shape
+    ng = g.shape[0]
+    if g.shape[1] != d:
+        raise ValueError(f"queries are {d}-d but the gallery is {g.shape[1]}-d")
+    if not 1 <= k <= _lib.KNN_MAX_K - (1 if exclude_self else 0):
+        raise ValueError(f"k={k} unsupported: 1 <= k <= {_lib.KNN_MAX_K - (1 if exclude_self else 0)}")
+    dev = q.device
+    nbytes = ctypes.c_size_t()
+    _lib.check(lib.mmsim_knn_workspace_bytes(nq, ng, d, k, ctypes.byref(nbytes)), "mmsim_knn_workspace_bytes")
+    ws = workspace("knn", nbytes.value, dev)
+    dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    status = torch.empty(8, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.mmsim_knn_f32(q.data_ptr(), nq, g.data_ptr(), ng, d, k, int(bool(exclude_self)), int(self_offset),
+                               dist.data_ptr(), idx.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(),
+                               stream_handle(dev))
+    _lib.check(rc, "mmsim_knn_f32")
+    return dist, idx, status
+
+
+def check_status(status: torch.Tensor) -> int:
+    """Synchronising check of a knn status word; returns the number of queries that took the exact fallback."""
+    s = status.tolist()
+    if s[1] or s[2]:
+        raise _lib.MmsimError(
+            f"knn: exact fallback could not finish (uncertified={s[0]}, overflow={s[1]}, too_many={s[2]}); the input has "
+            "massive exact ties or values outside the fp16 range")
+    return s[0]
+
+
+def retrieve(queries, gallery, k, *, exclude_self=False, self_offset=0, queries2=None, gallery2=None, check=True):
+    """Top-k gallery rows for every query.
+
+    Returns (dist [Q,k] float32, idx [Q,k] int64) -- the first k entries of the reference's
+    ``retrieve_one(q, gallery)`` (dist[idx[:k]], idx[:k]) for each query, ties ordered by index.
+    ``exclude_self`` removes gallery row ``self_offset + i`` for query i (leave-one-out, indices stay in the
+    gallery's numbering).  ``queries2`` / ``gallery2`` are a second modality, fused by concatenation (late fusion).
+    NumPy in -> NumPy out; CUDA tensors in -> CUDA tensors out.
+    """
+    as_numpy = is_numpy_like(queries) and is_numpy_like(gallery)
+    if (queries2 is None) != (gallery2 is None):
+        raise ValueError("late fusion needs both queries2 and gallery2")
+    if queries2 is not None:
+        queries, gallery = late_fusion(queries, queries2), late_fusion(gallery, gallery2)
+    q = to_cuda_f32(queries)
+    g = q if gallery is queries else to_cuda_f32(gallery, q.device)
+    dist, idx, status = knn_raw(q, g, int(k), exclude_self, self_offset)
+    if check:
+        check_status(status)
+    idx = idx.to(torch.int64)
+    if as_numpy:
+        return dist.cpu().numpy(), idx.cpu().numpy()
+    return dist, idx
+
+
+def retrieve_one(query, database, query_label=None, labels=None, normalize=False, k=None):
+    """The reference's single-query call (src/utils.py:55-81) restricted to the first k neighbours
+    (k defaults to min(N, 112)): returns (dist[idx], idx, ap@k) with ap@k the truncated AP
+    ``sum_{r<=k} P(r) rel(r) / min(k, #positives)`` (the full-ranking AP lives in evaluate())."""
+    if normalize:
+        raise NotImplementedError("retrieve_one(normalize=True) is broken in the reference (undefined name, src/utils.py:69)")
+    n = database.shape[0]
+    k = min(n, _lib.KNN_MAX_K) if k is None else k
+    q = np.asarray(query, dtype=np.float32).reshape(1, -1) if is_numpy_like(query) else query.reshape(1, -1)
+    dist, idx = retrieve(q, database, k)
+    dist, idx = dist[0], idx[0]
+    ap = None
+    if labels is not None:
+        lab = labels.cpu().numpy() if torch.is_tensor(labels) else np.asarray(labels)
+        ii = idx.cpu().numpy() if torch.is_tensor(idx) else idx
+        rel = (np.squeeze(lab)[ii] == query_label)
+        ap = average_precision_at_k(rel[None], np.array([(np.squeeze(lab) == query_label).sum()]))[0]
+    return dist, idx, ap
+
+
+def average_precision_at_k(rel: np.ndarray, n_pos: np.ndarray) -> np.ndarray:
+    """AP@k = sum_{r<=k} P(r) rel(r) / min(k, #positives) for boolean ``rel`` [Q,k] (an extension: the reference
+    only defines full-ranking AP).  nan where a query has no positive."""
+    rel = np.asarray(rel, dtype=bool)
+    k = rel.shape[1]
+    cum = np.cumsum(rel, axis=1)
+    prec = cum / np.arange(1, k + 1)[None, :]
+    denom = np.minimum(k, np.asarray(n_pos)).astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.where(denom > 0, (prec * rel).sum(1) / denom, np.nan)
+
+
+def recall_at_K(label_list, query_label, K=10):
+    """1 iff any of the first K ranked labels equals the query label (src/utils.py:257-266)."""
+    lab = label_list.cpu().numpy() if torch.is_tensor(label_list) else np.asarray(label_list)
+    return 1 if np.sum(lab[:K] == query_label) > 0 else 0
+
+
+def precision_at_recall(label_list, query_label, alpha=0.5):
+    """Per-class fractions of the ranked prefix that reaches recall alpha (src/utils.py:231-255)."""
+    lab = (label_list.cpu().numpy() if torch.is_tensor(label_list) else np.asarray(label_list)).tolist()
+    query_label = int(query_label)
+    target = int(alpha * sum(1 for l in lab if l == query_label))
+    counts = dict.fromkeys(sorted(set(lab)), 0)
+    depth = len(lab)
+    for i, l in enumerate(lab):
+        counts[l] += 1
+        if counts[query_label] == target:
+            depth = i + 1
+            break
+    frac = {c: n / depth for c, n in counts.items()}
+    return frac[query_label], frac
+
+
+def average_precision(y_true, score):
+    """sklearn-compatible AP (ties grouped into one threshold); see evaluate() for the fused GPU form."""
+    y = np.asarray(y_true).astype(bool).ravel()
+    s = np.asarray(score).ravel()
+    npos = int(y.sum())
+    if npos == 0:
+        return float("nan")
+    order = np.argsort(-s, kind="mergesort")
+    y, s = y[order], s[order]
+    ends = np.r_[np.where(np.diff(s))[0], y.size - 1]
+    tps = np.cumsum(y, dtype=np.float64)[ends]
+    prec = tps / (ends + 1)
+    rec = tps / npos
+    return float(np.sum(np.diff(np.r_[0.0, rec]) * prec))

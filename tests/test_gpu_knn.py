@@ -1,0 +1,136 @@
+"""K4: fused tcgen05 kNN + exact re-rank against the oracle (the reference's per-query distance + argsort)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import clustered, golden
+from oracle import retrieval_np as O
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_knn_equal(dist, idx, ref_d, ref_i):
+    """Distances bit-exact; indices exact outside exact-distance ties (argsort is unstable in the reference)."""
+    assert dist.dtype == np.float32 and idx.dtype == np.int64
+    assert np.array_equal(dist, ref_d), f"max |d - ref| = {np.nanmax(np.abs(dist - ref_d))}"
+    neq = idx != ref_i
+    if neq.any():
+        # a differing index must sit inside a run of equal distances (possibly cut by the k boundary)
+        q, r = np.nonzero(neq)
+        tied = np.zeros_like(neq)
+        tied[:, 1:] |= ref_d[:, 1:] == ref_d[:, :-1]
+        tied[:, :-1] |= ref_d[:, :-1] == ref_d[:, 1:]
+        tied[:, -1] = True
+        assert tied[q, r].all(), f"{neq.sum()} index mismatches outside ties"
+
+
+CASES = [
+    # nq, ng, d, k, classes
+    (300, 1000, 128, 10, 7),
+    (129, 4000, 256, 100, 20),
+    (64, 777, 64, 5, 3),
+    (200, 3000, 160, 50, 10),      # 128+32 late fusion width (evaluate_hallucination.py) -> padded to 192
+    (1, 300, 128, 112, 2),
+    (500, 257, 96, 16, 5),
+    (100, 20000, 128, 100, 50),
+]
+
+
+@pytest.mark.parametrize("nq,ng,d,k,c", CASES)
+def test_knn_vs_oracle(nq, ng, d, k, c, rs):
+    import multimodal_similarity_b200 as mm
+    g, _ = clustered(rs, ng, d, c)
+    q, _ = clustered(rs, nq, d, c)
+    q[: min(nq, 5)] = g[: min(nq, 5)]                      # exact duplicates: zero distances
+    dist, idx = mm.retrieve(q, g, k)
+    ref_d, ref_i = O.knn(q, g, k)
+    assert_knn_equal(dist, idx, ref_d, ref_i)
+
+
+def test_unnormalised_and_exclude_self(rs):
+    import multimodal_similarity_b200 as mm
+    x = (rs.randn(1500, 128) * 3.0 + 1.0).astype(np.float32)     # --no_normalized (App. A.1): not unit norm
+    dist, idx = mm.retrieve(x, x, 20, exclude_self=True)
+    ref_d, ref_i = O.knn(x, x, 20, exclude_self=True)
+    assert_knn_equal(dist, idx, ref_d, ref_i)
+    assert not (idx == np.arange(1500)[:, None]).any()
+
+
+def test_gallery_smaller_than_k(rs):
+    import multimodal_similarity_b200 as mm
+    g = rs.randn(7, 128).astype(np.float32)
+    q = rs.randn(40, 128).astype(np.float32)
+    dist, idx = mm.retrieve(q, g, 10)
+    ref_d, ref_i = O.knn(q, g, 7)
+    assert_knn_equal(dist[:, :7], idx[:, :7], ref_d, ref_i)
+    assert np.isinf(dist[:, 7:]).all() and (idx[:, 7:] == -1).all()
+
+
+def test_many_exact_ties(rs):
+    import multimodal_similarity_b200 as mm
+    base = rs.randn(40, 128).astype(np.float32)
+    g = np.repeat(base, 30, axis=0)                               # every row 30 times
+    q = base[:10] + 0.01 * rs.randn(10, 128).astype(np.float32)
+    dist, idx = mm.retrieve(q, g, 50)
+    ref_d, ref_i = O.knn(q, g, 50)
+    assert_knn_equal(dist, idx, ref_d, ref_i)
+    assert np.array_equal(idx, ref_i)                             # ties broken by index on both sides
+
+
+def test_golden_retrieve_one():
+    """First k of the reference's retrieve_one (golden vectors from the unmodified reference)."""
+    import multimodal_similarity_b200 as mm
+    for name in ("small", "fused", "odd"):
+        g = golden(f"retrieve_{name}.npz")
+        x = g["x"]
+        for n, qi in enumerate(g["queries"]):
+            db = np.delete(x, qi, 0)
+            dist, idx = mm.retrieve(x[qi:qi + 1], db, 50)
+            ref_sorted = g["dist"][n][g["order"][n]][:50]
+            assert np.array_equal(dist[0], ref_sorted)
+            untied = np.r_[True, ref_sorted[1:] != ref_sorted[:-1]] & np.r_[ref_sorted[:-1] != ref_sorted[1:], False]
+            assert np.array_equal(idx[0][untied], g["order"][n][:50][untied])
+
+
+def test_late_fusion_equals_concat(rs):
+    import multimodal_similarity_b200 as mm
+    cam, _ = clustered(rs, 3000, 128, 7)
+    sen, _ = clustered(rs, 3000, 128, 7)
+    d1, i1 = mm.retrieve(cam[:100], cam[100:], 50, queries2=sen[:100], gallery2=sen[100:])
+    fused = O.late_fusion(cam, sen)
+    ref_d, ref_i = O.knn(fused[:100], fused[100:], 50)
+    assert_knn_equal(d1, i1, ref_d, ref_i)
+
+
+def test_cuda_tensors_and_status(rs):
+    import multimodal_similarity_b200 as mm
+    from multimodal_similarity_b200.retrieval import knn_raw
+    g = torch.from_numpy(clustered(rs, 5000, 128, 9)[0]).cuda()
+    q = g[:256].clone()
+    d, i, status = knn_raw(q, g, 100)
+    s = status.cpu().numpy()
+    print("uncertified queries:", s[0])
+    assert s[1] == 0 and s[2] == 0
+    d2, i2 = mm.retrieve(q, g, 100)
+    assert d2.is_cuda and torch.equal(d2, d) and torch.equal(i2, i.long())
+    assert torch.all(i[:, 0] == torch.arange(256, device="cuda", dtype=torch.int32)) and torch.all(d[:, 0] == 0)
+
+
+def test_certificate_is_not_vacuous(rs):
+    """On ordinary data nearly every query is certified by the tcgen05 filter; the fallback stays (almost) idle."""
+    from multimodal_similarity_b200.retrieval import knn_raw
+    g = torch.from_numpy(clustered(rs, 30000, 128, 100)[0]).cuda()
+    q = torch.from_numpy(clustered(rs, 1024, 128, 100)[0]).cuda()
+    _, _, status = knn_raw(q, g, 100)
+    assert int(status[0]) <= 10, f"{int(status[0])} of 1024 queries fell back to the exact path"
+
+
+def test_rejects_bad_arguments(rs):
+    import multimodal_similarity_b200 as mm
+    x = rs.randn(10, 128).astype(np.float32)
+    with pytest.raises(ValueError):
+        mm.retrieve(x, x, 113)
+    with pytest.raises(ValueError):
+        mm.retrieve(x, rs.randn(10, 64).astype(np.float32), 3)
+    with pytest.raises(mm.MmsimError):
+        mm.retrieve(rs.randn(4, 300).astype(np.float32), rs.randn(9, 300).astype(np.float32), 3)   # D > 256

@@ -1,0 +1,45 @@
+"""K6: shard-simulation on one GPU -- split the gallery into R shards, local top-k on each, same merge kernel,
+compare with the unsharded result bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import clustered
+from oracle import retrieval_np as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("R", [2, 3, 8])
+@pytest.mark.parametrize("exclude_self", [False, True])
+def test_sharded_equals_unsharded(R, exclude_self, rs):
+    import multimodal_similarity_b200 as mm
+    from multimodal_similarity_b200.retrieval import knn_raw
+    from multimodal_similarity_b200.sharded import merge_parts, shard_bounds
+    x, _ = clustered(rs, 6001, 128, 11)
+    g = torch.from_numpy(x).cuda()
+    q = g[:300].clone() if exclude_self else torch.from_numpy(clustered(rs, 300, 128, 11)[0]).cuda()
+    k = 37
+    full_d, full_i = mm.retrieve(q, g, k, exclude_self=exclude_self)
+    packed = torch.empty((R, 2, 300, k), dtype=torch.int32, device="cuda")
+    bases = []
+    for r in range(R):
+        lo, hi = shard_bounds(6001, R, r)
+        d, i, st = knn_raw(q, g[lo:hi].contiguous(), k, exclude_self, -lo)
+        assert int(st[1]) == 0 and int(st[2]) == 0
+        packed[r, 0] = d.view(torch.int32)
+        packed[r, 1] = i
+        bases.append(lo)
+    md, mi = merge_parts(packed[:, 0].view(torch.float32), packed[:, 1], torch.tensor(bases, device="cuda"), k)
+    assert torch.equal(md, full_d) and torch.equal(mi, full_i)
+    ref_d, ref_i = O.knn(q.cpu().numpy(), x, k, exclude_self=exclude_self)
+    assert np.array_equal(md.cpu().numpy(), ref_d)
+
+
+def test_sharded_gallery_single_process(rs):
+    import multimodal_similarity_b200 as mm
+    x, _ = clustered(rs, 2000, 128, 5)
+    sg = mm.ShardedGallery(x)
+    d, i = sg.retrieve(x[:50], 10)
+    ref_d, ref_i = O.knn(x[:50], x, 10)
+    assert np.array_equal(d, ref_d) and i.dtype == np.int64
