@@ -10,7 +10,7 @@
  *     thread-local message of the last failure on the calling thread
  *   - all data pointers are DEVICE pointers, row-major contiguous; the caller owns every buffer; the library
  *     never allocates device memory: workspaces are sized by the *_workspace_bytes functions and passed in
- *     (1024-byte aligned; cudaMalloc / torch allocations are)
+ *     (256-byte aligned; cudaMalloc / torch allocations are)
  *   - all work is enqueued on the caller's stream and returns asynchronously; no host synchronisation inside
  *   - there is no CPU fallback: without a CUDA device of compute capability 10.0 the calls fail
  */
@@ -91,6 +91,19 @@ MMSIM_API int mmsim_knn_f32(const float* Q, int64_t nq, const float* G, int64_t 
  * parts * k <= 4096. */
 MMSIM_API int mmsim_knn_merge(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride, const int64_t* idx_base,
                     int parts, int64_t nq, int k, float* out_dist, int64_t* out_idx, mmsim_stream_t stream);
+
+/* Leave-one-out retrieval evaluation -- the loop body of utils.evaluate / utils.evaluate_simple
+ * (src/utils.py:83-229) for the query rows listed in `queries` (the rows with label > 0, :114,171).
+ * labels[N] are the raw int32 labels, cls[N] their dense class ids in [0, C).  Per query q (row i = queries[q]):
+ *   ap[q]     float64 sklearn average precision of retrieve_one (:78-79), 0 with npos[q] == 0 when row i has no positive
+ *   first[q]  rank (0-based) of the first ranked label equal to the query's (N-1 if none) -> recall_at_K (:257-266)
+ *   depth[q], hist[q*C + c]   prefix length walked by precision_at_recall (:231-255) and per-class counts inside it
+ *   rank[q*(N-1) + r]         (nullable) the full ranking in the row-i-deleted numbering, ordered by (distance, index)
+ * aligned == 0 reproduces the reference's label lookup (full label array indexed by deleted-gallery positions);
+ * aligned != 0 uses the deleted labels.  N <= 16385. */
+MMSIM_API int mmsim_evaluate_f32(const float* E, const int32_t* labels, const int32_t* cls, int64_t N, int64_t D, int C,
+                       const int32_t* queries, int64_t nq, double alpha, int aligned, double* ap, int32_t* npos,
+                       int32_t* first, int32_t* depth, int32_t* hist, int32_t* rank, mmsim_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,8 @@ from ._lib import MmsimError, load  # noqa: F401
 from .distance import all_diffs, all_diffs_tf, cdist, cdist_tf, pairwise_distance  # noqa: F401
 from .losses import batch_hard, lifted_loss  # noqa: F401
 from .retrieval import (  # noqa: F401
-    average_precision, late_fusion, precision_at_recall, recall_at_K, retrieve, retrieve_one,
+    average_precision, evaluate, evaluate_simple, full_ranking, late_fusion, precision_at_recall, recall_at_K, retrieve,
+    retrieve_one,
 )
 from .sharded import ShardedGallery  # noqa: F401
 

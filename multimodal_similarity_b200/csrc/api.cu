@@ -7,6 +7,7 @@
 
 #include "../../include/mmsim.h"
 #include "common.cuh"
+#include "eval.h"
 #include "knn.h"
 #include "loss.h"
 #include "merge.h"
@@ -72,6 +73,13 @@ MMSIM_API int mmsim_knn_merge(const float* dist_parts, const int32_t* idx_parts,
                     int parts, int64_t nq, int k, float* out_dist, int64_t* out_idx, mmsim_stream_t stream) {
   return merge::run(dist_parts, idx_parts, part_stride, idx_base, parts, nq, k, out_dist, out_idx,
                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+MMSIM_API int mmsim_evaluate_f32(const float* E, const int32_t* labels, const int32_t* cls, int64_t N, int64_t D, int C,
+                       const int32_t* queries, int64_t nq, double alpha, int aligned, double* ap, int32_t* npos,
+                       int32_t* first, int32_t* depth, int32_t* hist, int32_t* rank, mmsim_stream_t stream) {
+  return eval::run(E, labels, cls, N, D, C, queries, nq, alpha, aligned, ap, npos, first, depth, hist, rank,
+                   reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,9 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+namespace mmsim {
+namespace eval {
+int run(const float* E, const int* labels, const int* cls, int64_t N, int64_t D, int C, const int* queries, int64_t nq,
+        double alpha, int aligned, double* ap, int* npos, int* first, int* depth, int* hist, int* rank, cudaStream_t s);
+}
+}  // namespace mmsim

@@ -81,7 +81,7 @@ constexpr int NUM_THREADS = 192;           // warp 0: TMA, warp 1: MMA + TMEM ow
 
 template <int KATOMS>
 struct Smem {
-  static constexpr int NT = KATOMS == 1 ? 8 : 4;     // norm ring slots (>= ceil(NS/KATOMS) + 2)
+  static constexpr int NT = 4;                       // norm ring slots, recycled through their own empty barriers
   static constexpr int CB = KATOMS == 4 ? 24 : 32;   // candidate buffer entries per row
   static constexpr int CBP = CB + 1;                 // padded pitch: conflict-free append and row read
   static constexpr int A_OFF = 0;
@@ -90,7 +90,7 @@ struct Smem {
   static constexpr int CK_OFF = NORM_OFF + NT * BN * 4;
   static constexpr int CI_OFF = CK_OFF + BM * CBP * 4;
   static constexpr int BAR_OFF = CI_OFF + BM * CBP * 4;  // 8-byte aligned: all terms are multiples of 8? checked below
-  static constexpr int NUM_BARS = 2 * NS + 2 + 2 + 2;
+  static constexpr int NUM_BARS = 2 * NS + 2 + 2 + 2 + NT;
   static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
   static constexpr int TOTAL = TMEM_PTR_OFF + 8;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment of the base
@@ -142,6 +142,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   uint64_t* tempty = bars + 2 * NS + 2;  // [2]   epilogue -> MMA (accumulator drained)
   uint64_t* afull = bars + 2 * NS + 4;   //       query tile landed
   uint64_t* aempty = bars + 2 * NS + 5;  //       all MMAs of the item done, query tile may be overwritten
+  uint64_t* nempty = bars + 2 * NS + 6;  // [NT]  epilogue finished a tile: its norm slot may be refilled
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::TMEM_PTR_OFF);
 
   const uint32_t warp = threadIdx.x >> 5;
@@ -160,6 +161,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     }
     ptx::mbar_init(afull, 1);
     ptx::mbar_init(aempty, 1);
+    for (int i = 0; i < S::NT; ++i) ptx::mbar_init(&nempty[i], BM);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_ptr, 2 * BN);  // 512 columns: two 128x256 fp32 accumulators
@@ -188,7 +190,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             ptx::mbar_wait(&empty[stage], phase ^ 1);
             ptx::mbar_expect_tx(&full[stage], B_STAGE_BYTES + (ka == 0 ? BN * 4 : 0));
             ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tm_g, ka * KATOM, t * BN, &full[stage]);
-            if (ka == 0) ptx::bulk_load_1d(norm_ring + (tc % S::NT) * BN, gnorm + size_t(t) * BN, BN * 4, &full[stage]);
+            if (ka == 0) {
+              // the epilogue reads this tile's norms long after it released the accumulator: separate hand-back
+              ptx::mbar_wait(&nempty[tc % S::NT], ((tc / S::NT) & 1) ^ 1);
+              ptx::bulk_load_1d(norm_ring + (tc % S::NT) * BN, gnorm + size_t(t) * BN, BN * 4, &full[stage]);
+            }
           }
         }
       }
@@ -311,6 +317,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             }
           }
         }
+        ptx::mbar_arrive(&nempty[tc % S::NT]);
       }
       __syncwarp();
       flush_rows(__ballot_sync(0xffffffffu, cnt > 0));
@@ -605,7 +612,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   MMSIM_REQUIRE(k >= 1 && k + (exclude_self ? 1 : 0) <= KP - 16, MMSIM_ERR_UNSUPPORTED,
                 "knn: k=%d unsupported (1 <= k <= %d)", k, KP - 16 - (exclude_self ? 1 : 0));
   MMSIM_REQUIRE(ng < (int64_t(1) << 31) - BN && nq < (int64_t(1) << 31) - BM, MMSIM_ERR_ARG, "knn: a shard must hold < 2^31 rows");
-  MMSIM_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, MMSIM_ERR_WORKSPACE, "knn: workspace must be 1024-byte aligned");
+  MMSIM_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, MMSIM_ERR_WORKSPACE, "knn: workspace must be 256-byte aligned");
 
   int dev = 0, num_sms = 0;
   MMSIM_CUDA_CHECK(cudaGetDevice(&dev));

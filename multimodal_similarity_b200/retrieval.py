@@ -155,3 +155,88 @@ def average_precision(y_true, score):
     prec = tps / (ends + 1)
     rec = tps / npos
     return float(np.sum(np.diff(np.r_[0.0, rec]) * prec))
+
+
+# --------------------------------------------------------------------------- leave-one-out evaluation (K5)
+def _loo_records(embeddings, labels, normalize, standardize, alpha, aligned, want_rank=False):
+    """Run the fused per-query kernel (csrc/eval.cu) for every foreground row; returns host-side records."""
+    lib = _lib.load()
+    lab_np = np.squeeze(labels.cpu().numpy() if torch.is_tensor(labels) else np.asarray(labels)).astype(np.int32)
+    emb = to_cuda_f32(embeddings)
+    if normalize:      # src/utils.py:104-105,154-155 (the reference normalises the caller's array in place)
+        emb = emb / torch.linalg.vector_norm(emb, dim=1, keepdim=True)
+    if standardize:    # :106-109,156-159 (float32 statistics, like NumPy on a float32 array)
+        emb = (emb - emb.mean(dim=0)) / emb.std(dim=0, unbiased=False)
+    emb = emb.contiguous()
+    n, d = emb.shape
+    dev = emb.device
+    classes, cls_np = np.unique(lab_np, return_inverse=True)
+    queries_np = np.nonzero(lab_np > 0)[0].astype(np.int32)          # only foreground rows are queries (:114,171)
+    nq, C = int(queries_np.size), int(classes.size)
+    lab = torch.from_numpy(lab_np).to(dev)
+    cls = torch.from_numpy(cls_np.astype(np.int32)).to(dev)
+    queries = torch.from_numpy(queries_np).to(dev)
+    ap = torch.empty(nq, dtype=torch.float64, device=dev)
+    ints = torch.empty((3, max(nq, 1)), dtype=torch.int32, device=dev)
+    hist = torch.empty((max(nq, 1), C), dtype=torch.int32, device=dev)
+    rank = torch.empty((nq, n - 1), dtype=torch.int32, device=dev) if want_rank else None
+    with torch.cuda.device(dev):
+        rc = lib.mmsim_evaluate_f32(emb.data_ptr(), lab.data_ptr(), cls.data_ptr(), n, d, C, queries.data_ptr(), nq,
+                                    float(alpha), int(bool(aligned)), ap.data_ptr(), ints[0].data_ptr(), ints[1].data_ptr(),
+                                    ints[2].data_ptr(), hist.data_ptr(), _lib.ptr(rank), stream_handle(dev))
+    _lib.check(rc, "mmsim_evaluate_f32")
+    ints = ints.cpu().numpy()
+    rec = dict(classes=classes.tolist(), labels=lab_np, queries=queries_np, ap=ap.cpu().numpy(), npos=ints[0][:nq],
+               first=ints[1][:nq], depth=ints[2][:nq], hist=hist.cpu().numpy()[:nq], n=n)
+    if want_rank:
+        rec["rank"] = rank
+    return rec
+
+
+def evaluate_simple(embeddings, labels, normalize=False, standardize=False, alpha=0.5, aligned=False):
+    """Leave-one-out retrieval over all foreground rows -> (mAP, mPrec@alpha, R@1) (src/utils.py:83-138).
+
+    ``aligned=False`` keeps the reference's label lookup for mPrec / R@1 (see csrc/eval.cu); queries without any
+    positive are skipped like the reference's nan-AP branch (:118-123)."""
+    r = _loo_records(embeddings, labels, normalize, standardize, alpha, aligned)
+    ok = r["npos"] > 0
+    qcls = np.searchsorted(r["classes"], r["labels"][r["queries"]])
+    prec = r["hist"][np.arange(len(qcls)), qcls] / r["depth"]
+    return np.mean(r["ap"][ok]), np.mean(prec[ok]), np.mean((r["first"][ok] < 1).astype(np.int64))
+
+
+def evaluate(embeddings, labels, normalize=False, standardize=False, alpha=0.5, aligned=False):
+    """Leave-one-out retrieval -> (mAP, mAP_event, mPrec, confusion, count, recall) exactly as src/utils.py:140-229:
+    per-class mAP dict, confusion = {"confusion_matrix": float32 [C,C], "labels": [...]}, count int32 [C,1],
+    recall = [R@1, R@2, R@4, R@8, R@16, R@32]."""
+    r = _loo_records(embeddings, labels, normalize, standardize, alpha, aligned)
+    classes, lab = r["classes"], r["labels"]
+    ok = np.nonzero(r["npos"] > 0)[0]
+    qlab = lab[r["queries"][ok]]
+    qcls = np.searchsorted(classes, qlab)
+    aps = r["ap"][ok]
+    frac = r["hist"][ok] / r["depth"][ok][:, None]                      # python int / int -> float64 (:252)
+    mAP = np.mean(aps)
+    mPrec = np.mean(frac[np.arange(len(ok)), qcls])
+    mAP_event = {}
+    for a, l in zip(aps, qlab.tolist()):
+        mAP_event.setdefault(l, []).append(a)
+    mAP_event = {l: np.mean(v) for l, v in mAP_event.items()}
+    cm = np.zeros((len(classes), len(classes)), dtype="float32")
+    count = np.zeros((len(classes), 1), dtype="int32")
+    for n_, row in enumerate(qcls):                                     # sequential float32 accumulation (:214-220)
+        cm[row] += frac[n_].astype(np.float32)
+        count[row] += 1
+    cm[1:] /= count[1:]                                                 # :222 (assumes class 0 is row 0)
+    count[0] = (lab == 0).sum()                                         # :223
+    confusion = {"confusion_matrix": cm, "labels": classes}
+    recall = [float((r["first"][ok] < K).sum()) / len(ok) for K in RECALL_KS]
+    return mAP, mAP_event, mPrec, confusion, count, recall
+
+
+def full_ranking(embeddings, labels=None):
+    """[N, N-1] int32 leave-one-out rankings (row-i-deleted numbering, ordered by (distance, index)) for every row:
+    the argsort of the reference's retrieve_one, on the GPU."""
+    n = embeddings.shape[0]
+    lab = np.ones(n, np.int32) if labels is None else labels
+    return _loo_records(embeddings, lab, False, False, 0.5, True, want_rank=True)["rank"]

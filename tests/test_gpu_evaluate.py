@@ -1,0 +1,71 @@
+"""K5: utils.evaluate / utils.evaluate_simple on the GPU against golden outputs of the unmodified reference."""
+import numpy as np
+import pytest
+
+from conftest import clustered, golden
+from oracle import retrieval_np as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["hdd", "cub", "fused"])
+def test_evaluate_golden(name):
+    import multimodal_similarity_b200 as mm
+    g = golden(f"eval_{name}.npz")
+    mAP, mAP_event, mPrec, confusion, count, recall = mm.evaluate(g["x"], g["labels"], alpha=float(g["alpha"]))
+    assert mAP == pytest.approx(float(g["mAP"]), abs=1e-12)
+    assert mPrec == pytest.approx(float(g["mPrec"]), abs=1e-12)
+    assert sorted(mAP_event) == g["mAP_event_keys"].tolist()
+    assert np.allclose([mAP_event[k] for k in sorted(mAP_event)], g["mAP_event_vals"], atol=1e-12)
+    assert confusion["labels"] == g["confusion_labels"].tolist()
+    assert np.array_equal(confusion["confusion_matrix"], g["confusion"])        # float32, bit for bit
+    assert np.array_equal(count, g["count"]) and count.dtype == np.int32
+    assert recall == g["recall"].tolist()
+    s = mm.evaluate_simple(g["x"], g["labels"], alpha=float(g["alpha"]))
+    assert np.allclose(s, g["simple"], atol=1e-12)
+
+
+def test_evaluate_switches_golden():
+    import multimodal_similarity_b200 as mm
+    g = golden("eval_switches.npz")
+    # normalisation / standardisation run in torch on the GPU: distances can differ in the last bit from NumPy's,
+    # so these compare at metric level
+    assert np.allclose(mm.evaluate_simple(g["x"].copy(), g["labels"], normalize=True), g["normalize"], atol=2e-3)
+    assert np.allclose(mm.evaluate_simple(g["x"].copy(), g["labels"], standardize=True), g["standardize"], atol=2e-3)
+
+
+@pytest.mark.parametrize("n,d,c,bg,alpha", [(64, 16, 3, 0.3, 0.5), (513, 128, 11, 0.0, 0.3), (1025, 96, 6, 0.5, 1.0), (300, 256, 40, 0.1, 0.0)])
+def test_evaluate_vs_oracle(n, d, c, bg, alpha, rs):
+    import multimodal_similarity_b200 as mm
+    x, lab = clustered(rs, n, d, c, background=bg)
+    x[7] = x[3]                                            # duplicate rows: exact ties in distance and in score
+    for aligned in (False, True):
+        ref = O.evaluate(x, lab, alpha=alpha, aligned=aligned)
+        got = mm.evaluate(x, lab, alpha=alpha, aligned=aligned)
+        assert got[0] == pytest.approx(ref[0], abs=1e-12) and got[2] == pytest.approx(ref[2], abs=1e-9)
+        assert got[1].keys() == ref[1].keys()
+        assert np.allclose(got[3]["confusion_matrix"], ref[3]["confusion_matrix"], atol=1e-6)
+        assert np.array_equal(got[4], ref[4])
+        assert np.allclose(got[5], ref[5], atol=1.5 / n)   # a tie at the K boundary may flip one query
+
+
+def test_full_ranking_matches_reference_argsort(rs):
+    import multimodal_similarity_b200 as mm
+    x, _ = clustered(rs, 400, 128, 5)
+    rank = mm.full_ranking(x).cpu().numpy()
+    for i in (0, 1, 200, 399):
+        dist = O.l2_to_all(x[i], np.delete(x, i, 0))
+        assert np.array_equal(dist[rank[i]], np.sort(dist))
+        assert np.array_equal(rank[i], np.lexsort((np.arange(399), dist)))
+
+
+def test_cub_shape_recall(rs):
+    """BASELINE config 3 in miniature: GoogleNet-shaped features projected to 128-d, labels 101.., all foreground."""
+    import multimodal_similarity_b200 as mm
+    feats = rs.randn(20, 1024)[rs.randint(0, 20, 1200)] + rs.randn(1200, 1024)
+    emb = (feats @ (rs.randn(1024, 128) / 32)).astype(np.float32)
+    emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+    lab = (rs.randint(0, 20, 1200) + 101).astype(np.int32)
+    ref = O.evaluate(emb, lab)
+    got = mm.evaluate(emb, lab)
+    assert got[0] == pytest.approx(ref[0], abs=1e-12) and got[5] == ref[5]

@@ -134,3 +134,18 @@ def test_rejects_bad_arguments(rs):
         mm.retrieve(x, rs.randn(10, 64).astype(np.float32), 3)
     with pytest.raises(mm.MmsimError):
         mm.retrieve(rs.randn(4, 300).astype(np.float32), rs.randn(9, 300).astype(np.float32), 3)   # D > 256
+
+
+def test_random_shape_sweep(rs):
+    import multimodal_similarity_b200 as mm
+    for trial in range(24):
+        d = int(rs.choice([32, 64, 100, 128, 160, 192, 200, 256]))
+        nq = int(rs.randint(1, 700))
+        ng = int(rs.randint(1, 9000))
+        k = int(rs.randint(1, 113))
+        g, _ = clustered(rs, ng, d, int(rs.randint(1, 30)))
+        q, _ = clustered(rs, nq, d, 5)
+        dist, idx = mm.retrieve(q, g, k)
+        kk = min(k, ng)
+        ref_d, ref_i = O.knn(q, g, kk)
+        assert_knn_equal(dist[:, :kk], idx[:, :kk], ref_d, ref_i)
