@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Headline benchmark: kNN queries/s on a 1M x 128 gallery (BASELINE.json metric), at 1/2/4/8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # N > 1: launched by torchrun, one rank per GPU
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path (oracle port) on host cores
+
+One "step" = one pass of the hot path over one batch of synthetic input: 100,000 queries against the
+1,000,000-row gallery, top-100 (SURVEY.md 8(d) config 5 at the metric's 128-d): fp32 -> fp16 operand copies,
+the fused tcgen05 distance + candidate kernel, the exact fp32 re-rank + certificate, the exact fallback and (N > 1)
+the NCCL all-gather + merge.  With N GPUs the 1M gallery is split over the ranks (strong scaling: total work fixed).
+
+Rank 0 prints ONE JSON line.  `value` is whole-job queries/s with inputs resident in HBM; `e2e` is the same metric
+through the public API with pinned HOST buffers (H2D of gallery shard + queries and D2H of the result inside the
+timed region); `roofline` is the dominant kernel (knn_tc_kernel) against the measured dense bf16 tensor peak;
+`cpu_baseline` is the oracle's NumPy port of the reference's retrieve_one timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(queries=100_000, gallery=1_000_000, dim=128, k=100, clusters=1000)
+SEED = 12345  # configs/base_config.py:15
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--queries", type=int, default=WORKLOAD["queries"])
+    ap.add_argument("--gallery", type=int, default=WORKLOAD["gallery"])
+    ap.add_argument("--dim", type=int, default=WORKLOAD["dim"])
+    ap.add_argument("--k", type=int, default=WORKLOAD["k"])
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / loss timings (profiling runs)")
+    return ap.parse_args()
+
+
+def config_of(a, n_gpus):
+    return {"workload": f"sharded kNN: {a.queries} queries x {a.gallery} gallery, {a.dim}-d, top-{a.k} "
+                        f"(BASELINE configs[4] at the metric's 128-d), gallery rows split over {n_gpus} GPU(s)",
+            "queries": a.queries, "gallery": a.gallery, "dim": a.dim, "k": a.k,
+            "l2": f"inputs larger than L2 (fp32 gallery {a.gallery * a.dim * 4 / 1e6:.0f} MB + fp16 copy, 126 MB L2)",
+            "parallelism": f"gallery-sharded x{n_gpus}, queries replicated, NCCL all-gather merge" if n_gpus > 1 else "single GPU"}
+
+
+# ----------------------------------------------------------------------------------------------- synthetic data
+def synth_numpy(n, dim, clusters, seed):
+    """Cluster centroids + noise, L2-normalised."""
+    rs = np.random.RandomState(seed)
+    cent = rs.randn(clusters, dim).astype(np.float32)
+    x = cent[rs.randint(0, clusters, size=n)] + 0.5 * rs.randn(n, dim).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return x.astype(np.float32)
+
+
+def synth_torch(n, dim, clusters, seed, device):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    cent = torch.randn(clusters, dim, generator=g, device=device)
+    lab = torch.randint(0, clusters, (n,), generator=g, device=device)
+    x = cent[lab] + 0.5 * torch.randn(n, dim, generator=g, device=device)
+    return (x / x.norm(dim=1, keepdim=True)).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Sample nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arms
+def cpu_queries_per_s(q, g, n_queries, threads):
+    """The reference's retrieve_one body (distance to every row + full argsort, src/utils.py:73-74) via the oracle port."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import retrieval_np as O
+
+    def one(i):
+        dist = O.l2_to_all(q[i], g)
+        return np.argsort(dist)[:8].sum()
+
+    t0 = time.perf_counter()
+    if threads == 1:
+        for i in range(n_queries):
+            one(i)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(one, range(n_queries)))
+    dt = time.perf_counter() - t0
+    return n_queries / dt, dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 32))
+    g = synth_numpy(a.gallery, a.dim, WORKLOAD["clusters"], SEED)
+    q = synth_numpy(4 * threads, a.dim, WORKLOAD["clusters"], SEED + 1)
+    per_step = threads  # bounded sample of the 100k-query batch: one query per worker thread per step
+    for _ in range(max(1, min(a.warmup, 2))):
+        cpu_queries_per_s(q, g, per_step, threads)
+    times = []
+    for _ in range(a.steps):
+        _, dt = cpu_queries_per_s(q, g, per_step, threads)
+        times.append(dt)
+    total = sum(times)
+    v = per_step * a.steps / total
+    sample = f"{per_step} of {a.queries} queries per step against the full {a.gallery} x {a.dim} gallery, {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "knn_queries_per_s", "value": v, "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_of(a, a.gpus),
+        "cpu_baseline": {"value": v, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle/retrieval_np.py port of utils.retrieve_one (NumPy distance + full argsort), thread pool over queries; "
+                "TensorFlow is not installable here and the reference's retrieval path is NumPy anyway",
+    }))
+
+
+# ----------------------------------------------------------------------------------------------- loss timings
+def time_losses(torch, mm):
+    """batch-hard fwd+bwd (256 = 32 x 8, 128-d) and lifted fwd+bwd (512, 128-d): microseconds per call (second half of the metric)."""
+    out = {}
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for name, n, fn, margin in (("batch_hard_fwd_bwd_us", 256, mm.batch_hard, "soft"), ("lifted_fwd_bwd_us", 512, mm.lifted_loss, 1.0)):
+        e = synth_torch(n, 128, 32, SEED + 2, dev).requires_grad_(True)
+        pids = (torch.arange(n, device=dev) % 32 + 1).float() if n == 256 else (torch.arange(n, device=dev) % 7).float()
+        from multimodal_similarity_b200.losses import _run
+        kind = 0 if n == 256 else 1
+        soft = margin == "soft"
+        for _ in range(20):
+            _run(kind, e.detach(), pids, soft, 0.0 if soft else margin, True, True)
+        torch.cuda.synchronize()
+        reps = 500
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            _run(kind, e.detach(), pids, soft, 0.0 if soft else margin, True, True)
+        t.record()
+        torch.cuda.synchronize()
+        out[name] = 1e3 * s.elapsed_time(t) / reps
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- main arm
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import multimodal_similarity_b200 as mm
+    from multimodal_similarity_b200.retrieval import check_status, knn_raw
+    from multimodal_similarity_b200.sharded import ShardedGallery, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback -- use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mm.load()
+
+    Q, G, D, k = a.queries, a.gallery, a.dim, a.k
+    lo, hi = shard_bounds(G, world, rank)
+    # identical synthetic data on every rank (seeded); each rank keeps its contiguous gallery block
+    gallery_full = synth_torch(G, D, WORKLOAD["clusters"], SEED, dev)
+    shard = gallery_full[lo:hi].clone()
+    del gallery_full
+    queries = synth_torch(Q, D, WORKLOAD["clusters"], SEED + 1, dev)
+    sg = ShardedGallery(shard, presharded=True, row_offset=lo, total_rows=G)
+    torch.cuda.synchronize()
+
+    statuses = []
+
+    def step():
+        if world == 1:
+            d_, i_, st = knn_raw(queries, sg.shard, k)
+            statuses.append(st)
+            return d_, i_
+        return sg.retrieve(queries, k, check=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s.record()
+        for _ in range(steps):
+            out = fn()
+        t.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(t)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), out
+
+    for _ in range(a.warmup):
+        step()
+    with ClockSampler(local) as clk:
+        ms, (out_d, out_i) = timed(step, a.steps)
+    clocks = clk.summary()
+    fell_back = check_status(statuses[-1]) if statuses else 0
+    value = Q * a.steps / (ms / 1e3)
+
+    # ---- e2e: pinned host buffers in, host result out, every step
+    q_host = queries.cpu().pin_memory()
+    g_host = sg.shard.cpu().pin_memory()
+    res_d = torch.empty((Q, k), dtype=torch.float32).pin_memory()
+    res_i = torch.empty((Q, k), dtype=out_i.dtype).pin_memory()
+
+    def step_e2e():
+        qd = q_host.to(dev, non_blocking=True)
+        gd = g_host.to(dev, non_blocking=True)
+        if world == 1:
+            d_, i_, st = knn_raw(qd, gd, k)
+        else:
+            d_, i_ = ShardedGallery(gd, presharded=True, row_offset=lo, total_rows=G).retrieve(qd, k, check=False)
+        res_d.copy_(d_, non_blocking=True)
+        res_i.copy_(i_, non_blocking=True)
+        return d_, i_
+
+    for _ in range(2):
+        step_e2e()
+    e2e_steps = max(3, min(a.steps, 10))
+    ms_e2e, _ = timed(step_e2e, e2e_steps)
+    e2e = {"value": Q * e2e_steps / (ms_e2e / 1e3), "unit": "queries/s",
+           "h2d_bytes_per_step": int((q_host.numel() + g_host.numel()) * 4),
+           "d2h_bytes_per_step": int(res_d.numel() * 4 + res_i.numel() * res_i.element_size()),
+           "ms_per_step": ms_e2e / e2e_steps}
+
+    # ---- roofline of the dominant kernel (knn_tc_kernel), timed alone on its stream via the phase mask
+    d0, i0, st0 = knn_raw(queries, sg.shard, k)          # leaves a consistent workspace behind
+    outbuf = (d0, i0, st0)
+    for _ in range(2):
+        knn_raw(queries, sg.shard, k, phases=2, out=outbuf)
+    tc_reps = max(3, min(a.steps, 10))
+    ms_tc, _ = timed(lambda: knn_raw(queries, sg.shard, k, phases=2, out=outbuf), tc_reps)
+    ms_tc /= tc_reps
+    phase_ms = {}
+    for name, mask in (("prep", 1), ("rerank", 4), ("fallback", 8)):
+        m_, _ = timed(lambda: knn_raw(queries, sg.shard, k, phases=mask, out=outbuf), 3)
+        phase_ms[name] = m_ / 3
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    flops = 2.0 * Q * (hi - lo) * D
+    achieved = flops / (ms_tc / 1e3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "knn_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
+                "kernel_ms": ms_tc, "other_kernels_ms": phase_ms,
+                "algorithmic_flops_per_launch": flops}
+
+    result = {
+        "metric": "knn_queries_per_s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16 tensor-core filter + f32 exact re-rank", "data": "synthetic", "config": config_of(a, world),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": (6 if world == 1 else 7) * a.steps, "roofline": roofline,
+        "exact_fallback_queries": fell_back,
+    }
+
+    if rank == 0 and world == 1 and not a.no_extras:
+        try:
+            result.update(time_losses(torch, mm))
+        except Exception as e:  # noqa: BLE001
+            result["loss_timing_error"] = repr(e)
+        # CPU baseline: bounded sample of the same workload on this box's host cores (single NumPy thread, like the reference)
+        g_np = g_host.numpy()
+        q_np = q_host.numpy()
+        n_s = 12
+        cpu_queries_per_s(q_np, g_np, 2, 1)
+        v, dt = cpu_queries_per_s(q_np, g_np, n_s, 1)
+        result["cpu_baseline"] = {"value": v, "unit": "queries/s", "cores": 1, "kind": "port",
+                                  "sample": f"{n_s} of {Q} queries against the full {G} x {D} gallery, 1 NumPy thread of "
+                                            f"{os.cpu_count()} cores ({dt:.1f} s); oracle port of utils.retrieve_one"}
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

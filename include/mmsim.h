@@ -84,6 +84,17 @@ MMSIM_API int mmsim_knn_f32(const float* Q, int64_t nq, const float* G, int64_t 
                   int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
                   mmsim_stream_t stream);
 
+/* Measurement hook: the same call restricted to some of its phases, so each kernel can be timed alone with CUDA
+ * events on the caller's stream (bench.py, profiles/).  phases is a mask of MMSIM_KNN_PHASE_*; the workspace must
+ * hold the state of the earlier phases of a previous call with identical arguments. */
+#define MMSIM_KNN_PHASE_PREP 1     /* fp32 -> fp16 operand copies, norms, rounding-error norms */
+#define MMSIM_KNN_PHASE_TENSOR 2   /* fused tcgen05 distance + candidate selection */
+#define MMSIM_KNN_PHASE_RERANK 4   /* exact fp32 re-rank + certificate */
+#define MMSIM_KNN_PHASE_FALLBACK 8 /* exact recomputation of uncertified queries */
+MMSIM_API int mmsim_knn_f32_phases(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
+                         int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
+                         mmsim_stream_t stream, int phases);
+
 /* Merge `parts` shard-local results (as produced by mmsim_knn_f32 on each gallery shard and gathered with one
  * NCCL all-gather) into the global top-k ordered by (distance, global index).  Part p's [nq][k] block starts at
  * dist_parts + p * part_stride (same for idx_parts; part_stride in elements, >= nq*k, so a packed

@@ -24,6 +24,8 @@ SIGNATURES = {
     "mmsim_knn_workspace_bytes": (c_int, [c_int64, c_int64, c_int64, c_int, POINTER(c_size_t)]),
     "mmsim_knn_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int64,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mmsim_knn_f32_phases": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int64,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
     "mmsim_evaluate_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_double, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmsim_knn_merge": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

@@ -69,6 +69,14 @@ MMSIM_API int mmsim_knn_f32(const float* Q, int64_t nq, const float* G, int64_t 
                   reinterpret_cast<cudaStream_t>(stream));
 }
 
+MMSIM_API int mmsim_knn_f32_phases(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
+                         int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
+                         mmsim_stream_t stream, int phases) {
+  MMSIM_REQUIRE(phases > 0 && phases <= knn::kPhaseAll, MMSIM_ERR_ARG, "knn_phases: phases must be a mask in 1..15");
+  return knn::run(Q, nq, G, ng, D, k, exclude_self, self_offset, out_dist, out_idx, status, ws, ws_bytes,
+                  reinterpret_cast<cudaStream_t>(stream), phases);
+}
+
 MMSIM_API int mmsim_knn_merge(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride, const int64_t* idx_base,
                     int parts, int64_t nq, int k, float* out_dist, int64_t* out_idx, mmsim_stream_t stream) {
   return merge::run(dist_parts, idx_parts, part_stride, idx_base, parts, nq, k, out_dist, out_idx,

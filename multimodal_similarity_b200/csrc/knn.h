@@ -22,8 +22,10 @@ struct Plan {
 
 Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms);
 
+enum : int { kPhasePrep = 1, kPhaseTensor = 2, kPhaseRerank = 4, kPhaseFallback = 8, kPhaseAll = 15 };
+
 int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
-        float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream);
+        float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream, int phases = kPhaseAll);
 
 }  // namespace knn
 }  // namespace mmsim

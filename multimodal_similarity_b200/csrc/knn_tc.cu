@@ -604,7 +604,7 @@ static int launch_tc(const Plan& p, const CUtensorMap& tq, const CUtensorMap& tg
 }
 
 int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
-        float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream) {
+        float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream, int phases) {
   MMSIM_REQUIRE(Q && G && out_dist && out_idx && status && ws, MMSIM_ERR_ARG, "knn: null pointer argument");
   MMSIM_REQUIRE(nq > 0 && ng > 0 && D > 0, MMSIM_ERR_ARG, "knn: empty input (nq=%lld ng=%lld D=%lld)", (long long)nq,
                 (long long)ng, (long long)D);
@@ -635,12 +635,14 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   float* fb_dist = reinterpret_cast<float*>(w + p.off_fb_dist);
   int* fb_idx = reinterpret_cast<int*>(w + p.off_fb_idx);
 
-  MMSIM_CUDA_CHECK(cudaMemsetAsync(status, 0, 8 * sizeof(int), stream));
-  MMSIM_CUDA_CHECK(cudaMemsetAsync(gstats, 0, 64, stream));
-  MMSIM_CUDA_CHECK(cudaMemsetAsync(fb_count, 0, size_t(p.unc_cap) * 4, stream));
+  if (phases & kPhaseRerank) {
+    MMSIM_CUDA_CHECK(cudaMemsetAsync(status, 0, 8 * sizeof(int), stream));
+    MMSIM_CUDA_CHECK(cudaMemsetAsync(fb_count, 0, size_t(p.unc_cap) * 4, stream));
+  }
 
   // 1. operand copies
-  {
+  if (phases & kPhasePrep) {
+    MMSIM_CUDA_CHECK(cudaMemsetAsync(gstats, 0, 64, stream));
     const int threads = 256;
     const int64_t g_pad = int64_t(p.n_tiles) * BN;
     const int64_t gb = (g_pad * 32 + threads - 1) / threads;
@@ -653,8 +655,10 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   }
 
   // 2. fused distance + candidate selection
+  int rc = MMSIM_OK;
+  if (phases & kPhaseTensor) {
   CUtensorMap tq, tg;
-  int rc = make_tmap(&tq, qh, nq, p.Dp, BM);
+  rc = make_tmap(&tq, qh, nq, p.Dp, BM);
   if (rc) return rc;
   rc = make_tmap(&tg, gh, ng, p.Dp, BN);
   if (rc) return rc;
@@ -665,10 +669,11 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     default: rc = launch_tc<4>(p, tq, tg, gnorm, int(nq), cand_key, cand_idx, stream); break;
   }
   if (rc) return rc;
+  }
 
   // 3. exact re-rank + certificate.  delta bounds the fp32 accumulation error of key = |g|^2 - 2 q.g:
   //    (Dp + 8) roundings of relative size 2^-24, on terms bounded by (|q|^2 + |g|^2), with a 4x safety factor.
-  {
+  if (phases & kPhaseRerank) {
     const float delta_coeff = 4.0f * float(p.Dp + 8) * 5.9604645e-8f;
     const int blocks = int((nq + RR_WARPS - 1) / RR_WARPS);
     const size_t smem = size_t(RR_WARPS) * (size_t(D) + 2 * KP) * 4;
@@ -680,7 +685,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   }
 
   // 4. exact fallback for uncertified queries (no-op when status[0] == 0; the count lives on the device)
-  {
+  if (phases & kPhaseFallback) {
     dim3 grid(64, 16);
     knn_fallback_collect_kernel<<<grid, 256, size_t(D) * 4, stream>>>(Q, G, ng, int(D), exclude_self, self_offset, status,
                                                                       unc_query, unc_bound, p.unc_cap, fb_count, fb_dist,

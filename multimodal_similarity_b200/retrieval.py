@@ -27,7 +27,8 @@ def late_fusion(*modalities):
     return torch.cat([to_cuda_f32(m, dev) for m in modalities], dim=1)
 
 
-def knn_raw(q: torch.Tensor, g: torch.Tensor, k: int, exclude_self: bool = False, self_offset: int = 0):
+def knn_raw(q: torch.Tensor, g: torch.Tensor, k: int, exclude_self: bool = False, self_offset: int = 0, *, phases: int = 15,
+            out=None):
     """Low-level call: CUDA float32 tensors in, (dist [Q,k] f32, idx [Q,k] i32 shard-local, status [8] i32) out.
     Asynchronous on the current stream; ``status`` is checked by the callers that hand results to the user."""
     lib = _lib.load()
@@ -41,13 +42,16 @@ def knn_raw(q: torch.Tensor, g: torch.Tensor, k: int, exclude_self: bool = False
     nbytes = ctypes.c_size_t()
     _lib.check(lib.mmsim_knn_workspace_bytes(nq, ng, d, k, ctypes.byref(nbytes)), "mmsim_knn_workspace_bytes")
     ws = workspace("knn", nbytes.value, dev)
-    dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    idx = torch.empty((nq, k), dtype=torch.int32, device=dev)
-    status = torch.empty(8, dtype=torch.int32, device=dev)
+    if out is None:
+        dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        status = torch.empty(8, dtype=torch.int32, device=dev)
+    else:
+        dist, idx, status = out
     with torch.cuda.device(dev):
-        rc = lib.mmsim_knn_f32(q.data_ptr(), nq, g.data_ptr(), ng, d, k, int(bool(exclude_self)), int(self_offset),
-                               dist.data_ptr(), idx.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(),
-                               stream_handle(dev))
+        rc = lib.mmsim_knn_f32_phases(q.data_ptr(), nq, g.data_ptr(), ng, d, k, int(bool(exclude_self)), int(self_offset),
+                                      dist.data_ptr(), idx.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(),
+                                      stream_handle(dev), int(phases))
     _lib.check(rc, "mmsim_knn_f32")
     return dist, idx, status
 

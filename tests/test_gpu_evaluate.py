@@ -38,15 +38,22 @@ def test_evaluate_switches_golden():
 def test_evaluate_vs_oracle(n, d, c, bg, alpha, rs):
     import multimodal_similarity_b200 as mm
     x, lab = clustered(rs, n, d, c, background=bg)
-    x[7] = x[3]                                            # duplicate rows: exact ties in distance and in score
     for aligned in (False, True):
         ref = O.evaluate(x, lab, alpha=alpha, aligned=aligned)
         got = mm.evaluate(x, lab, alpha=alpha, aligned=aligned)
-        assert got[0] == pytest.approx(ref[0], abs=1e-12) and got[2] == pytest.approx(ref[2], abs=1e-9)
+        assert got[0] == pytest.approx(ref[0], abs=1e-12) and got[2] == pytest.approx(ref[2], abs=1e-12)
         assert got[1].keys() == ref[1].keys()
-        assert np.allclose(got[3]["confusion_matrix"], ref[3]["confusion_matrix"], atol=1e-6)
+        assert np.array_equal(got[3]["confusion_matrix"], ref[3]["confusion_matrix"])
         assert np.array_equal(got[4], ref[4])
-        assert np.allclose(got[5], ref[5], atol=1.5 / n)   # a tie at the K boundary may flip one query
+        assert got[5] == ref[5]
+    # exact duplicates: distance / score ties.  AP groups ties into one threshold so it is order independent; the
+    # rank-based metrics depend on the reference's unstable argsort inside a tie and are not compared here.
+    x[7] = x[3]
+    x[11] = x[3]
+    ref = O.evaluate(x, lab, alpha=alpha)
+    got = mm.evaluate(x, lab, alpha=alpha)
+    assert got[0] == pytest.approx(ref[0], abs=1e-12)
+    assert np.allclose([got[1][k] for k in sorted(got[1])], [ref[1][k] for k in sorted(ref[1])], atol=1e-12)
 
 
 def test_full_ranking_matches_reference_argsort(rs):
