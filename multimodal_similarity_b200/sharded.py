@@ -91,8 +91,10 @@ class ShardedGallery:
         k = int(k)
         packed, status = self._local(q, k, exclude_self, self_offset)
         if self.world > 1:
-            gathered = torch.empty((self.world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
-            dist.all_gather_into_tensor(gathered, packed, group=self.group)
+            # dim-0 concatenation layout (accepted by both NCCL and gloo), viewed as [world, 2, Q, k] afterwards
+            flat = torch.empty((self.world * 2,) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
+            dist.all_gather_into_tensor(flat, packed, group=self.group)
+            gathered = flat.view((self.world,) + tuple(packed.shape))
         else:
             gathered = packed.unsqueeze(0)
         per = -(-self.total // self.world)
