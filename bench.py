@@ -300,7 +300,7 @@ def main():
     ms_tc, _ = timed(lambda: knn_raw(queries, sg.shard, k, phases=2, out=outbuf), tc_reps)
     ms_tc /= tc_reps
     phase_ms = {}
-    for name, mask in (("prep", 1), ("rerank", 4), ("fallback", 8)):
+    for name, mask in (("prep", 1), ("pivot_prepass", 16), ("select_rerank", 4), ("fallback", 8)):
         m_, _ = timed(lambda: knn_raw(queries, sg.shard, k, phases=mask, out=outbuf), 3)
         phase_ms[name] = m_ / 3
     peaks = {}
@@ -321,7 +321,7 @@ def main():
         "metric": "knn_queries_per_s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f16 tensor-core filter + f32 exact re-rank", "data": "synthetic", "config": config_of(a, world),
-        "clocks": clocks, "e2e": e2e, "gpu_launches": (6 if world == 1 else 7) * a.steps, "roofline": roofline,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": (8 if world == 1 else 9) * a.steps, "roofline": roofline,
         "exact_fallback_queries": fell_back,
     }
 

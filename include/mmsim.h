@@ -88,9 +88,11 @@ MMSIM_API int mmsim_knn_f32(const float* Q, int64_t nq, const float* G, int64_t 
  * events on the caller's stream (bench.py, profiles/).  phases is a mask of MMSIM_KNN_PHASE_*; the workspace must
  * hold the state of the earlier phases of a previous call with identical arguments. */
 #define MMSIM_KNN_PHASE_PREP 1     /* fp32 -> fp16 operand copies, norms, rounding-error norms */
-#define MMSIM_KNN_PHASE_TENSOR 2   /* fused tcgen05 distance + candidate selection */
-#define MMSIM_KNN_PHASE_RERANK 4   /* exact fp32 re-rank + certificate */
+#define MMSIM_KNN_PHASE_TENSOR 2   /* fused tcgen05 distance + candidate sweep (the dominant kernel) */
+#define MMSIM_KNN_PHASE_RERANK 4   /* candidate selection, exact fp32 re-rank, certificate */
 #define MMSIM_KNN_PHASE_FALLBACK 8 /* exact recomputation of uncertified queries */
+#define MMSIM_KNN_PHASE_PIVOT 16   /* tcgen05 pre-pass over a gallery sample: per-query threshold ladder */
+#define MMSIM_KNN_PHASE_ALL 31
 MMSIM_API int mmsim_knn_f32_phases(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
                          int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
                          mmsim_stream_t stream, int phases);

@@ -72,7 +72,7 @@ MMSIM_API int mmsim_knn_f32(const float* Q, int64_t nq, const float* G, int64_t 
 MMSIM_API int mmsim_knn_f32_phases(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
                          int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
                          mmsim_stream_t stream, int phases) {
-  MMSIM_REQUIRE(phases > 0 && phases <= knn::kPhaseAll, MMSIM_ERR_ARG, "knn_phases: phases must be a mask in 1..15");
+  MMSIM_REQUIRE(phases > 0 && phases <= knn::kPhaseAll, MMSIM_ERR_ARG, "knn_phases: phases must be a mask in 1..31");
   return knn::run(Q, nq, G, ng, D, k, exclude_self, self_offset, out_dist, out_idx, status, ws, ws_bytes,
                   reinterpret_cast<cudaStream_t>(stream), phases);
 }

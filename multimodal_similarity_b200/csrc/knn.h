@@ -7,7 +7,7 @@
 namespace mmsim {
 namespace knn {
 
-constexpr int KP = 128;  // approximate candidates kept per (query, gallery split); k <= KP - 16
+constexpr int KP = 128;  // approximate candidates re-ranked exactly per query; k <= KP - 16
 
 // Launch geometry + workspace layout of one mmsim_knn_f32 call (pure function of the problem size).
 struct Plan {
@@ -15,14 +15,15 @@ struct Plan {
   int n_qblocks, n_tiles;     // 128-query blocks, 256-row gallery tiles
   int n_splits, tiles_per_split, grid;
   int unc_cap;                // max uncertified queries handled by the exact fallback
-  size_t off_qh, off_gh, off_gnorm, off_qnorm, off_qerr, off_stats, off_cand_key, off_cand_idx;
+  int logcap, use_pivots, n_sample_tiles, sample_cols, pivot_grid;   // candidate log / pivot pre-pass geometry
+  size_t off_qh, off_gh, off_gpack, off_qnorm, off_qerr, off_stats, off_pivots, off_log, off_log_cnt, off_log_tau;
   size_t off_unc_query, off_unc_bound, off_fb_count, off_fb_dist, off_fb_idx;
   size_t total_bytes;
 };
 
 Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms);
 
-enum : int { kPhasePrep = 1, kPhaseTensor = 2, kPhaseRerank = 4, kPhaseFallback = 8, kPhaseAll = 15 };
+enum : int { kPhasePrep = 1, kPhaseTensor = 2, kPhaseRerank = 4, kPhaseFallback = 8, kPhasePivot = 16, kPhaseAll = 31 };
 
 int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
         float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream, int phases = kPhaseAll);

@@ -28,16 +28,23 @@ namespace mmsim {
 namespace knn {
 
 // ------------------------------------------------------------------------------------------------ prep
-// One warp per row.  xh[row, 0..Dp) = fp16(x) * scale (zero padded), norm[row] = sum fp16(x)^2 (unscaled, fp32),
-// err[row] = ||x - fp16(x)||_2.  Rows in [n, n_pad) get norm = +inf (masks padded gallery columns).
+constexpr int BM = 128;                    // queries per CTA tile (UMMA M, one TMEM lane each)
+constexpr int BN = 256;                    // gallery rows per tile (UMMA N)
+constexpr int KATOM = 64;                  // fp16 elements per 128-byte swizzle atom
+constexpr int NPACK = 320;                 // floats per gallery tile in the norm pack: 256 norms | 32 min8 | 8 min32 | pad
+
+// One warp per row.  xh[row, 0..Dp) = fp16(x) * scale (zero padded), norm = sum fp16(x)^2 (unscaled, fp32),
+// err[row] = ||x - fp16(x)||_2.  With tile_pack != 0 (gallery) the norm goes to the per-tile pack
+// norm[(row / 256) * 320 + row % 256] and rows in [n, n_pad) get +inf (masks padded gallery columns).
 __global__ void prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int D, int Dp, float scale,
-                                 __half* __restrict__ xh, float* __restrict__ norm, float* __restrict__ err,
+                                 __half* __restrict__ xh, float* __restrict__ norm, float* __restrict__ err, int tile_pack,
                                  unsigned int* __restrict__ max_stats /* [0]=max err bits, [1]=max norm bits, or null */) {
   const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   if (row >= n_pad) return;
+  const int64_t nslot = tile_pack ? (row / BN) * NPACK + (row % BN) : row;
   if (row >= n) {
-    if (lane == 0) norm[row] = kInf;
+    if (lane == 0) norm[nslot] = kInf;
     return;
   }
   const float* xr = x + row * D;
@@ -61,7 +68,7 @@ __global__ void prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t
   if (lane == 0) {
     // inflate by a few ulps so the values are upper bounds despite fp32 summation error
     const float en = sqrtf(e) * 1.0001f;
-    norm[row] = s;
+    norm[nslot] = s;
     if (err) err[row] = en;
     if (max_stats) {
       atomicMax(&max_stats[0], __float_as_uint(en));
@@ -70,71 +77,99 @@ __global__ void prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t
   }
 }
 
+// One block per gallery tile: minima of the 256 norms over groups of 8 and of 32 columns (the epilogue's early-out bounds).
+__global__ void __launch_bounds__(BN) pack_min_kernel(float* __restrict__ pack) {
+  float* p = pack + size_t(blockIdx.x) * NPACK;
+  float v = p[threadIdx.x];
+  v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  if ((threadIdx.x & 7) == 0) p[BN + (threadIdx.x >> 3)] = v;
+  v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+  v = fminf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+  if ((threadIdx.x & 31) == 0) p[BN + 32 + (threadIdx.x >> 5)] = v;
+}
+
 // ------------------------------------------------------------------------------------------------ fused kernel
-constexpr int BM = 128;                    // queries per CTA tile (UMMA M, one TMEM lane each)
-constexpr int BN = 256;                    // gallery rows per tile (UMMA N)
-constexpr int KATOM = 64;                  // fp16 elements per 128-byte swizzle atom
 constexpr int NS = 4;                      // gallery smem stages (one K atom of one tile each)
+constexpr int NT = 4;                      // norm-pack ring slots
 constexpr int A_ATOM_BYTES = BM * 128;     // 16 KiB
 constexpr int B_STAGE_BYTES = BN * 128;    // 32 KiB
-constexpr int NUM_THREADS = 192;           // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-5: epilogue
+constexpr int NPIV = 16;                   // pivot pre-pass keeps the 16 smallest sampled keys per query
+constexpr int KPT = KP;                    // candidates that must lie below a pivot before it becomes the threshold
+
+enum { MODE_PIVOT = 0, MODE_SWEEP = 1 };
+
+struct SweepArgs {
+  const float* gpack;        // [n_tiles][NPACK]
+  int nq, n_qblocks, n_tiles;
+  // MODE_SWEEP: item = (split, query block); contiguous tile range per split
+  int n_splits, tiles_per_split;
+  int use_pivots;            // 0: threshold +inf (everything is logged; small galleries)
+  uint2* log;                // [(row * n_splits + split) * logcap] {key bits, gallery row}
+  int logcap;
+  int* log_cnt;              // [row * n_splits + split] entries appended (may exceed logcap: overflow)
+  float* log_tau;            // [row * n_splits + split] final threshold of the sweep
+  // MODE_PIVOT: item = query block; n_sample_tiles evenly spaced tiles, first sample_cols columns of each
+  int n_sample_tiles, sample_cols;
+  float* pivots;             // [row][4] = 2nd, 4th, 8th, 16th smallest sampled key
+};
 
 template <int KATOMS>
 struct Smem {
-  static constexpr int NT = 4;                       // norm ring slots, recycled through their own empty barriers
-  static constexpr int CB = KATOMS == 4 ? 24 : 32;   // candidate buffer entries per row
-  static constexpr int CBP = CB + 1;                 // padded pitch: conflict-free append and row read
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_OFF + KATOMS * A_ATOM_BYTES;
   static constexpr int NORM_OFF = B_OFF + NS * B_STAGE_BYTES;
-  static constexpr int CK_OFF = NORM_OFF + NT * BN * 4;
-  static constexpr int CI_OFF = CK_OFF + BM * CBP * 4;
-  static constexpr int BAR_OFF = CI_OFF + BM * CBP * 4;  // 8-byte aligned: all terms are multiples of 8? checked below
+  static constexpr int TAU_OFF = NORM_OFF + NT * NPACK * 4;   // float [BM]   current threshold of each row
+  static constexpr int CNT_OFF = TAU_OFF + BM * 4;            // int   [BM]   log cursor
+  static constexpr int CN_OFF = CNT_OFF + BM * 4;             // int   [BM][4] logged entries below pivot b
+  static constexpr int BAR_OFF = CN_OFF + BM * 16;
   static constexpr int NUM_BARS = 2 * NS + 2 + 2 + 2 + NT;
   static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
   static constexpr int TOTAL = TMEM_PTR_OFF + 8;
-  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment of the base
+  static constexpr int DYN_BYTES = TOTAL;
   static_assert(BAR_OFF % 8 == 0, "barriers must be 8-byte aligned");
   static_assert(DYN_BYTES <= 232448, "exceeds 227 KiB of shared memory");
 };
 
-// Merge the row's candidate buffer into its sorted KP-list (global, L2 resident); returns the new threshold
-// (the KP-th smallest key).  Executed by the whole warp for one row at a time.
-__device__ __noinline__ float flush_row(const float* __restrict__ bufk, const int* __restrict__ bufi, int n,
-                                        float* __restrict__ lk, int* __restrict__ li, uint32_t lane) {
-  float xk[KP / 32];
-  int xv[KP / 32];
-#pragma unroll
-  for (int j = 0; j < KP / 32; ++j) {  // issue the list loads first, they are the long-latency part
-    xk[j] = lk[j * 32 + lane];
-    xv[j] = li[j * 32 + lane];
-  }
-  float yk = int(lane) < n ? bufk[lane] : kInf;
-  int yv = int(lane) < n ? bufi[lane] : -1;
-  warp_sort32(yk, yv, lane);
-#pragma unroll
-  for (int j = 0; j < KP / 32; ++j) {
-    warp_merge_split32(xk[j], xv[j], yk, yv, lane);
-    lk[j * 32 + lane] = xk[j];
-    li[j * 32 + lane] = xv[j];
-  }
-  return __shfl_sync(0xffffffffu, xk[KP / 32 - 1], 31);
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void epi_bar_sync(int nthreads) {  // named barrier 1: epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+template <int MODE>
+__device__ __forceinline__ int tile_of(const SweepArgs& a, int t0, int i) {
+  if (MODE == MODE_SWEEP) return t0 + i;
+  return int((int64_t(2 * i + 1) * a.n_tiles) / (2 * a.n_sample_tiles));
 }
 
-template <int KATOMS>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_g,
-              const float* __restrict__ gnorm, int nq, int n_qblocks, int n_splits, int tiles_per_split, int n_tiles,
-              float* __restrict__ cand_key, int* __restrict__ cand_idx) {
+template <int KATOMS, int NEPI, int MODE>
+__global__ void __launch_bounds__(64 + NEPI * 32, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_g, const SweepArgs a) {
   using S = Smem<KATOMS>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NH = NEPI / 4;            // epilogue warps per TMEM lane quarter; each takes every NH-th 32-column chunk
+  constexpr int EPI_THREADS = NEPI * 32;
+  // No static shared memory in this kernel, so the dynamic window starts at the CTA's shared base and the declared
+  // alignment holds (checked below); keeping the pointer un-rounded lets the compiler emit LDS/STS/ATOMS.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
 
   uint8_t* smem_a = smem + S::A_OFF;
   uint8_t* smem_b = smem + S::B_OFF;
   float* norm_ring = reinterpret_cast<float*>(smem + S::NORM_OFF);
-  float* bufk = reinterpret_cast<float*>(smem + S::CK_OFF);
-  int* bufi = reinterpret_cast<int*>(smem + S::CI_OFF);
+  float* s_tau = reinterpret_cast<float*>(smem + S::TAU_OFF);
+  int* s_cnt = reinterpret_cast<int*>(smem + S::CNT_OFF);
+  int* s_cn = reinterpret_cast<int*>(smem + S::CN_OFF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* full = bars;                 // [NS]  TMA -> MMA
   uint64_t* empty = bars + NS;           // [NS]  MMA -> TMA
@@ -142,7 +177,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   uint64_t* tempty = bars + 2 * NS + 2;  // [2]   epilogue -> MMA (accumulator drained)
   uint64_t* afull = bars + 2 * NS + 4;   //       query tile landed
   uint64_t* aempty = bars + 2 * NS + 5;  //       all MMAs of the item done, query tile may be overwritten
-  uint64_t* nempty = bars + 2 * NS + 6;  // [NT]  epilogue finished a tile: its norm slot may be refilled
+  uint64_t* nempty = bars + 2 * NS + 6;  // [NT]  epilogue finished a tile: its norm-pack slot may be refilled
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::TMEM_PTR_OFF);
 
   const uint32_t warp = threadIdx.x >> 5;
@@ -157,11 +192,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull[i], 1);
-      ptx::mbar_init(&tempty[i], BM);
+      ptx::mbar_init(&tempty[i], EPI_THREADS);
     }
     ptx::mbar_init(afull, 1);
     ptx::mbar_init(aempty, 1);
-    for (int i = 0; i < S::NT; ++i) ptx::mbar_init(&nempty[i], BM);
+    for (int i = 0; i < NT; ++i) ptx::mbar_init(&nempty[i], EPI_THREADS);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_ptr, 2 * BN);  // 512 columns: two 128x256 fp32 accumulators
@@ -170,30 +205,40 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int n_items = n_qblocks * n_splits;
+  const int n_items = MODE == MODE_SWEEP ? a.n_qblocks * a.n_splits : a.n_qblocks;
+  auto item_range = [&](int item, int& qb, int& split, int& t0, int& nt) {
+    if (MODE == MODE_SWEEP) {
+      split = item / a.n_qblocks;
+      qb = item - split * a.n_qblocks;
+      t0 = split * a.tiles_per_split;
+      nt = min(a.n_tiles, t0 + a.tiles_per_split) - t0;
+    } else {
+      split = 0; qb = item; t0 = 0; nt = a.n_sample_tiles;
+    }
+  };
 
   if (warp == 0) {
     // =============================================================== TMA producer (one thread)
     if (lane == 0) {
       uint32_t it = 0, tc = 0, ic = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
-        const int split = item / n_qblocks, qb = item - split * n_qblocks;
-        const int t0 = split * tiles_per_split;
-        const int t1 = min(n_tiles, t0 + tiles_per_split);
+        int qb, split, t0, nt;
+        item_range(item, qb, split, t0, nt);
         ptx::mbar_wait(aempty, (ic & 1) ^ 1);
         ptx::mbar_expect_tx(afull, KATOMS * A_ATOM_BYTES);
         for (int ka = 0; ka < KATOMS; ++ka)
           ptx::tma_load_2d(smem_a + ka * A_ATOM_BYTES, &tm_q, ka * KATOM, qb * BM, afull);
-        for (int t = t0; t < t1; ++t, ++tc) {
+        for (int i = 0; i < nt; ++i, ++tc) {
+          const int t = tile_of<MODE>(a, t0, i);
           for (int ka = 0; ka < KATOMS; ++ka, ++it) {
             const uint32_t stage = it % NS, phase = (it / NS) & 1;
             ptx::mbar_wait(&empty[stage], phase ^ 1);
-            ptx::mbar_expect_tx(&full[stage], B_STAGE_BYTES + (ka == 0 ? BN * 4 : 0));
+            ptx::mbar_expect_tx(&full[stage], B_STAGE_BYTES + (ka == 0 ? NPACK * 4 : 0));
             ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tm_g, ka * KATOM, t * BN, &full[stage]);
             if (ka == 0) {
               // the epilogue reads this tile's norms long after it released the accumulator: separate hand-back
-              ptx::mbar_wait(&nempty[tc % S::NT], ((tc / S::NT) & 1) ^ 1);
-              ptx::bulk_load_1d(norm_ring + (tc % S::NT) * BN, gnorm + size_t(t) * BN, BN * 4, &full[stage]);
+              ptx::mbar_wait(&nempty[tc % NT], ((tc / NT) & 1) ^ 1);
+              ptx::bulk_load_1d(norm_ring + (tc % NT) * NPACK, a.gpack + size_t(t) * NPACK, NPACK * 4, &full[stage]);
             }
           }
         }
@@ -206,12 +251,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     const uint64_t bdesc0 = ptx::umma_desc_k128(ptx::smem_u32(smem_b));
     uint32_t it = 0, tc = 0, ic = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
-      const int split = item / n_qblocks;
-      const int t0 = split * tiles_per_split;
-      const int t1 = min(n_tiles, t0 + tiles_per_split);
+      int qb, split, t0, nt;
+      item_range(item, qb, split, t0, nt);
       ptx::mbar_wait(afull, ic & 1);
       ptx::tc_fence_after();
-      for (int t = t0; t < t1; ++t, ++tc) {
+      for (int i = 0; i < nt; ++i, ++tc) {
         const uint32_t as = tc & 1;
         ptx::mbar_wait(&tempty[as], ((tc >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
@@ -226,8 +270,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
               const uint64_t bd = bdesc0 + uint64_t(stage * (B_STAGE_BYTES >> 4) + k * 2);
               ptx::umma_f16(tmem_base + as * BN, ad, bd, idesc, (ka | k) != 0);
             }
-            ptx::umma_commit(&empty[stage]);              // smem stage reusable once these MMAs retire
-            if (ka == KATOMS - 1) ptx::umma_commit(&tfull[as]);  // accumulator complete
+            ptx::umma_commit(&empty[stage]);                      // smem stage reusable once these MMAs retire
+            if (ka == KATOMS - 1) ptx::umma_commit(&tfull[as]);   // accumulator complete
           }
           __syncwarp();
         }
@@ -236,91 +280,131 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       __syncwarp();
     }
   } else {
-    // =============================================================== epilogue: TMEM -> threshold-gated top-KP
+    // =============================================================== epilogue warps: TMEM -> candidates
     const uint32_t q = warp & 3;              // TMEM lane quarter this warp may read
+    const uint32_t h = (warp - 2) >> 2;       // which of the NH warps of this quarter
     const int row = q * 32 + lane;            // row of the CTA tile == TMEM lane
-    float* my_bk = bufk + row * S::CBP;
-    int* my_bi = bufi + row * S::CBP;
+    const uint32_t ring_u32 = ptx::smem_u32(norm_ring);
     uint32_t tc = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int split = item / n_qblocks, qb = item - split * n_qblocks;
-      const int t0 = split * tiles_per_split;
-      const int t1 = min(n_tiles, t0 + tiles_per_split);
-      // candidate lists of this warp's 32 rows: [(qb*128 + q*32 + r) * n_splits + split][KP]
-      const size_t list0 = (size_t(qb * BM + q * 32) * n_splits + split) * KP;
-      const size_t list_stride = size_t(n_splits) * KP;
-      for (int r = 0; r < 32; ++r) {
+      int qb, split, t0, nt;
+      item_range(item, qb, split, t0, nt);
+      const int grow = qb * BM + row;          // global query row (may be >= nq in the last block)
+      const bool valid = grow < a.nq;
+
+      float piv0 = -kInf, piv1 = -kInf, piv2 = -kInf;   // MODE_SWEEP: ladder below the initial threshold
+      float pv[NPIV];                                   // MODE_PIVOT: sorted ascending, the NPIV smallest keys so far
+      uint2* mylog = nullptr;
+      if (MODE == MODE_SWEEP) {
+        float tau0 = kInf;
+        if (a.use_pivots) {
+          const float4 pp = *reinterpret_cast<const float4*>(a.pivots + size_t(grow) * 4);
+          piv0 = pp.x; piv1 = pp.y; piv2 = pp.z; tau0 = pp.w;
+        }
+        epi_bar_sync(EPI_THREADS);             // every epilogue warp is done with the previous item
+        if (h == 0) {
+          s_tau[row] = valid ? tau0 : -kInf;   // rows past the last query never accept a candidate
+          s_cnt[row] = 0;
+          *reinterpret_cast<int4*>(s_cn + row * 4) = make_int4(0, 0, 0, 0);
+        }
+        epi_bar_sync(EPI_THREADS);
+        mylog = a.log + (size_t(grow) * a.n_splits + split) * a.logcap;
+      } else {
 #pragma unroll
-        for (int j = 0; j < KP / 32; ++j) {
-          cand_key[list0 + r * list_stride + j * 32 + lane] = kInf;
-          cand_idx[list0 + r * list_stride + j * 32 + lane] = -1;
-        }
+        for (int i = 0; i < NPIV; ++i) pv[i] = valid ? kInf : -kInf;
       }
-      __syncwarp();
-      float thr = (qb * BM + row < nq) ? kInf : -kInf;   // rows past the last query never accept a candidate
-      int cnt = 0;
 
-      auto flush_rows = [&](uint32_t need) {
-        while (need) {
-          const int r = __ffs(need) - 1;
-          need &= need - 1;
-          const int n = __shfl_sync(0xffffffffu, cnt, r);
-          __syncwarp();
-          const float nt = flush_row(bufk + (q * 32 + r) * S::CBP, bufi + (q * 32 + r) * S::CBP, n,
-                                     cand_key + list0 + r * list_stride, cand_idx + list0 + r * list_stride, lane);
-          if (int(lane) == r) {
-            thr = nt;
-            cnt = 0;
-          }
-        }
-      };
-
-      for (int t = t0; t < t1; ++t, ++tc) {
+      for (int i = 0; i < nt; ++i, ++tc) {
+        const int t = tile_of<MODE>(a, t0, i);
         const uint32_t as = tc & 1;
         ptx::mbar_wait(&tfull[as], (tc >> 1) & 1);
         ptx::tc_fence_after();
-        const float* nrm = norm_ring + (tc % S::NT) * BN;
+        const uint32_t nrm = ring_u32 + (tc % NT) * NPACK * 4;
         const uint32_t taddr = tmem_base + ((q * 32) << 16) + as * BN;
         const int col0 = t * BN;
+        const int nchunks = MODE == MODE_PIVOT ? a.sample_cols / 32 : BN / 32;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = h; c < BN / 32; c += NH) {
           float v[32];
           ptx::tmem_ld32(taddr + c * 32, v);
           ptx::tmem_ld_wait(v);
-          if (c == BN / 32 - 1) {  // accumulator fully copied to registers: hand the TMEM stage back to the MMA warp
+          if (c + NH >= BN / 32) {  // this warp's last chunk of the tile is in registers: hand its share of TMEM back
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[as]);
           }
+          if (c >= nchunks) continue;
+          // early out on the raw accumulator: key_j = acc_j + |g_j|^2 >= acc_j + (min |g|^2 over the chunk)
+          const float tau = MODE == MODE_SWEEP ? s_tau[row] : pv[NPIV - 1];
+          float gm[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            gm[g] = min3(min3(v[g * 8], v[g * 8 + 1], v[g * 8 + 2]), min3(v[g * 8 + 3], v[g * 8 + 4], v[g * 8 + 5]),
+                         fminf(v[g * 8 + 6], v[g * 8 + 7]));
+          const float m = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
+          const float nmin32 = lds_f32(nrm + (BN + 32 + c) * 4);
+          if (!__any_sync(0xffffffffu, m < tau - nmin32)) continue;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const float4 n0 = *reinterpret_cast<const float4*>(nrm + c * 32 + g * 8);
-            const float4 n1 = *reinterpret_cast<const float4*>(nrm + c * 32 + g * 8 + 4);
+            const float nmin8 = lds_f32(nrm + (BN + c * 4 + g) * 4);
+            if (!__any_sync(0xffffffffu, gm[g] < tau - nmin8)) continue;
+            const float4 n0 = lds_f32x4(nrm + (c * 32 + g * 8) * 4);
+            const float4 n1 = lds_f32x4(nrm + (c * 32 + g * 8 + 4) * 4);
             float key[8];
             // the query operand was pre-scaled by -2, so acc = -2 q.g and key = |g|^2 - 2 q.g
             key[0] = v[g * 8 + 0] + n0.x; key[1] = v[g * 8 + 1] + n0.y;
             key[2] = v[g * 8 + 2] + n0.z; key[3] = v[g * 8 + 3] + n0.w;
             key[4] = v[g * 8 + 4] + n1.x; key[5] = v[g * 8 + 5] + n1.y;
             key[6] = v[g * 8 + 6] + n1.z; key[7] = v[g * 8 + 7] + n1.w;
-            const float m = fminf(fminf(fminf(key[0], key[1]), fminf(key[2], key[3])),
-                                  fminf(fminf(key[4], key[5]), fminf(key[6], key[7])));
-            if (__any_sync(0xffffffffu, m < thr)) {
-              flush_rows(__ballot_sync(0xffffffffu, cnt > S::CB - 8));
-              const int cbase = col0 + c * 32 + g * 8;
+            const int cbase = col0 + c * 32 + g * 8;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (key[j] < thr) {
-                  my_bk[cnt] = key[j];
-                  my_bi[cnt] = cbase + j;
-                  ++cnt;
+            for (int j = 0; j < 8; ++j) {
+              if (MODE == MODE_SWEEP) {
+                if (key[j] < tau) {
+                  const int slot = atomicAdd(&s_cnt[row], 1);
+                  if (slot < a.logcap) mylog[slot] = make_uint2(__float_as_uint(key[j]), uint32_t(cbase + j));
+                  if (key[j] < piv2) {
+                    atomicAdd(&s_cn[row * 4 + 2], 1);
+                    if (key[j] < piv1) {
+                      atomicAdd(&s_cn[row * 4 + 1], 1);
+                      if (key[j] < piv0) atomicAdd(&s_cn[row * 4 + 0], 1);
+                    }
+                  }
+                }
+              } else {
+                float x = key[j];
+                if (x < pv[NPIV - 1]) {   // sorted insertion network: x bubbles up, the old maximum falls out
+#pragma unroll
+                  for (int i2 = 0; i2 < NPIV; ++i2) {
+                    const float lo = fminf(pv[i2], x);
+                    x = fmaxf(pv[i2], x);
+                    pv[i2] = lo;
+                  }
                 }
               }
             }
           }
         }
-        ptx::mbar_arrive(&nempty[tc % S::NT]);
+        if (MODE == MODE_SWEEP && h == 0) {
+          // tighten: once KPT logged entries lie below a pivot, nothing at or above it can be among the KPT smallest
+          const int4 cn = *reinterpret_cast<const int4*>(s_cn + row * 4);
+          float nt_ = s_tau[row];
+          if (cn.z >= KPT) nt_ = fminf(nt_, piv2);
+          if (cn.y >= KPT) nt_ = fminf(nt_, piv1);
+          if (cn.x >= KPT) nt_ = fminf(nt_, piv0);
+          s_tau[row] = nt_;
+        }
+        ptx::mbar_arrive(&nempty[tc % NT]);
       }
-      __syncwarp();
-      flush_rows(__ballot_sync(0xffffffffu, cnt > 0));
+
+      if (MODE == MODE_SWEEP) {
+        epi_bar_sync(EPI_THREADS);             // all appends of this item are done
+        if (h == 0) {
+          a.log_cnt[size_t(grow) * a.n_splits + split] = s_cnt[row];
+          a.log_tau[size_t(grow) * a.n_splits + split] = s_tau[row];
+        }
+      } else {
+        *reinterpret_cast<float4*>(a.pivots + size_t(grow) * 4) = make_float4(pv[1], pv[3], pv[7], pv[15]);
+      }
     }
   }
 
@@ -330,54 +414,98 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------ rerank
-// One warp per query: merge the per-split candidate lists, recompute the KP candidates' distances exactly,
-// sort by (distance, index), emit top-k, certify.
+// One warp per query: pick the KP smallest approximate keys from the sweep's candidate log, recompute those
+// candidates' distances exactly, sort by (distance, index), emit top-k, certify.
 constexpr int RR_WARPS = 4;
+
+__device__ __forceinline__ uint32_t sortable(uint32_t fbits) { return (fbits & 0x80000000u) ? ~fbits : (fbits | 0x80000000u); }
+__device__ __forceinline__ float unsortable(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 
 __global__ void __launch_bounds__(RR_WARPS * 32)
 knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int nq, int64_t ng, int D,
-                  const float* __restrict__ cand_key, const int* __restrict__ cand_idx, int n_splits,
-                  const float* __restrict__ qnorm, const float* __restrict__ qerr, const float* __restrict__ gstats,
-                  float delta_coeff, int k, int exclude_self, int64_t self_offset,
+                  const uint2* __restrict__ log, int logcap, const int* __restrict__ log_cnt, const float* __restrict__ log_tau,
+                  int n_splits, const float* __restrict__ qnorm, const float* __restrict__ qerr,
+                  const float* __restrict__ gstats, float delta_coeff, int k, int exclude_self, int64_t self_offset,
                   float* __restrict__ out_dist, int* __restrict__ out_idx,
                   int* __restrict__ status, int* __restrict__ unc_query, float* __restrict__ unc_bound, int unc_cap) {
   extern __shared__ float rr_smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qi = blockIdx.x * RR_WARPS + warp;
   if (qi >= nq) return;
-  float* qs = rr_smem + warp * (D + 2 * KP);      // query vector, then sort scratch
+  float* qs = rr_smem + warp * (D + 2 * KP);      // query vector, then candidate / sort scratch
   float* sk = qs + D;
   int* sv = reinterpret_cast<int*>(sk + KP);
 
   for (int c = lane; c < D; c += 32) qs[c] = Q[size_t(qi) * D + c];
+  for (int c = lane; c < KP; c += 32) { sk[c] = kInf; sv[c] = -1; }
 
-  // ---- merge split lists by approximate key
-  const size_t base = size_t(qi) * n_splits * KP;
-  float xk[KP / 32];
-  int xv[KP / 32];
-#pragma unroll
-  for (int j = 0; j < KP / 32; ++j) {
-    xk[j] = cand_key[base + j * 32 + lane];
-    xv[j] = cand_idx[base + j * 32 + lane];
+  // ---- gather the KP smallest logged keys (all of them when there are fewer)
+  const size_t l0 = size_t(qi) * n_splits;
+  int total = 0;
+  bool overflow = false;
+  float tau_min = kInf;
+  for (int s = 0; s < n_splits; ++s) {
+    const int c = log_cnt[l0 + s];
+    overflow |= c > logcap;
+    total += min(c, logcap);
+    tau_min = fminf(tau_min, log_tau[l0 + s]);
   }
-  for (int s = 1; s < n_splits; ++s) {
-    for (int j2 = 0; j2 < KP / 32; ++j2) {
-      float yk = cand_key[base + size_t(s) * KP + j2 * 32 + lane];
-      int yv = cand_idx[base + size_t(s) * KP + j2 * 32 + lane];
-#pragma unroll
-      for (int j = 0; j < KP / 32; ++j) warp_merge_split32(xk[j], xv[j], yk, yv, lane);
+  uint32_t ustar = 0xffffffffu;   // KP-th smallest key in sortable-uint form
+  if (total > KP) {
+    // radix descent, one bit per pass: smallest value u with #{entries <= u} >= KP
+    uint32_t prefix = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t mid = prefix | ((1u << bit) - 1u);
+      int cnt = 0;
+      for (int s = 0; s < n_splits; ++s) {
+        const uint2* ls = log + (l0 + s) * logcap;
+        const int c = min(log_cnt[l0 + s], logcap);
+        for (int e = lane; e < c; e += 32) cnt += sortable(__ldg(&ls[e].x)) <= mid ? 1 : 0;
+      }
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt < KP) prefix |= (1u << bit);
+    }
+    ustar = prefix;
+  }
+  __syncwarp();
+  int filled = 0;
+  for (int pass = 0; pass < 2; ++pass) {        // pass 0: keys < u*, pass 1: keys == u* until KP slots are used
+    if (pass == 1 && total <= KP) break;
+    for (int s = 0; s < n_splits; ++s) {
+      const uint2* ls = log + (l0 + s) * logcap;
+      const int c = min(log_cnt[l0 + s], logcap);
+      for (int e0 = 0; e0 < c; e0 += 32) {
+        const int e = e0 + lane;
+        uint2 ent = make_uint2(0, 0);
+        bool take = false;
+        if (e < c) {
+          ent = __ldg(&ls[e]);
+          const uint32_t u = sortable(ent.x);
+          take = total <= KP ? true : (pass == 0 ? u < ustar : u == ustar);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, take);
+        const int pos = filled + __popc(bal & ((1u << lane) - 1u));
+        if (take && pos < KP) {
+          sk[pos] = __uint_as_float(ent.x);
+          sv[pos] = int(ent.y);
+        }
+        filled += __popc(bal);
+      }
     }
   }
-  const float tau = __shfl_sync(0xffffffffu, xk[KP / 32 - 1], 31);
   __syncwarp();
+  // every gallery row that is not a candidate has an approximate key >= tau (never logged: >= the sweep's final
+  // threshold; logged but not selected: >= the KP-th smallest logged key)
+  const float tau = total > KP ? fminf(tau_min, unsortable(ustar)) : tau_min;
 
   // ---- exact distances (reference arithmetic), one candidate per lane at a time
   const int self = exclude_self ? int(self_offset + qi) : -1;
 #pragma unroll
   for (int j = 0; j < KP / 32; ++j) {
-    const int idx = xv[j];
+    const int idx = sv[j * 32 + lane];
     float d = kInf;
     if (idx >= 0 && idx != self) d = exact_l2(qs, G + size_t(idx) * D, D);
+    __syncwarp();
     sk[j * 32 + lane] = d;
     sv[j * 32 + lane] = (idx >= 0 && idx != self) ? idx : 0x7fffffff;
   }
@@ -412,8 +540,10 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
   if (lane == 0) {
     const float dk = sk[k - 1];
     bool ok;
-    if (!(tau < kInf)) {
-      // the list never filled: every gallery row with a finite key is a candidate
+    if (overflow) {
+      ok = false;                     // the log dropped entries: the candidate set is incomplete
+    } else if (!(tau < kInf)) {
+      // no threshold was ever applied and every logged row is a candidate: exact by construction
       ok = (gstats[0] < kInf) && (gstats[1] < kInf) && (qerr[qi] < kInf);
     } else {
       const float qn = qnorm[qi];
@@ -555,12 +685,12 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   double best_eff = 0;
   for (int s = 1; s <= 8; ++s) {
     const int tps = (p.n_tiles + s - 1) / s;
-    if (s > 1 && tps < 64) break;
+    if (s > 1 && tps < 256) break;
     const int s_eff = (p.n_tiles + tps - 1) / tps;
     const int64_t items = int64_t(p.n_qblocks) * s_eff;
     const int64_t waves = (items + num_sms - 1) / num_sms;
-    // cost model: waves * tiles per sweep (+ a small per-split rerank/merge overhead)
-    const double eff = double(p.n_qblocks) * p.n_tiles / (double(waves) * num_sms * tps) - 0.01 * (s - 1);
+    // cost model: waves * tiles per sweep, minus a penalty per extra split (every split restarts its threshold ladder)
+    const double eff = double(p.n_qblocks) * p.n_tiles / (double(waves) * num_sms * tps) - 0.02 * (s - 1);
     if (eff > best_eff + 1e-9) {
       best_eff = eff;
       best_s = s_eff;
@@ -572,17 +702,33 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   p.grid = int(std::min<int64_t>(num_sms, int64_t(p.n_qblocks) * p.n_splits));
   p.unc_cap = int(std::min<int64_t>(nq, 1024));
 
+  // candidate log + pivot pre-pass.  Small galleries are logged whole (threshold +inf); otherwise a sample of
+  // about 1/64 of the gallery gives each query the 16 smallest sampled keys: the 16th is the initial threshold
+  // (about 1000 gallery rows below it), the 8th / 4th / 2nd are the ladder the sweep tightens along.
+  p.logcap = p.n_splits == 1 ? 2048 : 1024;
+  p.use_pivots = ng > p.logcap ? 1 : 0;
+  p.sample_cols = BN;
+  p.n_sample_tiles = 0;
+  if (p.use_pivots) {
+    const int64_t target = std::max<int64_t>(ng / 64, 32);
+    p.sample_cols = target >= 8 * BN ? BN : 32;
+    p.n_sample_tiles = int(std::min<int64_t>(p.n_tiles, std::max<int64_t>(1, (target + p.sample_cols / 2) / p.sample_cols)));
+    p.pivot_grid = std::min(num_sms, p.n_qblocks);
+  }
+
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   const size_t q_rows = size_t(p.n_qblocks) * BM;
   p.off_qh = take(q_rows * p.Dp * 2);
   p.off_gh = take(size_t(ng) * p.Dp * 2);
-  p.off_gnorm = take(size_t(p.n_tiles) * BN * 4);
+  p.off_gpack = take(size_t(p.n_tiles) * NPACK * 4);
   p.off_qnorm = take(q_rows * 4);
   p.off_qerr = take(q_rows * 4);
   p.off_stats = take(64);
-  p.off_cand_key = take(q_rows * p.n_splits * KP * 4);
-  p.off_cand_idx = take(q_rows * p.n_splits * KP * 4);
+  p.off_pivots = take(q_rows * 16);
+  p.off_log = take(q_rows * p.n_splits * p.logcap * 8);
+  p.off_log_cnt = take(q_rows * p.n_splits * 4);
+  p.off_log_tau = take(q_rows * p.n_splits * 4);
   p.off_unc_query = take(size_t(p.unc_cap) * 4);
   p.off_unc_bound = take(size_t(p.unc_cap) * 4);
   p.off_fb_count = take(size_t(p.unc_cap) * 4);
@@ -592,15 +738,27 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   return p;
 }
 
-template <int KATOMS>
-static int launch_tc(const Plan& p, const CUtensorMap& tq, const CUtensorMap& tg, const float* gnorm, int nq,
-                     float* cand_key, int* cand_idx, cudaStream_t stream) {
+constexpr int NEPI_SWEEP = 8;   // epilogue warps of the main sweep (two per TMEM lane quarter)
+
+template <int KATOMS, int NEPI, int MODE>
+static int launch_tc(int grid, const CUtensorMap& tq, const CUtensorMap& tg, const SweepArgs& args, cudaStream_t stream) {
   using S = Smem<KATOMS>;
-  MMSIM_CUDA_CHECK(cudaFuncSetAttribute(knn_tc_kernel<KATOMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
-  knn_tc_kernel<KATOMS><<<p.grid, NUM_THREADS, S::DYN_BYTES, stream>>>(tq, tg, gnorm, nq, p.n_qblocks, p.n_splits,
-                                                                       p.tiles_per_split, p.n_tiles, cand_key, cand_idx);
+  auto kern = knn_tc_kernel<KATOMS, NEPI, MODE>;
+  MMSIM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
+  kern<<<grid, 64 + NEPI * 32, S::DYN_BYTES, stream>>>(tq, tg, args);
   MMSIM_CUDA_CHECK(cudaGetLastError());
   return MMSIM_OK;
+}
+
+template <int MODE>
+static int launch_mode(int katoms, int grid, const CUtensorMap& tq, const CUtensorMap& tg, const SweepArgs& args, cudaStream_t s) {
+  constexpr int NEPI = MODE == MODE_SWEEP ? NEPI_SWEEP : 4;
+  switch (katoms) {
+    case 1: return launch_tc<1, NEPI, MODE>(grid, tq, tg, args, s);
+    case 2: return launch_tc<2, NEPI, MODE>(grid, tq, tg, args, s);
+    case 3: return launch_tc<3, NEPI, MODE>(grid, tq, tg, args, s);
+    default: return launch_tc<4, NEPI, MODE>(grid, tq, tg, args, s);
+  }
 }
 
 int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
@@ -623,12 +781,14 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   uint8_t* w = static_cast<uint8_t*>(ws);
   __half* qh = reinterpret_cast<__half*>(w + p.off_qh);
   __half* gh = reinterpret_cast<__half*>(w + p.off_gh);
-  float* gnorm = reinterpret_cast<float*>(w + p.off_gnorm);
+  float* gpack = reinterpret_cast<float*>(w + p.off_gpack);
   float* qnorm = reinterpret_cast<float*>(w + p.off_qnorm);
   float* qerr = reinterpret_cast<float*>(w + p.off_qerr);
   float* gstats = reinterpret_cast<float*>(w + p.off_stats);
-  float* cand_key = reinterpret_cast<float*>(w + p.off_cand_key);
-  int* cand_idx = reinterpret_cast<int*>(w + p.off_cand_idx);
+  float* pivots = reinterpret_cast<float*>(w + p.off_pivots);
+  uint2* log = reinterpret_cast<uint2*>(w + p.off_log);
+  int* log_cnt = reinterpret_cast<int*>(w + p.off_log_cnt);
+  float* log_tau = reinterpret_cast<float*>(w + p.off_log_tau);
   int* unc_query = reinterpret_cast<int*>(w + p.off_unc_query);
   float* unc_bound = reinterpret_cast<float*>(w + p.off_unc_bound);
   int* fb_count = reinterpret_cast<int*>(w + p.off_fb_count);
@@ -640,45 +800,56 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     MMSIM_CUDA_CHECK(cudaMemsetAsync(fb_count, 0, size_t(p.unc_cap) * 4, stream));
   }
 
-  // 1. operand copies
+  // 1. operand copies: fp16 rows, norm pack (+ per-8 / per-32 column minima), rounding-error norms
   if (phases & kPhasePrep) {
     MMSIM_CUDA_CHECK(cudaMemsetAsync(gstats, 0, 64, stream));
     const int threads = 256;
     const int64_t g_pad = int64_t(p.n_tiles) * BN;
     const int64_t gb = (g_pad * 32 + threads - 1) / threads;
-    prep_rows_kernel<<<unsigned(gb), threads, 0, stream>>>(G, ng, g_pad, int(D), p.Dp, 1.0f, gh, gnorm, nullptr,
+    prep_rows_kernel<<<unsigned(gb), threads, 0, stream>>>(G, ng, g_pad, int(D), p.Dp, 1.0f, gh, gpack, nullptr, 1,
                                                            reinterpret_cast<unsigned int*>(gstats));
     MMSIM_CUDA_CHECK(cudaGetLastError());
+    pack_min_kernel<<<unsigned(p.n_tiles), BN, 0, stream>>>(gpack);
+    MMSIM_CUDA_CHECK(cudaGetLastError());
     const int64_t qb = (nq * 32 + threads - 1) / threads;
-    prep_rows_kernel<<<unsigned(qb), threads, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, nullptr);
+    prep_rows_kernel<<<unsigned(qb), threads, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, 0, nullptr);
     MMSIM_CUDA_CHECK(cudaGetLastError());
   }
 
-  // 2. fused distance + candidate selection
+  // 2. pivot pre-pass (sampled gallery tiles) + fused distance / candidate sweep
   int rc = MMSIM_OK;
-  if (phases & kPhaseTensor) {
-  CUtensorMap tq, tg;
-  rc = make_tmap(&tq, qh, nq, p.Dp, BM);
-  if (rc) return rc;
-  rc = make_tmap(&tg, gh, ng, p.Dp, BN);
-  if (rc) return rc;
-  switch (p.katoms) {
-    case 1: rc = launch_tc<1>(p, tq, tg, gnorm, int(nq), cand_key, cand_idx, stream); break;
-    case 2: rc = launch_tc<2>(p, tq, tg, gnorm, int(nq), cand_key, cand_idx, stream); break;
-    case 3: rc = launch_tc<3>(p, tq, tg, gnorm, int(nq), cand_key, cand_idx, stream); break;
-    default: rc = launch_tc<4>(p, tq, tg, gnorm, int(nq), cand_key, cand_idx, stream); break;
-  }
-  if (rc) return rc;
+  if (phases & (kPhaseTensor | kPhasePivot)) {
+    CUtensorMap tq, tg;
+    rc = make_tmap(&tq, qh, nq, p.Dp, BM);
+    if (rc) return rc;
+    rc = make_tmap(&tg, gh, ng, p.Dp, BN);
+    if (rc) return rc;
+    SweepArgs args{};
+    args.gpack = gpack;
+    args.nq = int(nq); args.n_qblocks = p.n_qblocks; args.n_tiles = p.n_tiles;
+    args.n_splits = p.n_splits; args.tiles_per_split = p.tiles_per_split;
+    args.use_pivots = p.use_pivots;
+    args.log = log; args.logcap = p.logcap; args.log_cnt = log_cnt; args.log_tau = log_tau;
+    args.n_sample_tiles = p.n_sample_tiles; args.sample_cols = p.sample_cols;
+    args.pivots = pivots;
+    if ((phases & kPhasePivot) && p.use_pivots) {
+      rc = launch_mode<MODE_PIVOT>(p.katoms, p.pivot_grid, tq, tg, args, stream);
+      if (rc) return rc;
+    }
+    if (phases & kPhaseTensor) {
+      rc = launch_mode<MODE_SWEEP>(p.katoms, p.grid, tq, tg, args, stream);
+      if (rc) return rc;
+    }
   }
 
-  // 3. exact re-rank + certificate.  delta bounds the fp32 accumulation error of key = |g|^2 - 2 q.g:
-  //    (Dp + 8) roundings of relative size 2^-24, on terms bounded by (|q|^2 + |g|^2), with a 4x safety factor.
+  // 3. candidate selection + exact re-rank + certificate.  delta bounds the fp32 accumulation error of
+  //    key = |g|^2 - 2 q.g: (Dp + 8) roundings of relative size 2^-24, on terms bounded by (|q|^2 + |g|^2), 4x safety.
   if (phases & kPhaseRerank) {
     const float delta_coeff = 4.0f * float(p.Dp + 8) * 5.9604645e-8f;
     const int blocks = int((nq + RR_WARPS - 1) / RR_WARPS);
     const size_t smem = size_t(RR_WARPS) * (size_t(D) + 2 * KP) * 4;
-    knn_rerank_kernel<<<blocks, RR_WARPS * 32, smem, stream>>>(Q, G, int(nq), ng, int(D), cand_key, cand_idx, p.n_splits,
-                                                               qnorm, qerr, gstats, delta_coeff, k, exclude_self,
+    knn_rerank_kernel<<<blocks, RR_WARPS * 32, smem, stream>>>(Q, G, int(nq), ng, int(D), log, p.logcap, log_cnt, log_tau,
+                                                               p.n_splits, qnorm, qerr, gstats, delta_coeff, k, exclude_self,
                                                                self_offset, out_dist, out_idx, status, unc_query,
                                                                unc_bound, p.unc_cap);
     MMSIM_CUDA_CHECK(cudaGetLastError());
