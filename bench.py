@@ -173,26 +173,51 @@ def run_reference(a):
 
 # ----------------------------------------------------------------------------------------------- loss timings
 def time_losses(torch, mm):
-    """batch-hard fwd+bwd (256 = 32 x 8, 128-d) and lifted fwd+bwd (512, 128-d): microseconds per call (second half of the metric)."""
+    """batch-hard fwd+bwd (256 = 32 x 8, 128-d) and lifted fwd+bwd (512, 128-d), the second half of the metric.
+    Two figures per loss, microseconds per call (one call = memset + ONE cooperative kernel: loss, 5 aux vectors,
+    mined indices and dE): `_us` = back-to-back eager launches through the C-ABI (includes the host launch path),
+    `_graph_us` = the same call captured 20x in a CUDA graph and replayed (device time per call)."""
+    from multimodal_similarity_b200.losses import _run
     out = {}
     dev = torch.device("cuda", torch.cuda.current_device())
-    for name, n, fn, margin in (("batch_hard_fwd_bwd_us", 256, mm.batch_hard, "soft"), ("lifted_fwd_bwd_us", 512, mm.lifted_loss, 1.0)):
-        e = synth_torch(n, 128, 32, SEED + 2, dev).requires_grad_(True)
+    for name, n, kind, soft, margin in (("batch_hard_fwd_bwd", 256, 0, True, 0.0), ("lifted_fwd_bwd", 512, 1, False, 1.0)):
+        e = synth_torch(n, 128, 32, SEED + 2, dev)
         pids = (torch.arange(n, device=dev) % 32 + 1).float() if n == 256 else (torch.arange(n, device=dev) % 7).float()
-        from multimodal_similarity_b200.losses import _run
-        kind = 0 if n == 256 else 1
-        soft = margin == "soft"
+        call = lambda: _run(kind, e, pids, soft, margin, True, True)  # noqa: E731
         for _ in range(20):
-            _run(kind, e.detach(), pids, soft, 0.0 if soft else margin, True, True)
+            call()
         torch.cuda.synchronize()
         reps = 500
         s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(reps):
-            _run(kind, e.detach(), pids, soft, 0.0 if soft else margin, True, True)
+            call()
         t.record()
         torch.cuda.synchronize()
-        out[name] = 1e3 * s.elapsed_time(t) / reps
+        out[name + "_us"] = 1e3 * s.elapsed_time(t) / reps
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                call()
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            inner = 20
+            with torch.cuda.graph(g):
+                for _ in range(inner):
+                    keep = call()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            s.record()
+            for _ in range(50):
+                g.replay()
+            t.record()
+            torch.cuda.synchronize()
+            out[name + "_graph_us"] = 1e3 * s.elapsed_time(t) / (50 * inner)
+            del keep
+        except Exception as ex:  # noqa: BLE001
+            out[name + "_graph_error"] = repr(ex)[:200]
     return out
 
 

@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "loss.h"
@@ -485,7 +487,7 @@ static int pick_shape(int64_t N, int64_t D) {
   return -1;
 }
 
-Layout make_layout(int64_t N, int64_t D) {
+static Layout compute_layout(int64_t N, int64_t D) {
   Layout L{};
   L.shape = pick_shape(N, D);
   const int s = L.shape < 0 ? 2 : L.shape;
@@ -505,6 +507,21 @@ Layout make_layout(int64_t N, int64_t D) {
   L.off_row_active = take(size_t(N) * 4);
   L.total_bytes = off;
   L.smem_bytes = smem_for(L.TI, L.TJ, D);
+  return L;
+}
+
+// The layout (tile shape by occupancy query, shared-memory attribute) is computed once per (N, D): the losses are
+// microsecond-scale, so the per-call host path must stay a memset + one launch.
+Layout make_layout(int64_t N, int64_t D) {
+  static std::mutex mu;
+  static std::unordered_map<int64_t, Layout> cache;
+  const int64_t key = (N << 20) | D;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  Layout L = compute_layout(N, D);
+  if (L.shape >= 0) cudaFuncSetAttribute(kernel_for(L.shape), cudaFuncAttributeMaxDynamicSharedMemorySize, int(L.smem_bytes));
+  cache.emplace(key, L);
   return L;
 }
 
@@ -541,7 +558,6 @@ int run(int kind, const float* E, const float* pids, int64_t N, int64_t D, int s
   void* args[] = {const_cast<Params*>(&p)};
   const dim3 grid(unsigned(L.NBI * L.NBJ)), block(THREADS);
   const void* fn = kernel_for(L.shape);
-  MMSIM_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L.smem_bytes)));
   MMSIM_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, grid, block, args, L.smem_bytes, stream));
   return MMSIM_OK;
 }
