@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "exact.cuh"
@@ -110,6 +111,7 @@ struct SweepArgs {
   int logcap;
   int* log_cnt;              // [row * n_splits + split] entries appended (may exceed logcap: overflow)
   float* log_tau;            // [row * n_splits + split] final threshold of the sweep
+  int* split_done;           // [row * n_splits + split] 1 once log_tau is published (later splits start from it)
   // MODE_PIVOT: item = query block; n_sample_tiles evenly spaced tiles, first sample_cols columns of each
   int n_sample_tiles, sample_cols;
   float* pivots;             // [row][4] = 2nd, 4th, 8th, 16th smallest sampled key
@@ -123,7 +125,8 @@ struct Smem {
   static constexpr int TAU_OFF = NORM_OFF + NT * NPACK * 4;   // float [BM]   current threshold of each row
   static constexpr int CNT_OFF = TAU_OFF + BM * 4;            // int   [BM]   log cursor
   static constexpr int CN_OFF = CNT_OFF + BM * 4;             // int   [BM][4] logged entries below pivot b
-  static constexpr int BAR_OFF = CN_OFF + BM * 16;
+  static constexpr int PV_OFF = CN_OFF + BM * 16;             // float [NPIV][BM] pivot pre-pass: sorted smallest keys per row
+  static constexpr int BAR_OFF = PV_OFF + NPIV * BM * 4;
   static constexpr int NUM_BARS = 2 * NS + 2 + 2 + 2 + NT;
   static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
   static constexpr int TOTAL = TMEM_PTR_OFF + 8;
@@ -146,6 +149,53 @@ __device__ __forceinline__ void epi_bar_sync(int nthreads) {  // named barrier 1
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ int atoms_add(uint32_t addr, int v) {
+  int old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+
+// Rare path of the sweep, out of line to keep the hot loop small: the 8 keys of one column group that has at least one
+// candidate in the warp.  Appends every key below the row threshold to the row's log and counts it against the ladder.
+__device__ __noinline__ void sweep_group8(float k0, float k1, float k2, float k3, float k4, float k5, float k6, float k7,
+                                          int cbase, float tau, float piv0, float piv1, float piv2, uint2* mylog, int logcap,
+                                          uint32_t cnt_addr, uint32_t cn_addr) {
+  const float key[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (key[j] < tau) {
+      const int slot = atoms_add(cnt_addr, 1);
+      if (slot < logcap) mylog[slot] = make_uint2(__float_as_uint(key[j]), uint32_t(cbase + j));
+      if (key[j] < piv2) {
+        atoms_add(cn_addr + 8, 1);
+        if (key[j] < piv1) {
+          atoms_add(cn_addr + 4, 1);
+          if (key[j] < piv0) atoms_add(cn_addr, 1);
+        }
+      }
+    }
+  }
+}
+
+// Rare path of the pivot pre-pass: insert x into the row's sorted list of the NPIV smallest keys (lane-private column
+// of shared memory, stride BM floats); returns the new NPIV-th smallest.
+__device__ __noinline__ float pivot_insert(float x, uint32_t pv_addr) {
+  float p[NPIV];
+#pragma unroll
+  for (int i = 0; i < NPIV; ++i) p[i] = lds_f32(pv_addr + i * BM * 4);
+#pragma unroll
+  for (int i = 0; i < NPIV; ++i) {
+    const float lo = fminf(p[i], x);
+    x = fmaxf(p[i], x);
+    p[i] = lo;
+  }
+#pragma unroll
+  for (int i = 0; i < NPIV; ++i) sts_f32(pv_addr + i * BM * 4, p[i]);
+  return p[NPIV - 1];
+}
 
 template <int MODE>
 __device__ __forceinline__ int tile_of(const SweepArgs& a, int t0, int i) {
@@ -170,6 +220,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   float* s_tau = reinterpret_cast<float*>(smem + S::TAU_OFF);
   int* s_cnt = reinterpret_cast<int*>(smem + S::CNT_OFF);
   int* s_cn = reinterpret_cast<int*>(smem + S::CN_OFF);
+  float* s_pv = reinterpret_cast<float*>(smem + S::PV_OFF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* full = bars;                 // [NS]  TMA -> MMA
   uint64_t* empty = bars + NS;           // [NS]  MMA -> TMA
@@ -293,13 +344,26 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       const bool valid = grow < a.nq;
 
       float piv0 = -kInf, piv1 = -kInf, piv2 = -kInf;   // MODE_SWEEP: ladder below the initial threshold
-      float pv[NPIV];                                   // MODE_PIVOT: sorted ascending, the NPIV smallest keys so far
+      float pv_thr = kInf;                              // MODE_PIVOT: current NPIV-th smallest sampled key of the row
       uint2* mylog = nullptr;
+      const uint32_t cnt_addr = ptx::smem_u32(s_cnt + row), cn_addr = ptx::smem_u32(s_cn + row * 4);
+      const uint32_t pv_addr = ptx::smem_u32(s_pv + row);
       if (MODE == MODE_SWEEP) {
         float tau0 = kInf;
         if (a.use_pivots) {
           const float4 pp = *reinterpret_cast<const float4*>(a.pivots + size_t(grow) * 4);
           piv0 = pp.x; piv1 = pp.y; piv2 = pp.z; tau0 = pp.w;
+        }
+        // A finished sweep of another gallery split of the same query ended with a threshold that is usually much
+        // tighter than the sampled one: start from it.  Items are ordered split-major, so with more query blocks than
+        // SMs the earlier splits of this block finished waves ago.  (Thresholds only steer how many candidates are
+        // kept; the certificate in the rerank kernel bounds every unlogged row by the smallest threshold in force.)
+        for (int s2 = 0; s2 < a.n_splits; ++s2) {
+          if (s2 == split) continue;
+          const size_t o = size_t(grow) * a.n_splits + s2;
+          int done;
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.split_done + o) : "memory");
+          if (done) tau0 = fminf(tau0, __ldcg(a.log_tau + o));
         }
         epi_bar_sync(EPI_THREADS);             // every epilogue warp is done with the previous item
         if (h == 0) {
@@ -310,9 +374,44 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         epi_bar_sync(EPI_THREADS);
         mylog = a.log + (size_t(grow) * a.n_splits + split) * a.logcap;
       } else {
+        pv_thr = valid ? kInf : -kInf;
 #pragma unroll
-        for (int i = 0; i < NPIV; ++i) pv[i] = valid ? kInf : -kInf;
+        for (int i = 0; i < NPIV; ++i) s_pv[i * BM + row] = pv_thr;
       }
+
+      // one 32-column chunk of the accumulator, already in registers
+      auto scan_chunk = [&](float (&v)[32], int c, uint32_t nrm, int col0) {
+        // early out on the raw accumulator: key_j = acc_j + |g_j|^2 >= acc_j + (min |g|^2 over the 8-column group)
+        const float tau = MODE == MODE_SWEEP ? s_tau[row] : pv_thr;
+        const float4 nm8 = lds_f32x4(nrm + (BN + c * 4) * 4);
+        float gm[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          gm[g] = min3(min3(v[g * 8], v[g * 8 + 1], v[g * 8 + 2]), min3(v[g * 8 + 3], v[g * 8 + 4], v[g * 8 + 5]),
+                       fminf(v[g * 8 + 6], v[g * 8 + 7]));
+        const uint32_t mine = (gm[0] < tau - nm8.x ? 1u : 0u) | (gm[1] < tau - nm8.y ? 2u : 0u) |
+                              (gm[2] < tau - nm8.z ? 4u : 0u) | (gm[3] < tau - nm8.w ? 8u : 0u);
+        if (!__any_sync(0xffffffffu, mine != 0)) return;
+        const uint32_t groups = __reduce_or_sync(0xffffffffu, mine);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (!(groups & (1u << g))) continue;
+          const float4 n0 = lds_f32x4(nrm + (c * 32 + g * 8) * 4);
+          const float4 n1 = lds_f32x4(nrm + (c * 32 + g * 8 + 4) * 4);
+          // the query operand was pre-scaled by -2, so acc = -2 q.g and key = |g|^2 - 2 q.g
+          const float k0 = v[g * 8 + 0] + n0.x, k1 = v[g * 8 + 1] + n0.y, k2 = v[g * 8 + 2] + n0.z, k3 = v[g * 8 + 3] + n0.w;
+          const float k4 = v[g * 8 + 4] + n1.x, k5 = v[g * 8 + 5] + n1.y, k6 = v[g * 8 + 6] + n1.z, k7 = v[g * 8 + 7] + n1.w;
+          if (MODE == MODE_SWEEP) {
+            sweep_group8(k0, k1, k2, k3, k4, k5, k6, k7, col0 + c * 32 + g * 8, tau, piv0, piv1, piv2, mylog, a.logcap,
+                         cnt_addr, cn_addr);
+          } else {
+            const float key[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (key[j] < pv_thr) pv_thr = pivot_insert(key[j], pv_addr);
+          }
+        }
+      };
 
       for (int i = 0; i < nt; ++i, ++tc) {
         const int t = tile_of<MODE>(a, t0, i);
@@ -323,69 +422,26 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         const uint32_t taddr = tmem_base + ((q * 32) << 16) + as * BN;
         const int col0 = t * BN;
         const int nchunks = MODE == MODE_PIVOT ? a.sample_cols / 32 : BN / 32;
+        constexpr int CPW = (BN / 32) / NH;    // chunks per warp and tile (even): two register buffers ping-pong
+        float va[32], vb[32];
+        ptx::tmem_ld32(taddr + h * 32, va);
 #pragma unroll 1
-        for (int c = h; c < BN / 32; c += NH) {
-          float v[32];
-          ptx::tmem_ld32(taddr + c * 32, v);
-          ptx::tmem_ld_wait(v);
-          if (c + NH >= BN / 32) {  // this warp's last chunk of the tile is in registers: hand its share of TMEM back
+        for (int cp = 0; cp < CPW; cp += 2) {
+          const int c0 = h + cp * NH, c1 = c0 + NH;
+          ptx::tmem_ld_wait(va);
+          ptx::tmem_ld32(taddr + c1 * 32, vb);                 // next chunk streams in while this one is scanned
+          if (c0 < nchunks) scan_chunk(va, c0, nrm, col0);
+          ptx::tmem_ld_wait(vb);
+          if (cp + 2 < CPW) {
+            ptx::tmem_ld32(taddr + (c1 + NH) * 32, va);
+          } else {  // this warp's last chunk of the tile is in registers: hand its share of TMEM back
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[as]);
           }
-          if (c >= nchunks) continue;
-          // early out on the raw accumulator: key_j = acc_j + |g_j|^2 >= acc_j + (min |g|^2 over the chunk)
-          const float tau = MODE == MODE_SWEEP ? s_tau[row] : pv[NPIV - 1];
-          float gm[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            gm[g] = min3(min3(v[g * 8], v[g * 8 + 1], v[g * 8 + 2]), min3(v[g * 8 + 3], v[g * 8 + 4], v[g * 8 + 5]),
-                         fminf(v[g * 8 + 6], v[g * 8 + 7]));
-          const float m = fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3]));
-          const float nmin32 = lds_f32(nrm + (BN + 32 + c) * 4);
-          if (!__any_sync(0xffffffffu, m < tau - nmin32)) continue;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float nmin8 = lds_f32(nrm + (BN + c * 4 + g) * 4);
-            if (!__any_sync(0xffffffffu, gm[g] < tau - nmin8)) continue;
-            const float4 n0 = lds_f32x4(nrm + (c * 32 + g * 8) * 4);
-            const float4 n1 = lds_f32x4(nrm + (c * 32 + g * 8 + 4) * 4);
-            float key[8];
-            // the query operand was pre-scaled by -2, so acc = -2 q.g and key = |g|^2 - 2 q.g
-            key[0] = v[g * 8 + 0] + n0.x; key[1] = v[g * 8 + 1] + n0.y;
-            key[2] = v[g * 8 + 2] + n0.z; key[3] = v[g * 8 + 3] + n0.w;
-            key[4] = v[g * 8 + 4] + n1.x; key[5] = v[g * 8 + 5] + n1.y;
-            key[6] = v[g * 8 + 6] + n1.z; key[7] = v[g * 8 + 7] + n1.w;
-            const int cbase = col0 + c * 32 + g * 8;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (MODE == MODE_SWEEP) {
-                if (key[j] < tau) {
-                  const int slot = atomicAdd(&s_cnt[row], 1);
-                  if (slot < a.logcap) mylog[slot] = make_uint2(__float_as_uint(key[j]), uint32_t(cbase + j));
-                  if (key[j] < piv2) {
-                    atomicAdd(&s_cn[row * 4 + 2], 1);
-                    if (key[j] < piv1) {
-                      atomicAdd(&s_cn[row * 4 + 1], 1);
-                      if (key[j] < piv0) atomicAdd(&s_cn[row * 4 + 0], 1);
-                    }
-                  }
-                }
-              } else {
-                float x = key[j];
-                if (x < pv[NPIV - 1]) {   // sorted insertion network: x bubbles up, the old maximum falls out
-#pragma unroll
-                  for (int i2 = 0; i2 < NPIV; ++i2) {
-                    const float lo = fminf(pv[i2], x);
-                    x = fmaxf(pv[i2], x);
-                    pv[i2] = lo;
-                  }
-                }
-              }
-            }
-          }
+          if (c1 < nchunks) scan_chunk(vb, c1, nrm, col0);
         }
         if (MODE == MODE_SWEEP && h == 0) {
-          // tighten: once KPT logged entries lie below a pivot, nothing at or above it can be among the KPT smallest
+          // tighten: once KPT logged entries lie below a pivot, the KPT smallest keys all lie below it
           const int4 cn = *reinterpret_cast<const int4*>(s_cn + row * 4);
           float nt_ = s_tau[row];
           if (cn.z >= KPT) nt_ = fminf(nt_, piv2);
@@ -399,11 +455,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       if (MODE == MODE_SWEEP) {
         epi_bar_sync(EPI_THREADS);             // all appends of this item are done
         if (h == 0) {
-          a.log_cnt[size_t(grow) * a.n_splits + split] = s_cnt[row];
-          a.log_tau[size_t(grow) * a.n_splits + split] = s_tau[row];
+          const size_t o = size_t(grow) * a.n_splits + split;
+          a.log_cnt[o] = s_cnt[row];
+          a.log_tau[o] = s_tau[row];
+          if (a.n_splits > 1) {
+            // Thresholds only steer how many candidates are kept: the final certificate (rerank kernel) bounds every
+            // unlogged row by the smallest threshold in force, so a shared threshold can cost a fallback, never exactness.
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.split_done + o), "r"(1) : "memory");
+          }
         }
       } else {
-        *reinterpret_cast<float4*>(a.pivots + size_t(grow) * 4) = make_float4(pv[1], pv[3], pv[7], pv[15]);
+        *reinterpret_cast<float4*>(a.pivots + size_t(grow) * 4) =
+            make_float4(s_pv[1 * BM + row], s_pv[3 * BM + row], s_pv[7 * BM + row], s_pv[15 * BM + row]);
       }
     }
   }
@@ -729,6 +793,7 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   p.off_log = take(q_rows * p.n_splits * p.logcap * 8);
   p.off_log_cnt = take(q_rows * p.n_splits * 4);
   p.off_log_tau = take(q_rows * p.n_splits * 4);
+  p.off_split_done = take(q_rows * p.n_splits * 4);
   p.off_unc_query = take(size_t(p.unc_cap) * 4);
   p.off_unc_bound = take(size_t(p.unc_cap) * 4);
   p.off_fb_count = take(size_t(p.unc_cap) * 4);
@@ -738,7 +803,15 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   return p;
 }
 
-constexpr int NEPI_SWEEP = 8;   // epilogue warps of the main sweep (two per TMEM lane quarter)
+// epilogue warps of the main sweep (per TMEM lane quarter: NEPI / 4); MMSIM_NEPI=8|16 overrides for experiments
+static int nepi_sweep() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("MMSIM_NEPI");
+    v = (e && atoi(e) == 16) ? 16 : 8;
+  }
+  return v;
+}
 
 template <int KATOMS, int NEPI, int MODE>
 static int launch_tc(int grid, const CUtensorMap& tq, const CUtensorMap& tg, const SweepArgs& args, cudaStream_t stream) {
@@ -750,9 +823,8 @@ static int launch_tc(int grid, const CUtensorMap& tq, const CUtensorMap& tg, con
   return MMSIM_OK;
 }
 
-template <int MODE>
+template <int MODE, int NEPI>
 static int launch_mode(int katoms, int grid, const CUtensorMap& tq, const CUtensorMap& tg, const SweepArgs& args, cudaStream_t s) {
-  constexpr int NEPI = MODE == MODE_SWEEP ? NEPI_SWEEP : 4;
   switch (katoms) {
     case 1: return launch_tc<1, NEPI, MODE>(grid, tq, tg, args, s);
     case 2: return launch_tc<2, NEPI, MODE>(grid, tq, tg, args, s);
@@ -789,6 +861,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   uint2* log = reinterpret_cast<uint2*>(w + p.off_log);
   int* log_cnt = reinterpret_cast<int*>(w + p.off_log_cnt);
   float* log_tau = reinterpret_cast<float*>(w + p.off_log_tau);
+  int* split_done = reinterpret_cast<int*>(w + p.off_split_done);
   int* unc_query = reinterpret_cast<int*>(w + p.off_unc_query);
   float* unc_bound = reinterpret_cast<float*>(w + p.off_unc_bound);
   int* fb_count = reinterpret_cast<int*>(w + p.off_fb_count);
@@ -829,15 +902,18 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     args.nq = int(nq); args.n_qblocks = p.n_qblocks; args.n_tiles = p.n_tiles;
     args.n_splits = p.n_splits; args.tiles_per_split = p.tiles_per_split;
     args.use_pivots = p.use_pivots;
-    args.log = log; args.logcap = p.logcap; args.log_cnt = log_cnt; args.log_tau = log_tau;
+    args.log = log; args.logcap = p.logcap; args.log_cnt = log_cnt; args.log_tau = log_tau; args.split_done = split_done;
     args.n_sample_tiles = p.n_sample_tiles; args.sample_cols = p.sample_cols;
     args.pivots = pivots;
     if ((phases & kPhasePivot) && p.use_pivots) {
-      rc = launch_mode<MODE_PIVOT>(p.katoms, p.pivot_grid, tq, tg, args, stream);
+      rc = launch_mode<MODE_PIVOT, 4>(p.katoms, p.pivot_grid, tq, tg, args, stream);
       if (rc) return rc;
     }
     if (phases & kPhaseTensor) {
-      rc = launch_mode<MODE_SWEEP>(p.katoms, p.grid, tq, tg, args, stream);
+      if (p.n_splits > 1)
+        MMSIM_CUDA_CHECK(cudaMemsetAsync(split_done, 0, size_t(p.n_qblocks) * BM * p.n_splits * 4, stream));
+      rc = nepi_sweep() == 16 ? launch_mode<MODE_SWEEP, 16>(p.katoms, p.grid, tq, tg, args, stream)
+                              : launch_mode<MODE_SWEEP, 8>(p.katoms, p.grid, tq, tg, args, stream);
       if (rc) return rc;
     }
   }
