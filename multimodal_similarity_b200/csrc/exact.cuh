@@ -88,6 +88,71 @@ __device__ float exact_reduce(const float* __restrict__ a, const float* __restri
   return ret;
 }
 
+
+// ---- cooperative form: 8 adjacent lanes (sub = lane & 7) evaluate one pair; lane `sub` owns NumPy's accumulator r[sub].
+// Loads are 32-byte-sector coalesced across the 8 lanes and independent of each other (memory-level parallelism), the
+// summation order -- and therefore every bit -- is the same as exact_reduce().  All 32 lanes of the warp must call
+// these together (full-mask shuffles); every lane of a group returns the result.
+template <int METRIC>
+__device__ __forceinline__ float exact_leaf_8(const float* __restrict__ a, const float* __restrict__ b, int n, int sub) {
+  if (n < 8) {
+    float r = 0.f;
+    if (n > 0) r = exact_term<METRIC>(a[0], b[0]);
+    for (int i = 1; i < n; ++i) r = __fadd_rn(r, exact_term<METRIC>(a[i], b[i]));
+    return r;
+  }
+  float r = exact_term<METRIC>(a[sub], b[sub]);
+  int i = 8;
+#pragma unroll 8
+  for (; i + 8 <= n; i += 8) r = __fadd_rn(r, exact_term<METRIC>(a[i + sub], b[i + sub]));
+  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));   // (r0+r1) (r2+r3) (r4+r5) (r6+r7)
+  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));   // ((r0+r1)+(r2+r3)) ((r4+r5)+(r6+r7))
+  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+  for (; i < n; ++i) r = __fadd_rn(r, exact_term<METRIC>(a[i], b[i]));
+  return r;
+}
+
+template <int METRIC>
+__device__ float exact_reduce_8(const float* __restrict__ a, const float* __restrict__ b, int n, int sub) {
+  if (n <= 128) return exact_leaf_8<METRIC>(a, b, n, sub);
+  int off_stack[24], len_stack[24];
+  float val_stack[24];
+  unsigned char state[24];
+  int sp = 0;
+  off_stack[0] = 0;
+  len_stack[0] = n;
+  state[0] = 0;
+  float ret = 0.f;
+  while (sp >= 0) {
+    const int off = off_stack[sp], len = len_stack[sp];
+    if (len <= 128) {
+      ret = exact_leaf_8<METRIC>(a + off, b + off, len, sub);
+      --sp;
+      continue;
+    }
+    int n2 = len / 2;
+    n2 -= n2 % 8;
+    if (state[sp] == 0) {
+      state[sp] = 1;
+      ++sp;
+      off_stack[sp] = off;
+      len_stack[sp] = n2;
+      state[sp] = 0;
+    } else if (state[sp] == 1) {
+      val_stack[sp] = ret;
+      state[sp] = 2;
+      ++sp;
+      off_stack[sp] = off + n2;
+      len_stack[sp] = len - n2;
+      state[sp] = 0;
+    } else {
+      ret = __fadd_rn(val_stack[sp], ret);
+      --sp;
+    }
+  }
+  return ret;
+}
+
 template <int METRIC>
 __device__ __forceinline__ float exact_finish(float s) {
   if (METRIC == kEuclidean) return __fsqrt_rn(__fadd_rn(s, 1e-12f));  // src/utils.py:337 (float32 + python float -> float32)

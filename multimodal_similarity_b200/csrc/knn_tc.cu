@@ -96,7 +96,8 @@ constexpr int NS = 4;                      // gallery smem stages (one K atom of
 constexpr int NT = 4;                      // norm-pack ring slots
 constexpr int A_ATOM_BYTES = BM * 128;     // 16 KiB
 constexpr int B_STAGE_BYTES = BN * 128;    // 32 KiB
-constexpr int NPIV = 16;                   // pivot pre-pass keeps the 16 smallest sampled keys per query
+constexpr int NPIV = 16;                   // pivot pre-pass: the 16 smallest sampled keys per query define the ladder
+constexpr int NPSUB = 8;                   // ... gathered from per-warp sub-lists of 8 (each warp scans a quarter of the columns)
 constexpr int KPT = KP;                    // candidates that must lie below a pivot before it becomes the threshold
 
 enum { MODE_PIVOT = 0, MODE_SWEEP = 1 };
@@ -125,8 +126,8 @@ struct Smem {
   static constexpr int TAU_OFF = NORM_OFF + NT * NPACK * 4;   // float [BM]   current threshold of each row
   static constexpr int CNT_OFF = TAU_OFF + BM * 4;            // int   [BM]   log cursor
   static constexpr int CN_OFF = CNT_OFF + BM * 4;             // int   [BM][4] logged entries below pivot b
-  static constexpr int PV_OFF = CN_OFF + BM * 16;             // float [NPIV][BM] pivot pre-pass: sorted smallest keys per row
-  static constexpr int BAR_OFF = PV_OFF + NPIV * BM * 4;
+  static constexpr int PV_OFF = CN_OFF + BM * 16;             // float [4][NPSUB][BM] pivot pre-pass: per-warp sorted sub-lists
+  static constexpr int BAR_OFF = PV_OFF + 4 * NPSUB * BM * 4;
   static constexpr int NUM_BARS = 2 * NS + 2 + 2 + 2 + NT;
   static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
   static constexpr int TOTAL = TMEM_PTR_OFF + 8;
@@ -180,21 +181,21 @@ __device__ __noinline__ void sweep_group8(float k0, float k1, float k2, float k3
   }
 }
 
-// Rare path of the pivot pre-pass: insert x into the row's sorted list of the NPIV smallest keys (lane-private column
-// of shared memory, stride BM floats); returns the new NPIV-th smallest.
+// Rare path of the pivot pre-pass: insert x into this thread's sorted sub-list of the NPSUB smallest keys (lane-private
+// column of shared memory, stride BM floats); returns the new NPSUB-th smallest.
 __device__ __noinline__ float pivot_insert(float x, uint32_t pv_addr) {
-  float p[NPIV];
+  float p[NPSUB];
 #pragma unroll
-  for (int i = 0; i < NPIV; ++i) p[i] = lds_f32(pv_addr + i * BM * 4);
+  for (int i = 0; i < NPSUB; ++i) p[i] = lds_f32(pv_addr + i * BM * 4);
 #pragma unroll
-  for (int i = 0; i < NPIV; ++i) {
+  for (int i = 0; i < NPSUB; ++i) {
     const float lo = fminf(p[i], x);
     x = fmaxf(p[i], x);
     p[i] = lo;
   }
 #pragma unroll
-  for (int i = 0; i < NPIV; ++i) sts_f32(pv_addr + i * BM * 4, p[i]);
-  return p[NPIV - 1];
+  for (int i = 0; i < NPSUB; ++i) sts_f32(pv_addr + i * BM * 4, p[i]);
+  return p[NPSUB - 1];
 }
 
 template <int MODE>
@@ -347,7 +348,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       float pv_thr = kInf;                              // MODE_PIVOT: current NPIV-th smallest sampled key of the row
       uint2* mylog = nullptr;
       const uint32_t cnt_addr = ptx::smem_u32(s_cnt + row), cn_addr = ptx::smem_u32(s_cn + row * 4);
-      const uint32_t pv_addr = ptx::smem_u32(s_pv + row);
+      const uint32_t pv_addr = ptx::smem_u32(s_pv + (h * NPSUB) * BM + row);
       if (MODE == MODE_SWEEP) {
         float tau0 = kInf;
         if (a.use_pivots) {
@@ -374,9 +375,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         epi_bar_sync(EPI_THREADS);
         mylog = a.log + (size_t(grow) * a.n_splits + split) * a.logcap;
       } else {
+        static_assert(MODE == MODE_SWEEP || NH <= 4, "pivot sub-lists are laid out for at most 4 warps per quarter");
+        epi_bar_sync(EPI_THREADS);             // the previous item's merge has read every sub-list
         pv_thr = valid ? kInf : -kInf;
 #pragma unroll
-        for (int i = 0; i < NPIV; ++i) s_pv[i * BM + row] = pv_thr;
+        for (int i = 0; i < NPSUB; ++i) s_pv[(h * NPSUB + i) * BM + row] = pv_thr;
       }
 
       // one 32-column chunk of the accumulator, already in registers
@@ -421,7 +424,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         const uint32_t nrm = ring_u32 + (tc % NT) * NPACK * 4;
         const uint32_t taddr = tmem_base + ((q * 32) << 16) + as * BN;
         const int col0 = t * BN;
-        const int nchunks = MODE == MODE_PIVOT ? a.sample_cols / 32 : BN / 32;
+        // MODE_PIVOT samples either whole tiles or ONE 32-column chunk per sampled tile (rotating over the tile's 8
+        // chunks so the epilogue warps share the work)
+        const int only_chunk = (MODE == MODE_PIVOT && a.sample_cols < BN) ? (i & 7) : -1;
         constexpr int CPW = (BN / 32) / NH;    // chunks per warp and tile (even): two register buffers ping-pong
         float va[32], vb[32];
         ptx::tmem_ld32(taddr + h * 32, va);
@@ -430,7 +435,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           const int c0 = h + cp * NH, c1 = c0 + NH;
           ptx::tmem_ld_wait(va);
           ptx::tmem_ld32(taddr + c1 * 32, vb);                 // next chunk streams in while this one is scanned
-          if (c0 < nchunks) scan_chunk(va, c0, nrm, col0);
+          if (only_chunk < 0 || c0 == only_chunk) scan_chunk(va, c0, nrm, col0);
           ptx::tmem_ld_wait(vb);
           if (cp + 2 < CPW) {
             ptx::tmem_ld32(taddr + (c1 + NH) * 32, va);
@@ -438,7 +443,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[as]);
           }
-          if (c1 < nchunks) scan_chunk(vb, c1, nrm, col0);
+          if (only_chunk < 0 || c1 == only_chunk) scan_chunk(vb, c1, nrm, col0);
         }
         if (MODE == MODE_SWEEP && h == 0) {
           // tighten: once KPT logged entries lie below a pivot, the KPT smallest keys all lie below it
@@ -466,8 +471,29 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           }
         }
       } else {
-        *reinterpret_cast<float4*>(a.pivots + size_t(grow) * 4) =
-            make_float4(s_pv[1 * BM + row], s_pv[3 * BM + row], s_pv[7 * BM + row], s_pv[15 * BM + row]);
+        // merge the NH sub-lists: the ladder is the 2nd / 4th / 8th / 16th smallest of their union.  (A sub-list keeps
+        // only 8 keys, so the union can miss a few of the true 16 smallest: the pivots are steering values, not bounds.)
+        epi_bar_sync(EPI_THREADS);
+        if (h == 0) {
+          float m[NPIV];
+#pragma unroll
+          for (int i = 0; i < NPIV; ++i) m[i] = kInf;
+          for (int e = 0; e < NH * NPSUB; ++e) {
+            float x = s_pv[e * BM + row];
+#pragma unroll
+            for (int i = 0; i < NPIV; ++i) {
+              const float lo = fminf(m[i], x);
+              x = fmaxf(m[i], x);
+              m[i] = lo;
+            }
+          }
+          // tiny samples leave fewer than 16 finite keys: the initial threshold is then the largest finite one
+          float top = m[0];
+#pragma unroll
+          for (int i = 1; i < NPIV; ++i) top = m[i] < kInf ? m[i] : top;
+          *reinterpret_cast<float4*>(a.pivots + size_t(grow) * 4) =
+              make_float4(m[1] < top ? m[1] : -kInf, m[3] < top ? m[3] : -kInf, m[7] < top ? m[7] : -kInf, top);
+        }
       }
     }
   }
@@ -562,16 +588,21 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
   // threshold; logged but not selected: >= the KP-th smallest logged key)
   const float tau = total > KP ? fminf(tau_min, unsortable(ustar)) : tau_min;
 
-  // ---- exact distances (reference arithmetic), one candidate per lane at a time
+  // ---- exact distances (reference arithmetic): 8 lanes per candidate, 4 candidates per round
   const int self = exclude_self ? int(self_offset + qi) : -1;
-#pragma unroll
-  for (int j = 0; j < KP / 32; ++j) {
-    const int idx = sv[j * 32 + lane];
-    float d = kInf;
-    if (idx >= 0 && idx != self) d = exact_l2(qs, G + size_t(idx) * D, D);
-    __syncwarp();
-    sk[j * 32 + lane] = d;
-    sv[j * 32 + lane] = (idx >= 0 && idx != self) ? idx : 0x7fffffff;
+  {
+    const int sub = lane & 7, grp = lane >> 3;
+#pragma unroll 1
+    for (int r0 = 0; r0 < KP; r0 += 4) {
+      const int idx = sv[r0 + grp];
+      const bool live = idx >= 0 && idx != self;
+      const float s2 = exact_reduce_8<kSquaredEuclidean>(qs, G + size_t(live ? idx : 0) * D, D, sub);
+      __syncwarp();
+      if (sub == 0) {
+        sk[r0 + grp] = live ? __fsqrt_rn(s2) : kInf;
+        sv[r0 + grp] = live ? idx : 0x7fffffff;
+      }
+    }
   }
   __syncwarp();
 
@@ -803,12 +834,13 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   return p;
 }
 
-// epilogue warps of the main sweep (per TMEM lane quarter: NEPI / 4); MMSIM_NEPI=8|16 overrides for experiments
+// epilogue warps of the sweep (NEPI / 4 per TMEM lane quarter).  16 measured best on B200 (60.6% of the dense bf16 peak
+// vs 47.7% with 8, profiles/); MMSIM_NEPI=8 keeps the smaller variant reachable for experiments.
 static int nepi_sweep() {
   static int v = 0;
   if (!v) {
     const char* e = getenv("MMSIM_NEPI");
-    v = (e && atoi(e) == 16) ? 16 : 8;
+    v = (e && atoi(e) == 8) ? 8 : 16;
   }
   return v;
 }
@@ -906,7 +938,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     args.n_sample_tiles = p.n_sample_tiles; args.sample_cols = p.sample_cols;
     args.pivots = pivots;
     if ((phases & kPhasePivot) && p.use_pivots) {
-      rc = launch_mode<MODE_PIVOT, 4>(p.katoms, p.pivot_grid, tq, tg, args, stream);
+      rc = launch_mode<MODE_PIVOT, 16>(p.katoms, p.pivot_grid, tq, tg, args, stream);
       if (rc) return rc;
     }
     if (phases & kPhaseTensor) {
