@@ -29,12 +29,14 @@ def stream_handle(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def workspace(tag: str, nbytes: int, device) -> torch.Tensor:
-    """Per (tag, device, stream) byte buffer, grown on demand.  The C-ABI never allocates: we pass this in."""
+def workspace(tag: str, nbytes: int, device, zero: bool = False) -> torch.Tensor:
+    """Per (tag, device, stream) byte buffer, grown on demand.  The C-ABI never allocates: we pass this in.
+    zero=True hands out a zero-filled buffer on (re)allocation (the loss kernels keep theirs zeroed between calls)."""
     key = (tag, device.index, stream_handle(device))
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1024), dtype=torch.uint8, device=device)
+        alloc = torch.zeros if zero else torch.empty
+        buf = alloc(max(int(nbytes), 1024), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
 

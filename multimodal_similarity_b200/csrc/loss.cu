@@ -440,7 +440,10 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
     if (t == 0) {
       *p.loss = s_l[0];
       *p.num_active = p.kind == 0 ? s_a[0] / s_f[0] : 1.0f;
+      p.sync[0] = 0;   // every CTA has passed the barrier and finished phase 2: leave the workspace ready for the
+      p.sync[1] = 0;   // next launch (contract: zero-filled before the first call, left zero-filled by every call)
     }
+    for (int i = t; i < N; i += THREADS) p.same_cnt[i] = 0;
   }
 }
 
@@ -554,7 +557,6 @@ int run(int kind, const float* E, const float* pids, int64_t N, int64_t D, int s
   p.row_active = reinterpret_cast<float*>(b + L.off_row_active);
   p.NBI = L.NBI; p.NBJ = L.NBJ; p.Npad = L.Npad;
 
-  MMSIM_CUDA_CHECK(cudaMemsetAsync(b, 0, L.zero_bytes, stream));
   void* args[] = {const_cast<Params*>(&p)};
   const dim3 grid(unsigned(L.NBI * L.NBJ)), block(THREADS);
   const void* fn = kernel_for(L.shape);

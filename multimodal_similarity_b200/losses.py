@@ -28,22 +28,32 @@ class LossOutput(tuple):
     neg_idx = None
 
 
+_ws_bytes: dict = {}
+
+
 def _run(kind, emb, pids, soft, margin, weighted, need_grad):
+    """One C-ABI call = one cooperative kernel launch.  Returns (scalars [2], vectors [4,N], indices [2,N], dE or None)."""
     lib = _lib.load()
     n, d = emb.shape
     dev = emb.device
-    nbytes = ctypes.c_size_t()
-    _lib.check(lib.mmsim_loss_workspace_bytes(n, d, ctypes.byref(nbytes)), "mmsim_loss_workspace_bytes")
-    ws = workspace("loss", nbytes.value, dev)
-    scal = torch.empty(2, dtype=torch.float32, device=dev)
-    vec = torch.empty((4, n), dtype=torch.float32, device=dev)
-    idx = torch.empty((2, n), dtype=torch.int32, device=dev)
+    nbytes = _ws_bytes.get((n, d))
+    if nbytes is None:
+        c = ctypes.c_size_t()
+        _lib.check(lib.mmsim_loss_workspace_bytes(n, d, ctypes.byref(c)), "mmsim_loss_workspace_bytes")
+        nbytes = _ws_bytes[(n, d)] = c.value
+    ws = workspace("loss", nbytes, dev, zero=True)
+    out = torch.empty((6, n + 2), dtype=torch.float32, device=dev)      # rows 0-3 vectors, 4-5 indices (int32 view), tail scalars
+    vec = out[:4, :n]
+    idx = out[4:6, :n].view(torch.int32)
+    scal = out[0, n:n + 2]
     grad = torch.empty_like(emb) if need_grad else None
-    with torch.cuda.device(dev):
-        rc = lib.mmsim_loss_f32(kind, emb.data_ptr(), pids.data_ptr(), n, d, int(soft), float(margin), int(bool(weighted)),
-                                scal.data_ptr(), scal.data_ptr() + 4, vec[0].data_ptr(), vec[1].data_ptr(),
-                                vec[2].data_ptr(), vec[3].data_ptr(), idx[0].data_ptr(), idx[1].data_ptr(),
-                                _lib.ptr(grad), ws.data_ptr(), ws.numel(), stream_handle(dev))
+    base, pitch = out.data_ptr(), (n + 2) * 4
+    if dev.index != torch.cuda.current_device():
+        torch.cuda.set_device(dev)      # the library launches on the calling thread's current device
+    rc = lib.mmsim_loss_f32(kind, emb.data_ptr(), pids.data_ptr(), n, d, int(soft), float(margin), int(bool(weighted)),
+                            base + n * 4, base + n * 4 + 4, base, base + pitch, base + 2 * pitch, base + 3 * pitch,
+                            base + 4 * pitch, base + 5 * pitch, _lib.ptr(grad), ws.data_ptr(), ws.numel(),
+                            stream_handle(dev))
     _lib.check(rc, "mmsim_loss_f32")
     return scal, vec, idx, grad
 
