@@ -65,8 +65,9 @@ MMSIM_API int mmsim_sqdist_f32(const float* A, int64_t M, const float* B, int64_
  * Outputs follow the reference's return tuple: loss[1], num_active[1], diff[N], weights[N],
  * furthest_positive[N], closest_negative[N]; plus the mined column indices pos_idx[N], neg_idx[N]
  * (-1 when the row has no positive / negative; lifted writes -1).  dE[N*D] may be NULL (forward only).
- * Workspace contract: ws must be ZERO-FILLED before its first use; every successful call leaves it zero-filled again
- * (the kernel resets its own barrier words), so one call is exactly one cooperative kernel launch -- no memset. */
+ * Workspace contract: ws must be ZERO-FILLED before its first use with a given (N, D); every successful call leaves the
+ * words it depends on zeroed again (the kernel resets its own barrier words), so one call is exactly one cooperative
+ * kernel launch -- no memset.  Re-zero (or use a separate workspace) when N or D changes. */
 MMSIM_API int mmsim_loss_workspace_bytes(int64_t N, int64_t D, size_t* bytes);
 MMSIM_API int mmsim_loss_f32(int kind, const float* E, const float* pids, int64_t N, int64_t D, int soft, float margin,
                    int weighted, float* loss, float* num_active, float* diff, float* weights, float* furthest_positive,

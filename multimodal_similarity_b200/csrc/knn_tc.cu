@@ -124,9 +124,9 @@ struct Smem {
   static constexpr int B_OFF = A_OFF + KATOMS * A_ATOM_BYTES;
   static constexpr int NORM_OFF = B_OFF + NS * B_STAGE_BYTES;
   static constexpr int TAU_OFF = NORM_OFF + NT * NPACK * 4;   // float [BM]   current threshold of each row
-  static constexpr int CNT_OFF = TAU_OFF + BM * 4;            // int   [BM]   log cursor
-  static constexpr int CN_OFF = CNT_OFF + BM * 4;             // int   [BM][4] logged entries below pivot b
-  static constexpr int PV_OFF = CN_OFF + BM * 16;             // float [4][NPSUB][BM] pivot pre-pass: per-warp sorted sub-lists
+  static constexpr int CNT_OFF = TAU_OFF + BM * 4;            // u64   [BM]   low word: log cursor; high word: three 10-bit
+                                                              //              counters of logged entries below ladder pivot b
+  static constexpr int PV_OFF = CNT_OFF + BM * 8;             // float [4][NPSUB][BM] pivot pre-pass: per-warp sorted sub-lists
   static constexpr int BAR_OFF = PV_OFF + 4 * NPSUB * BM * 4;
   static constexpr int NUM_BARS = 2 * NS + 2 + 2 + 2 + NT;
   static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
@@ -153,30 +153,29 @@ __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(
 
 
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ int atoms_add(uint32_t addr, int v) {
-  int old;
-  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ unsigned long long atoms_add64(uint32_t addr, unsigned long long v) {
+  unsigned long long old;
+  asm volatile("atom.shared.add.u64 %0, [%1], %2;" : "=l"(old) : "r"(addr), "l"(v) : "memory");
   return old;
 }
 
 // Rare path of the sweep, out of line to keep the hot loop small: the 8 keys of one column group that has at least one
-// candidate in the warp.  Appends every key below the row threshold to the row's log and counts it against the ladder.
+// candidate in the warp.  Every key below the row threshold is appended to the row's log; ONE 64-bit shared atomic per
+// candidate claims the log slot (low word) and bumps the ladder counters (high word: 10-bit fields, one per pivot that
+// is still below the threshold -- a counter stops moving once the threshold has reached its pivot, so it stays far
+// below 1024: at most KPT plus one tile's worth of columns).
 __device__ __noinline__ void sweep_group8(float k0, float k1, float k2, float k3, float k4, float k5, float k6, float k7,
                                           int cbase, float tau, float piv0, float piv1, float piv2, uint2* mylog, int logcap,
-                                          uint32_t cnt_addr, uint32_t cn_addr) {
+                                          uint32_t cnt_addr) {
   const float key[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (key[j] < tau) {
-      const int slot = atoms_add(cnt_addr, 1);
+      const unsigned long long inc = 1ull | (key[j] < piv0 && piv0 < tau ? (1ull << 32) : 0ull) |
+                                     (key[j] < piv1 && piv1 < tau ? (1ull << 42) : 0ull) |
+                                     (key[j] < piv2 && piv2 < tau ? (1ull << 52) : 0ull);
+      const int slot = int(uint32_t(atoms_add64(cnt_addr, inc)));
       if (slot < logcap) mylog[slot] = make_uint2(__float_as_uint(key[j]), uint32_t(cbase + j));
-      if (key[j] < piv2) {
-        atoms_add(cn_addr + 8, 1);
-        if (key[j] < piv1) {
-          atoms_add(cn_addr + 4, 1);
-          if (key[j] < piv0) atoms_add(cn_addr, 1);
-        }
-      }
     }
   }
 }
@@ -219,8 +218,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   uint8_t* smem_b = smem + S::B_OFF;
   float* norm_ring = reinterpret_cast<float*>(smem + S::NORM_OFF);
   float* s_tau = reinterpret_cast<float*>(smem + S::TAU_OFF);
-  int* s_cnt = reinterpret_cast<int*>(smem + S::CNT_OFF);
-  int* s_cn = reinterpret_cast<int*>(smem + S::CN_OFF);
+  unsigned long long* s_cnt = reinterpret_cast<unsigned long long*>(smem + S::CNT_OFF);
   float* s_pv = reinterpret_cast<float*>(smem + S::PV_OFF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* full = bars;                 // [NS]  TMA -> MMA
@@ -347,7 +345,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       float piv0 = -kInf, piv1 = -kInf, piv2 = -kInf;   // MODE_SWEEP: ladder below the initial threshold
       float pv_thr = kInf;                              // MODE_PIVOT: current NPIV-th smallest sampled key of the row
       uint2* mylog = nullptr;
-      const uint32_t cnt_addr = ptx::smem_u32(s_cnt + row), cn_addr = ptx::smem_u32(s_cn + row * 4);
+      const uint32_t cnt_addr = ptx::smem_u32(s_cnt + row);
       const uint32_t pv_addr = ptx::smem_u32(s_pv + (h * NPSUB) * BM + row);
       if (MODE == MODE_SWEEP) {
         float tau0 = kInf;
@@ -369,8 +367,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         epi_bar_sync(EPI_THREADS);             // every epilogue warp is done with the previous item
         if (h == 0) {
           s_tau[row] = valid ? tau0 : -kInf;   // rows past the last query never accept a candidate
-          s_cnt[row] = 0;
-          *reinterpret_cast<int4*>(s_cn + row * 4) = make_int4(0, 0, 0, 0);
+          s_cnt[row] = 0ull;
         }
         epi_bar_sync(EPI_THREADS);
         mylog = a.log + (size_t(grow) * a.n_splits + split) * a.logcap;
@@ -406,7 +403,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           const float k4 = v[g * 8 + 4] + n1.x, k5 = v[g * 8 + 5] + n1.y, k6 = v[g * 8 + 6] + n1.z, k7 = v[g * 8 + 7] + n1.w;
           if (MODE == MODE_SWEEP) {
             sweep_group8(k0, k1, k2, k3, k4, k5, k6, k7, col0 + c * 32 + g * 8, tau, piv0, piv1, piv2, mylog, a.logcap,
-                         cnt_addr, cn_addr);
+                         cnt_addr);
           } else {
             const float key[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
 #pragma unroll
@@ -427,31 +424,35 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         // MODE_PIVOT samples either whole tiles or ONE 32-column chunk per sampled tile (rotating over the tile's 8
         // chunks so the epilogue warps share the work)
         const int only_chunk = (MODE == MODE_PIVOT && a.sample_cols < BN) ? (i & 7) : -1;
-        constexpr int CPW = (BN / 32) / NH;    // chunks per warp and tile (even): two register buffers ping-pong
+        constexpr int CPW = (BN / 32) / NH;    // chunks per warp and tile (even)
+        // Two register buffers.  Both loads of a pair are issued before either chunk is scanned, and the TMEM stage is
+        // handed back to the MMA warp as soon as this warp's LAST load has landed -- before scanning -- so the next
+        // tile's MMAs never wait on the scan (with 16 epilogue warps a warp owns exactly two chunks per tile).
         float va[32], vb[32];
         ptx::tmem_ld32(taddr + h * 32, va);
+        ptx::tmem_ld32(taddr + (h + NH) * 32, vb);
 #pragma unroll 1
         for (int cp = 0; cp < CPW; cp += 2) {
           const int c0 = h + cp * NH, c1 = c0 + NH;
           ptx::tmem_ld_wait(va);
-          ptx::tmem_ld32(taddr + c1 * 32, vb);                 // next chunk streams in while this one is scanned
-          if (only_chunk < 0 || c0 == only_chunk) scan_chunk(va, c0, nrm, col0);
           ptx::tmem_ld_wait(vb);
-          if (cp + 2 < CPW) {
-            ptx::tmem_ld32(taddr + (c1 + NH) * 32, va);
-          } else {  // this warp's last chunk of the tile is in registers: hand its share of TMEM back
+          const bool last = cp + 2 >= CPW;
+          if (last) {
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[as]);
           }
+          if (only_chunk < 0 || c0 == only_chunk) scan_chunk(va, c0, nrm, col0);
+          if (!last) ptx::tmem_ld32(taddr + (c1 + NH) * 32, va);
           if (only_chunk < 0 || c1 == only_chunk) scan_chunk(vb, c1, nrm, col0);
+          if (!last) ptx::tmem_ld32(taddr + (c1 + 2 * NH) * 32, vb);
         }
         if (MODE == MODE_SWEEP && h == 0) {
           // tighten: once KPT logged entries lie below a pivot, the KPT smallest keys all lie below it
-          const int4 cn = *reinterpret_cast<const int4*>(s_cn + row * 4);
+          const uint32_t cn = uint32_t(s_cnt[row] >> 32);
           float nt_ = s_tau[row];
-          if (cn.z >= KPT) nt_ = fminf(nt_, piv2);
-          if (cn.y >= KPT) nt_ = fminf(nt_, piv1);
-          if (cn.x >= KPT) nt_ = fminf(nt_, piv0);
+          if (((cn >> 20) & 1023u) >= KPT) nt_ = fminf(nt_, piv2);
+          if (((cn >> 10) & 1023u) >= KPT) nt_ = fminf(nt_, piv1);
+          if ((cn & 1023u) >= KPT) nt_ = fminf(nt_, piv0);
           s_tau[row] = nt_;
         }
         ptx::mbar_arrive(&nempty[tc % NT]);
@@ -461,7 +462,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         epi_bar_sync(EPI_THREADS);             // all appends of this item are done
         if (h == 0) {
           const size_t o = size_t(grow) * a.n_splits + split;
-          a.log_cnt[o] = s_cnt[row];
+          a.log_cnt[o] = int(uint32_t(s_cnt[row]));
           a.log_tau[o] = s_tau[row];
           if (a.n_splits > 1) {
             // Thresholds only steer how many candidates are kept: the final certificate (rerank kernel) bounds every

@@ -41,7 +41,7 @@ def _run(kind, emb, pids, soft, margin, weighted, need_grad):
         c = ctypes.c_size_t()
         _lib.check(lib.mmsim_loss_workspace_bytes(n, d, ctypes.byref(c)), "mmsim_loss_workspace_bytes")
         nbytes = _ws_bytes[(n, d)] = c.value
-    ws = workspace("loss", nbytes, dev, zero=True)
+    ws = workspace(f"loss{n}x{d}", nbytes, dev, zero=True)    # one zero-initialised workspace per layout (see mmsim.h)
     out = torch.empty((6, n + 2), dtype=torch.float32, device=dev)      # rows 0-3 vectors, 4-5 indices (int32 view), tail scalars
     vec = out[:4, :n]
     idx = out[4:6, :n].view(torch.int32)
