@@ -108,6 +108,7 @@ struct SweepArgs {
   // MODE_SWEEP: item = (split, query block); contiguous tile range per split
   int n_splits, tiles_per_split;
   int use_pivots;            // 0: threshold +inf (everything is logged; small galleries)
+  int flags;                 // experiment switches (MMSIM_SWEEP_FLAGS): 1 = release TMEM after the scan instead of before
   uint2* log;                // [(row * n_splits + split) * logcap] {key bits, gallery row}
   int logcap;
   int* log_cnt;              // [row * n_splits + split] entries appended (may exceed logcap: overflow)
@@ -437,7 +438,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           ptx::tmem_ld_wait(va);
           ptx::tmem_ld_wait(vb);
           const bool last = cp + 2 >= CPW;
-          if (last) {
+          if (last && !(a.flags & 1)) {
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[as]);
           }
@@ -445,6 +446,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           if (!last) ptx::tmem_ld32(taddr + (c1 + NH) * 32, va);
           if (only_chunk < 0 || c1 == only_chunk) scan_chunk(vb, c1, nrm, col0);
           if (!last) ptx::tmem_ld32(taddr + (c1 + 2 * NH) * 32, vb);
+          if (last && (a.flags & 1)) {
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty[as]);
+          }
         }
         if (MODE == MODE_SWEEP && h == 0) {
           // tighten: once KPT logged entries lie below a pivot, the KPT smallest keys all lie below it
@@ -935,6 +940,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     args.nq = int(nq); args.n_qblocks = p.n_qblocks; args.n_tiles = p.n_tiles;
     args.n_splits = p.n_splits; args.tiles_per_split = p.tiles_per_split;
     args.use_pivots = p.use_pivots;
+    { const char* e = getenv("MMSIM_SWEEP_FLAGS"); args.flags = e ? atoi(e) : 0; }
     args.log = log; args.logcap = p.logcap; args.log_cnt = log_cnt; args.log_tau = log_tau; args.split_done = split_done;
     args.n_sample_tiles = p.n_sample_tiles; args.sample_cols = p.sample_cols;
     args.pivots = pivots;

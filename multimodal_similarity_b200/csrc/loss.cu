@@ -144,14 +144,28 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
     for (int64_t x = int64_t(blockIdx.x) * THREADS + t; x < total; x += int64_t(G) * THREADS) p.dE[x] = 0.f;
   }
 
-  // ---- stage the two row panels (coalesced, zero padded)
-  for (int x = t; x < TI * D4; x += THREADS) {
-    const int r = x / D4, c = x - r * D4;
-    Ei[r * DP + c] = (i0 + r < N && c < D) ? p.E[size_t(i0 + r) * D + c] : 0.f;
-  }
-  for (int x = t; x < TJ * D4; x += THREADS) {
-    const int r = x / D4, c = x - r * D4;
-    Ej[r * DP + c] = (j0 + r < N && c < D) ? p.E[size_t(j0 + r) * D + c] : 0.f;
+  // ---- stage the two row panels (coalesced, zero padded); 128-bit loads when the rows are 16-byte aligned
+  {
+    const int Q4 = D4 >> 2;                       // float4 slots per row
+    const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.E) & 15) == 0);
+    for (int r = t / Q4, c4 = t % Q4; r < TI + TJ; r += THREADS / Q4 > 0 ? THREADS / Q4 : 1) {
+      // (THREADS / Q4 == 0 only for D > 512, which run() rejects)
+      const bool is_i = r < TI;
+      const int gr = is_i ? i0 + r : j0 + (r - TI);
+      float* dst = (is_i ? Ei + r * DP : Ej + (r - TI) * DP) + c4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr < N) {
+        const float* src = p.E + size_t(gr) * D + c4 * 4;
+        if (vec) {
+          v = *reinterpret_cast<const float4*>(src);
+        } else {
+          const int c = c4 * 4;
+          v.x = c + 0 < D ? src[0] : 0.f; v.y = c + 1 < D ? src[1] : 0.f;
+          v.z = c + 2 < D ? src[2] : 0.f; v.w = c + 3 < D ? src[3] : 0.f;
+        }
+      }
+      *reinterpret_cast<float4*>(dst) = v;
+    }
   }
   if (t < TI) pid_i[t] = i0 + t < N ? p.pids[i0 + t] : 0.f;
   if (t < TJ) pid_j[t] = j0 + t < N ? p.pids[j0 + t] : 0.f;
