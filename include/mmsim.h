@@ -94,8 +94,9 @@ MMSIM_API int mmsim_knn_f32(const float* Q, int64_t nq, const float* G, int64_t 
 #define MMSIM_KNN_PHASE_TENSOR 2   /* fused tcgen05 distance + candidate sweep (the dominant kernel) */
 #define MMSIM_KNN_PHASE_RERANK 4   /* candidate selection, exact fp32 re-rank, certificate */
 #define MMSIM_KNN_PHASE_FALLBACK 8 /* exact recomputation of uncertified queries */
-#define MMSIM_KNN_PHASE_PIVOT 16   /* tcgen05 pre-pass over a gallery sample: per-query threshold ladder */
-#define MMSIM_KNN_PHASE_ALL 31
+#define MMSIM_KNN_PHASE_PIVOT 16   /* tcgen05 pre-pass over a gallery sample: the 16 smallest sampled keys per query */
+#define MMSIM_KNN_PHASE_LADDER 32  /* pivot list -> threshold ladder (after an optional cross-shard merge of the lists) */
+#define MMSIM_KNN_PHASE_ALL 63
 MMSIM_API int mmsim_knn_f32_phases(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
                          int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
                          mmsim_stream_t stream, int phases);
@@ -107,6 +108,30 @@ MMSIM_API int mmsim_knn_f32_phases(const float* Q, int64_t nq, const float* G, i
  * parts * k <= 4096. */
 MMSIM_API int mmsim_knn_merge(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride, const int64_t* idx_base,
                     int parts, int64_t nq, int k, float* out_dist, int64_t* out_idx, mmsim_stream_t stream);
+
+/* ---- gallery-sharded retrieval with a reduced re-rank and a GLOBAL certificate ----------------------
+ * Per-rank costs that do not shrink with the number of shards (each shard's own threshold estimate, a full 128-row
+ * exact re-rank per query and shard) are removed by splitting the call:
+ *   1. every rank: mmsim_knn_shard_f32(phases = PREP | PIVOT)   -> its pivot lists in the workspace
+ *      (mmsim_knn_pivot_region gives offset/size: [query rows padded to 128][16] float)
+ *   2. all-gather the lists, mmsim_knn_merge_pivots(...) back into every rank's workspace: all shards now filter each
+ *      query with the same threshold (about 1000 gallery rows below it in TOTAL, not per shard)
+ *   3. every rank: mmsim_knn_shard_f32(phases = LADDER | TENSOR | RERANK) with kp << 128: its kp best candidates re-ranked
+ *      exactly (out_dist/out_idx [nq*kp], shard-local indices) and out_lb[nq], a lower bound on the true distance of
+ *      every row of the shard that was NOT re-ranked
+ *   4. all-gather, mmsim_knn_merge_certified: global top-k by (distance, global index); status[0] counts queries whose
+ *      k-th distance is not below every shard's bound.  If it is non-zero the caller repeats with the plain per-shard
+ *      mmsim_knn_f32 + mmsim_knn_merge path (always exact; multimodal_similarity_b200/sharded.py does this).
+ * kp is the caller's choice (sharded.py: twice the expected share of the 128 best keys per shard plus a margin). */
+MMSIM_API int mmsim_knn_shard_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int kp, int exclude_self,
+                        int64_t self_offset, float* out_dist, int32_t* out_idx, float* out_lb, int32_t* status, void* ws,
+                        size_t ws_bytes, mmsim_stream_t stream, int phases);
+MMSIM_API int mmsim_knn_pivot_region(int64_t nq, int64_t ng, int64_t D, int k, size_t* offset, size_t* bytes);
+MMSIM_API int mmsim_knn_merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t rows, float* out,
+                           mmsim_stream_t stream);
+MMSIM_API int mmsim_knn_merge_certified(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride,
+                              const int64_t* idx_base, int parts, int64_t nq, int k_in, int k, const float* lb_parts,
+                              int64_t lb_stride, float* out_dist, int64_t* out_idx, int32_t* status, mmsim_stream_t stream);
 
 /* Leave-one-out retrieval evaluation -- the loop body of utils.evaluate / utils.evaluate_simple
  * (src/utils.py:83-229) for the query rows listed in `queries` (the rows with label > 0, :114,171).

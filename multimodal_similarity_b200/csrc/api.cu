@@ -72,14 +72,14 @@ MMSIM_API int mmsim_knn_f32(const float* Q, int64_t nq, const float* G, int64_t 
 MMSIM_API int mmsim_knn_f32_phases(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
                          int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
                          mmsim_stream_t stream, int phases) {
-  MMSIM_REQUIRE(phases > 0 && phases <= knn::kPhaseAll, MMSIM_ERR_ARG, "knn_phases: phases must be a mask in 1..31");
+  MMSIM_REQUIRE(phases > 0 && phases <= knn::kPhaseAll, MMSIM_ERR_ARG, "knn_phases: phases must be a mask in 1..63");
   return knn::run(Q, nq, G, ng, D, k, exclude_self, self_offset, out_dist, out_idx, status, ws, ws_bytes,
                   reinterpret_cast<cudaStream_t>(stream), phases);
 }
 
 MMSIM_API int mmsim_knn_merge(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride, const int64_t* idx_base,
                     int parts, int64_t nq, int k, float* out_dist, int64_t* out_idx, mmsim_stream_t stream) {
-  return merge::run(dist_parts, idx_parts, part_stride, idx_base, parts, nq, k, out_dist, out_idx,
+  return merge::run(dist_parts, idx_parts, part_stride, idx_base, parts, nq, k, k, nullptr, 0, out_dist, out_idx, nullptr,
                     reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -88,6 +88,36 @@ MMSIM_API int mmsim_evaluate_f32(const float* E, const int32_t* labels, const in
                        int32_t* first, int32_t* depth, int32_t* hist, int32_t* rank, mmsim_stream_t stream) {
   return eval::run(E, labels, cls, N, D, C, queries, nq, alpha, aligned, ap, npos, first, depth, hist, rank,
                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+MMSIM_API int mmsim_knn_shard_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int kp, int exclude_self,
+                        int64_t self_offset, float* out_dist, int32_t* out_idx, float* out_lb, int32_t* status, void* ws,
+                        size_t ws_bytes, mmsim_stream_t stream, int phases) {
+  MMSIM_REQUIRE(phases > 0 && phases <= knn::kPhaseAll, MMSIM_ERR_ARG, "knn_shard: phases must be a mask in 1..63");
+  MMSIM_REQUIRE(kp >= 1 && kp <= knn::KP, MMSIM_ERR_ARG, "knn_shard: kp must be in 1..%d", knn::KP);
+  return knn::run(Q, nq, G, ng, D, k, exclude_self, self_offset, out_dist, out_idx, status, ws, ws_bytes,
+                  reinterpret_cast<cudaStream_t>(stream), phases, kp, out_lb);
+}
+
+MMSIM_API int mmsim_knn_pivot_region(int64_t nq, int64_t ng, int64_t D, int k, size_t* offset, size_t* bytes) {
+  MMSIM_REQUIRE(offset && bytes, MMSIM_ERR_ARG, "knn_pivot_region: null output");
+  MMSIM_REQUIRE(nq > 0 && ng > 0 && D > 0 && D <= 256 && k >= 1, MMSIM_ERR_ARG, "knn_pivot_region: bad sizes");
+  const knn::Plan p = knn::make_plan(nq, ng, D, k, 148);   // the region does not depend on the SM count
+  *offset = p.off_piv16;
+  *bytes = size_t(p.n_qblocks) * 128 * knn::kPivotsPerRow * sizeof(float);
+  return MMSIM_OK;
+}
+
+MMSIM_API int mmsim_knn_merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t rows, float* out,
+                           mmsim_stream_t stream) {
+  return knn::merge_pivots(parts, nparts, part_stride, rows, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+MMSIM_API int mmsim_knn_merge_certified(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride,
+                              const int64_t* idx_base, int parts, int64_t nq, int k_in, int k, const float* lb_parts,
+                              int64_t lb_stride, float* out_dist, int64_t* out_idx, int32_t* status, mmsim_stream_t stream) {
+  return merge::run(dist_parts, idx_parts, part_stride, idx_base, parts, nq, k_in, k, lb_parts, lb_stride, out_dist, out_idx,
+                    status, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

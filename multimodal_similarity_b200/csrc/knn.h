@@ -16,17 +16,21 @@ struct Plan {
   int n_splits, tiles_per_split, grid;
   int unc_cap;                // max uncertified queries handled by the exact fallback
   int logcap, use_pivots, n_sample_tiles, sample_cols, pivot_grid;   // candidate log / pivot pre-pass geometry
-  size_t off_qh, off_gh, off_gpack, off_qnorm, off_qerr, off_stats, off_pivots, off_log, off_log_cnt, off_log_tau, off_split_done;
+  size_t off_qh, off_gh, off_gpack, off_qnorm, off_qerr, off_stats, off_piv16, off_ladder, off_log, off_log_cnt, off_log_tau, off_split_done;
   size_t off_unc_query, off_unc_bound, off_fb_count, off_fb_dist, off_fb_idx;
   size_t total_bytes;
 };
 
 Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms);
 
-enum : int { kPhasePrep = 1, kPhaseTensor = 2, kPhaseRerank = 4, kPhaseFallback = 8, kPhasePivot = 16, kPhaseAll = 31 };
+enum : int { kPhasePrep = 1, kPhaseTensor = 2, kPhaseRerank = 4, kPhaseFallback = 8, kPhasePivot = 16, kPhaseLadder = 32, kPhaseAll = 63 };
 
 int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
-        float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream, int phases = kPhaseAll);
+        float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream, int phases = kPhaseAll,
+        int shard_kp = 0, float* out_lb = nullptr);
+
+constexpr int kPivotsPerRow = 16;  // floats per query row in the pivot region of the workspace
+int merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t rows, float* out, cudaStream_t stream);
 
 }  // namespace knn
 }  // namespace mmsim

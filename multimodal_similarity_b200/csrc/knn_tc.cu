@@ -116,7 +116,8 @@ struct SweepArgs {
   int* split_done;           // [row * n_splits + split] 1 once log_tau is published (later splits start from it)
   // MODE_PIVOT: item = query block; n_sample_tiles evenly spaced tiles, first sample_cols columns of each
   int n_sample_tiles, sample_cols;
-  float* pivots;             // [row][4] = 2nd, 4th, 8th, 16th smallest sampled key
+  float* piv16;              // MODE_PIVOT out: [row][16] the smallest sampled keys, ascending (+inf where missing)
+  const float* ladder;       // MODE_SWEEP in:  [row][4] = ladder pivots (ascending) and the initial threshold
 };
 
 template <int KATOMS>
@@ -351,7 +352,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       if (MODE == MODE_SWEEP) {
         float tau0 = kInf;
         if (a.use_pivots) {
-          const float4 pp = *reinterpret_cast<const float4*>(a.pivots + size_t(grow) * 4);
+          const float4 pp = *reinterpret_cast<const float4*>(a.ladder + size_t(grow) * 4);
           piv0 = pp.x; piv1 = pp.y; piv2 = pp.z; tau0 = pp.w;
         }
         // A finished sweep of another gallery split of the same query ended with a threshold that is usually much
@@ -493,12 +494,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
               m[i] = lo;
             }
           }
-          // tiny samples leave fewer than 16 finite keys: the initial threshold is then the largest finite one
-          float top = m[0];
+          float4* dst = reinterpret_cast<float4*>(a.piv16 + size_t(grow) * NPIV);
 #pragma unroll
-          for (int i = 1; i < NPIV; ++i) top = m[i] < kInf ? m[i] : top;
-          *reinterpret_cast<float4*>(a.pivots + size_t(grow) * 4) =
-              make_float4(m[1] < top ? m[1] : -kInf, m[3] < top ? m[3] : -kInf, m[7] < top ? m[7] : -kInf, top);
+          for (int i = 0; i < NPIV / 4; ++i) dst[i] = make_float4(m[4 * i], m[4 * i + 1], m[4 * i + 2], m[4 * i + 3]);
         }
       }
     }
@@ -507,6 +505,49 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ------------------------------------------------------------------------------------------------ threshold ladder
+// piv16 -> ladder: the 2nd / 4th / 8th smallest sampled keys and, as the initial threshold, the 16th (or the largest
+// finite one when the sample was tiny).  A separate step so that the gallery-sharded path can first merge the shards'
+// lists into the list of the whole gallery's sample (all shards then filter with the same per-query threshold).
+__global__ void make_ladder_kernel(const float* __restrict__ piv16, int rows, float* __restrict__ ladder) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* m = piv16 + size_t(r) * NPIV;
+  float top = m[0];
+  for (int i = 1; i < NPIV; ++i) top = m[i] < kInf ? m[i] : top;
+  *reinterpret_cast<float4*>(ladder + size_t(r) * 4) =
+      make_float4(m[1] < top ? m[1] : -kInf, m[3] < top ? m[3] : -kInf, m[7] < top ? m[7] : -kInf, top);
+}
+
+__global__ void fill_f32_kernel(float* __restrict__ p, int64_t n, float v) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// out[row] = the NPIV smallest of the union of parts[p][row] (p < nparts), ascending.
+__global__ void merge_pivots_kernel(const float* __restrict__ parts, int nparts, int64_t part_stride, int rows,
+                                    float* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float m[NPIV];
+#pragma unroll
+  for (int i = 0; i < NPIV; ++i) m[i] = kInf;
+  for (int p = 0; p < nparts; ++p) {
+    const float* src = parts + size_t(p) * part_stride + size_t(r) * NPIV;
+    for (int e = 0; e < NPIV; ++e) {
+      float x = src[e];
+#pragma unroll
+      for (int i = 0; i < NPIV; ++i) {
+        const float lo = fminf(m[i], x);
+        x = fmaxf(m[i], x);
+        m[i] = lo;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NPIV; ++i) out[size_t(r) * NPIV + i] = m[i];
 }
 
 // ------------------------------------------------------------------------------------------------ rerank
@@ -521,9 +562,12 @@ __global__ void __launch_bounds__(RR_WARPS * 32)
 knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int nq, int64_t ng, int D,
                   const uint2* __restrict__ log, int logcap, const int* __restrict__ log_cnt, const float* __restrict__ log_tau,
                   int n_splits, const float* __restrict__ qnorm, const float* __restrict__ qerr,
-                  const float* __restrict__ gstats, float delta_coeff, int k, int exclude_self, int64_t self_offset,
-                  float* __restrict__ out_dist, int* __restrict__ out_idx,
+                  const float* __restrict__ gstats, float delta_coeff, int k, int kp, int exclude_self, int64_t self_offset,
+                  float* __restrict__ out_dist, int* __restrict__ out_idx, float* __restrict__ out_lb,
                   int* __restrict__ status, int* __restrict__ unc_query, float* __restrict__ unc_bound, int unc_cap) {
+  // kp <= KP candidates are re-ranked.  out_lb == nullptr: emit the top-k and certify locally (k <= kp).
+  // out_lb != nullptr (gallery-shard mode): emit all kp re-ranked candidates (k == kp) plus the lower bound on the
+  // true distance of every row of this shard that is NOT among them; the certificate is evaluated after the merge.
   extern __shared__ float rr_smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qi = blockIdx.x * RR_WARPS + warp;
@@ -547,8 +591,8 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
     tau_min = fminf(tau_min, log_tau[l0 + s]);
   }
   uint32_t ustar = 0xffffffffu;   // KP-th smallest key in sortable-uint form
-  if (total > KP) {
-    // radix descent, one bit per pass: smallest value u with #{entries <= u} >= KP
+  if (total > kp) {
+    // radix descent, one bit per pass: smallest value u with #{entries <= u} >= kp
     uint32_t prefix = 0;
     for (int bit = 31; bit >= 0; --bit) {
       const uint32_t mid = prefix | ((1u << bit) - 1u);
@@ -559,14 +603,14 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
         for (int e = lane; e < c; e += 32) cnt += sortable(__ldg(&ls[e].x)) <= mid ? 1 : 0;
       }
       cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (cnt < KP) prefix |= (1u << bit);
+      if (cnt < kp) prefix |= (1u << bit);
     }
     ustar = prefix;
   }
   __syncwarp();
   int filled = 0;
-  for (int pass = 0; pass < 2; ++pass) {        // pass 0: keys < u*, pass 1: keys == u* until KP slots are used
-    if (pass == 1 && total <= KP) break;
+  for (int pass = 0; pass < 2; ++pass) {        // pass 0: keys < u*, pass 1: keys == u* until kp slots are used
+    if (pass == 1 && total <= kp) break;
     for (int s = 0; s < n_splits; ++s) {
       const uint2* ls = log + (l0 + s) * logcap;
       const int c = min(log_cnt[l0 + s], logcap);
@@ -577,11 +621,11 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
         if (e < c) {
           ent = __ldg(&ls[e]);
           const uint32_t u = sortable(ent.x);
-          take = total <= KP ? true : (pass == 0 ? u < ustar : u == ustar);
+          take = total <= kp ? true : (pass == 0 ? u < ustar : u == ustar);
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, take);
         const int pos = filled + __popc(bal & ((1u << lane) - 1u));
-        if (take && pos < KP) {
+        if (take && pos < kp) {
           sk[pos] = __uint_as_float(ent.x);
           sv[pos] = int(ent.y);
         }
@@ -592,7 +636,7 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
   __syncwarp();
   // every gallery row that is not a candidate has an approximate key >= tau (never logged: >= the sweep's final
   // threshold; logged but not selected: >= the KP-th smallest logged key)
-  const float tau = total > KP ? fminf(tau_min, unsortable(ustar)) : tau_min;
+  const float tau = total > kp ? fminf(tau_min, unsortable(ustar)) : tau_min;
 
   // ---- exact distances (reference arithmetic): 8 lanes per candidate, 4 candidates per round
   const int self = exclude_self ? int(self_offset + qi) : -1;
@@ -600,6 +644,7 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
     const int sub = lane & 7, grp = lane >> 3;
 #pragma unroll 1
     for (int r0 = 0; r0 < KP; r0 += 4) {
+      if (r0 >= kp) break;                      // slots >= kp hold the (+inf, -1) padding
       const int idx = sv[r0 + grp];
       const bool live = idx >= 0 && idx != self;
       const float s2 = exact_reduce_8<kSquaredEuclidean>(qs, G + size_t(live ? idx : 0) * D, D, sub);
@@ -637,29 +682,33 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
     out_idx[size_t(qi) * k + r] = (d < kInf) ? sv[r] : -1;
   }
 
-  // ---- certificate
+  // ---- certificate: lower bound on the true distance of every row that is not a candidate
   if (lane == 0) {
-    const float dk = sk[k - 1];
-    bool ok;
+    float lb;
     if (overflow) {
-      ok = false;                     // the log dropped entries: the candidate set is incomplete
+      lb = -kInf;                     // the log dropped entries: the candidate set is incomplete
     } else if (!(tau < kInf)) {
       // no threshold was ever applied and every logged row is a candidate: exact by construction
-      ok = (gstats[0] < kInf) && (gstats[1] < kInf) && (qerr[qi] < kInf);
+      lb = ((gstats[0] < kInf) && (gstats[1] < kInf) && (qerr[qi] < kInf)) ? kInf : -kInf;
     } else {
       const float qn = qnorm[qi];
       const float delta = delta_coeff * (qn + gstats[1]);
       const float lb2 = tau + qn - delta;
-      const float lb = sqrtf(fmaxf(lb2, 0.f)) * 0.999999f - (qerr[qi] + gstats[0]);
-      ok = dk < lb;
+      lb = sqrtf(fmaxf(lb2, 0.f)) * 0.999999f - (qerr[qi] + gstats[0]);
+      if (!(lb == lb)) lb = -kInf;    // NaN inputs certify nothing
     }
-    if (!ok) {
-      const int slot = atomicAdd(&status[0], 1);
-      if (slot < unc_cap) {
-        unc_query[slot] = qi;
-        unc_bound[slot] = dk;
-      } else {
-        status[2] = 1;
+    if (out_lb) {
+      out_lb[qi] = lb;
+    } else {
+      const float dk = sk[k - 1];
+      if (!(dk < lb)) {
+        const int slot = atomicAdd(&status[0], 1);
+        if (slot < unc_cap) {
+          unc_query[slot] = qi;
+          unc_bound[slot] = dk;
+        } else {
+          status[2] = 1;
+        }
       }
     }
   }
@@ -826,7 +875,8 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   p.off_qnorm = take(q_rows * 4);
   p.off_qerr = take(q_rows * 4);
   p.off_stats = take(64);
-  p.off_pivots = take(q_rows * 16);
+  p.off_piv16 = take(q_rows * NPIV * 4);
+  p.off_ladder = take(q_rows * 16);
   p.off_log = take(q_rows * p.n_splits * p.logcap * 8);
   p.off_log_cnt = take(q_rows * p.n_splits * 4);
   p.off_log_tau = take(q_rows * p.n_splits * 4);
@@ -872,7 +922,10 @@ static int launch_mode(int katoms, int grid, const CUtensorMap& tq, const CUtens
 }
 
 int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
-        float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream, int phases) {
+        float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream, int phases, int shard_kp,
+        float* out_lb) {
+  MMSIM_REQUIRE(shard_kp == 0 || (out_lb && shard_kp >= 1 && shard_kp <= KP), MMSIM_ERR_ARG,
+                "knn: shard mode needs out_lb and 1 <= kp <= %d", KP);
   MMSIM_REQUIRE(Q && G && out_dist && out_idx && status && ws, MMSIM_ERR_ARG, "knn: null pointer argument");
   MMSIM_REQUIRE(nq > 0 && ng > 0 && D > 0, MMSIM_ERR_ARG, "knn: empty input (nq=%lld ng=%lld D=%lld)", (long long)nq,
                 (long long)ng, (long long)D);
@@ -895,7 +948,8 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   float* qnorm = reinterpret_cast<float*>(w + p.off_qnorm);
   float* qerr = reinterpret_cast<float*>(w + p.off_qerr);
   float* gstats = reinterpret_cast<float*>(w + p.off_stats);
-  float* pivots = reinterpret_cast<float*>(w + p.off_pivots);
+  float* piv16 = reinterpret_cast<float*>(w + p.off_piv16);
+  float* ladder = reinterpret_cast<float*>(w + p.off_ladder);
   uint2* log = reinterpret_cast<uint2*>(w + p.off_log);
   int* log_cnt = reinterpret_cast<int*>(w + p.off_log_cnt);
   float* log_tau = reinterpret_cast<float*>(w + p.off_log_tau);
@@ -929,7 +983,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
 
   // 2. pivot pre-pass (sampled gallery tiles) + fused distance / candidate sweep
   int rc = MMSIM_OK;
-  if (phases & (kPhaseTensor | kPhasePivot)) {
+  if (phases & (kPhaseTensor | kPhasePivot | kPhaseLadder)) {
     CUtensorMap tq, tg;
     rc = make_tmap(&tq, qh, nq, p.Dp, BM);
     if (rc) return rc;
@@ -943,10 +997,20 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     { const char* e = getenv("MMSIM_SWEEP_FLAGS"); args.flags = e ? atoi(e) : 0; }
     args.log = log; args.logcap = p.logcap; args.log_cnt = log_cnt; args.log_tau = log_tau; args.split_done = split_done;
     args.n_sample_tiles = p.n_sample_tiles; args.sample_cols = p.sample_cols;
-    args.pivots = pivots;
+    args.piv16 = piv16; args.ladder = ladder;
+    if ((phases & kPhasePivot) && !p.use_pivots) {   // shard small enough to be logged whole: an empty (+inf) pivot list
+      const int64_t n = int64_t(p.n_qblocks) * BM * NPIV;
+      fill_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(piv16, n, kInf);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
+    }
     if ((phases & kPhasePivot) && p.use_pivots) {
       rc = launch_mode<MODE_PIVOT, 16>(p.katoms, p.pivot_grid, tq, tg, args, stream);
       if (rc) return rc;
+    }
+    if ((phases & kPhaseLadder) && p.use_pivots) {
+      const int rows = p.n_qblocks * BM;
+      make_ladder_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(piv16, rows, ladder);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
     }
     if (phases & kPhaseTensor) {
       if (p.n_splits > 1)
@@ -964,14 +1028,15 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     const int blocks = int((nq + RR_WARPS - 1) / RR_WARPS);
     const size_t smem = size_t(RR_WARPS) * (size_t(D) + 2 * KP) * 4;
     knn_rerank_kernel<<<blocks, RR_WARPS * 32, smem, stream>>>(Q, G, int(nq), ng, int(D), log, p.logcap, log_cnt, log_tau,
-                                                               p.n_splits, qnorm, qerr, gstats, delta_coeff, k, exclude_self,
-                                                               self_offset, out_dist, out_idx, status, unc_query,
+                                                               p.n_splits, qnorm, qerr, gstats, delta_coeff, shard_kp ? shard_kp : k,
+                                                               shard_kp ? shard_kp : KP, exclude_self, self_offset, out_dist,
+                                                               out_idx, shard_kp ? out_lb : nullptr, status, unc_query,
                                                                unc_bound, p.unc_cap);
     MMSIM_CUDA_CHECK(cudaGetLastError());
   }
 
   // 4. exact fallback for uncertified queries (no-op when status[0] == 0; the count lives on the device)
-  if (phases & kPhaseFallback) {
+  if ((phases & kPhaseFallback) && !shard_kp) {
     dim3 grid(64, 16);
     knn_fallback_collect_kernel<<<grid, 256, size_t(D) * 4, stream>>>(Q, G, ng, int(D), exclude_self, self_offset, status,
                                                                       unc_query, unc_bound, p.unc_cap, fb_count, fb_dist,
@@ -981,6 +1046,14 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
                                                        out_idx);
     MMSIM_CUDA_CHECK(cudaGetLastError());
   }
+  return MMSIM_OK;
+}
+
+int merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t rows, float* out, cudaStream_t stream) {
+  MMSIM_REQUIRE(parts && out && nparts >= 1 && rows >= 0 && part_stride >= rows * NPIV, MMSIM_ERR_ARG, "merge_pivots: bad arguments");
+  if (rows == 0) return MMSIM_OK;
+  merge_pivots_kernel<<<unsigned((rows + 127) / 128), 128, 0, stream>>>(parts, nparts, part_stride, int(rows), out);
+  MMSIM_CUDA_CHECK(cudaGetLastError());
   return MMSIM_OK;
 }
 

@@ -3,7 +3,8 @@
 #include <cstdint>
 namespace mmsim {
 namespace merge {
-int run(const float* dist_parts, const int* idx_parts, int64_t part_stride, const int64_t* idx_base, int parts, int64_t nq, int k,
-        float* out_dist, int64_t* out_idx, cudaStream_t s);
+int run(const float* dist_parts, const int* idx_parts, int64_t part_stride, const int64_t* idx_base, int parts, int64_t nq,
+        int k_in, int k, const float* lb_parts, int64_t lb_stride, float* out_dist, int64_t* out_idx, int* status,
+        cudaStream_t s);
 }
 }  // namespace mmsim

@@ -27,7 +27,7 @@ def late_fusion(*modalities):
     return torch.cat([to_cuda_f32(m, dev) for m in modalities], dim=1)
 
 
-def knn_raw(q: torch.Tensor, g: torch.Tensor, k: int, exclude_self: bool = False, self_offset: int = 0, *, phases: int = 31,
+def knn_raw(q: torch.Tensor, g: torch.Tensor, k: int, exclude_self: bool = False, self_offset: int = 0, *, phases: int = 63,
             out=None):
     """Low-level call: CUDA float32 tensors in, (dist [Q,k] f32, idx [Q,k] i32 shard-local, status [8] i32) out.
     Asynchronous on the current stream; ``status`` is checked by the callers that hand results to the user."""

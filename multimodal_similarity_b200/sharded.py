@@ -1,12 +1,24 @@
 """Gallery-sharded retrieval over the GPUs of one box (no counterpart in the single-process reference).
 
 One process per GPU (``torch.distributed``, NCCL over NVLink).  The gallery rows are split contiguously over the
-ranks, the queries are replicated.  Every rank runs the fused kNN kernel on its shard (exact, certified local
-top-k), one all-gather exchanges the ``[Q, k]`` (distance f32, shard-local index i32) lists, and every rank runs the
-same merge kernel ordered by (distance, global index) -- so the output is bit-identical on every rank and equal
-to the single-GPU result by construction.  The training-loss kernels are not sharded (replicas only).
+ranks, the queries are replicated.  Two protocols, both giving results bit-identical on every rank and equal to the
+single-GPU result:
+
+``exact-shards``  every rank computes the exact, locally certified top-k of its shard (``mmsim_knn_f32``), one
+                  all-gather of the packed ``[2, Q, k]`` lists, the same merge kernel on every rank.
+``reduced``       (default with CUDA tensors) the per-rank work that does not shrink with the number of shards is removed:
+                  (1) the pivot pre-pass lists are all-gathered and merged, so all shards filter every query with ONE
+                  threshold (about 1000 gallery rows below it in total, not per shard); (2) each shard re-ranks exactly
+                  only ``kp`` << 128 candidates and reports a lower bound for everything it did not re-rank; (3) the merge
+                  certifies the global top-k against those bounds.  If any query is uncertified (adversarial row
+                  order, massive ties) the call falls back to ``exact-shards`` -- so the result is always exact.
+
+The training-loss kernels are not sharded (replicas only).
 """
 from __future__ import annotations
+
+import ctypes
+import math
 
 import torch
 import torch.distributed as dist
@@ -15,12 +27,22 @@ from . import _lib
 from ._util import is_numpy_like, stream_handle, to_cuda_f32
 from .retrieval import check_status, knn_raw
 
+PH_PREP, PH_TENSOR, PH_RERANK, PH_FALLBACK, PH_PIVOT, PH_LADDER = 1, 2, 4, 8, 16, 32
+
 
 def shard_bounds(n_rows: int, world: int, rank: int):
     """Contiguous row block of ``rank``: [lo, hi) with ceil(n/world) rows per rank (the last ranks may be short/empty)."""
     per = -(-n_rows // world)
     lo = min(n_rows, rank * per)
     return lo, min(n_rows, lo + per)
+
+
+def reduced_kp(world: int, k: int) -> int:
+    """Candidates each shard re-ranks exactly in the reduced protocol.  With rows in random order a shard holds
+    Binomial(128, 1/world) of the 128 best approximate keys: mean + 6 sigma + 8 (and never fewer than its share of k)."""
+    p = 1.0 / world
+    kp = int(math.ceil(128 * p + 6.0 * math.sqrt(128 * p * (1 - p)))) + 8
+    return min(128, max(kp, -(-k // world) + 8))
 
 
 def merge_parts(dist_parts: torch.Tensor, idx_parts: torch.Tensor, idx_base: torch.Tensor, k: int):
@@ -36,6 +58,93 @@ def merge_parts(dist_parts: torch.Tensor, idx_parts: torch.Tensor, idx_base: tor
                                  parts, nq, k, out_d.data_ptr(), out_i.data_ptr(), stream_handle(dev))
     _lib.check(rc, "mmsim_knn_merge")
     return out_d, out_i
+
+
+class ReducedShard:
+    """State of one shard in the reduced protocol (its own workspace: the pivot lists live inside it)."""
+
+    def __init__(self, shard: torch.Tensor, lo: int):
+        self.shard, self.lo = shard, lo
+        self.ws = None
+
+    def _ws(self, nq, d, k):
+        lib = _lib.load()
+        n = ctypes.c_size_t()
+        _lib.check(lib.mmsim_knn_workspace_bytes(nq, self.shard.shape[0], d, k, ctypes.byref(n)), "mmsim_knn_workspace_bytes")
+        if self.ws is None or self.ws.numel() < n.value:
+            self.ws = torch.empty(n.value, dtype=torch.uint8, device=self.shard.device)
+        off, nb = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(lib.mmsim_knn_pivot_region(nq, self.shard.shape[0], d, k, ctypes.byref(off), ctypes.byref(nb)),
+                   "mmsim_knn_pivot_region")
+        return self.ws[off.value:off.value + nb.value].view(torch.float32).view(-1, 16)
+
+    def _call(self, q, k, kp, exclude_self, self_offset, phases, out):
+        lib = _lib.load()
+        dev = q.device
+        d_, i_, lb_, st_ = out
+        with torch.cuda.device(dev):
+            rc = lib.mmsim_knn_shard_f32(q.data_ptr(), q.shape[0], self.shard.data_ptr(), self.shard.shape[0], q.shape[1], k, kp,
+                                         int(bool(exclude_self)), int(self_offset - self.lo), d_.data_ptr(), i_.data_ptr(),
+                                         lb_.data_ptr(), st_.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+                                         stream_handle(dev), phases)
+        _lib.check(rc, "mmsim_knn_shard_f32")
+
+    def stage1(self, q, k, kp, packed):
+        """Operand copies + pivot pre-pass; returns this shard's pivot lists [rows, 16] (a view into the workspace)."""
+        piv = self._ws(q.shape[0], q.shape[1], k)
+        if self.shard.shape[0] == 0:
+            return None
+        self._call(q, k, kp, False, 0, PH_PREP | PH_PIVOT, self._views(packed, q.shape[0], kp))
+        return piv
+
+    def stage2(self, q, k, kp, exclude_self, self_offset, packed):
+        """Threshold ladder from the (merged) pivot lists, sweep, reduced exact re-rank -> fills `packed`."""
+        nq = q.shape[0]
+        d_, i_, lb_, st_ = self._views(packed, nq, kp)
+        if self.shard.shape[0] == 0:
+            d_.fill_(float("inf")); i_.fill_(-1); lb_.fill_(float("inf"))
+            return
+        self._call(q, k, kp, exclude_self, self_offset, PH_LADDER | PH_TENSOR | PH_RERANK, (d_, i_, lb_, st_))
+
+    @staticmethod
+    def packed_elems(nq, kp):
+        return 2 * nq * kp + nq + 8
+
+    @staticmethod
+    def _views(packed, nq, kp):
+        """int32 buffer [2*nq*kp + nq + 8]: distance bits | shard-local indices | lower-bound bits | status."""
+        d_ = packed[:nq * kp].view(torch.float32).view(nq, kp)
+        i_ = packed[nq * kp:2 * nq * kp].view(nq, kp)
+        lb_ = packed[2 * nq * kp:2 * nq * kp + nq].view(torch.float32)
+        st_ = packed[2 * nq * kp + nq:]
+        return d_, i_, lb_, st_
+
+
+def merge_pivots_into(piv_parts: torch.Tensor, out: torch.Tensor):
+    """[parts, rows, 16] pivot lists -> out [rows, 16]: the 16 smallest of the union (mmsim_knn_merge_pivots)."""
+    lib = _lib.load()
+    dev = out.device
+    with torch.cuda.device(dev):
+        rc = lib.mmsim_knn_merge_pivots(piv_parts.data_ptr(), piv_parts.shape[0], piv_parts.stride(0), out.shape[0],
+                                        out.data_ptr(), stream_handle(dev))
+    _lib.check(rc, "mmsim_knn_merge_pivots")
+
+
+def merge_certified(gathered: torch.Tensor, bases: torch.Tensor, nq: int, kp: int, k: int):
+    """[parts, packed_elems] gathered stage-2 buffers -> (dist [Q,k], idx [Q,k] i64, status [8] i32; status[0] = uncertified)."""
+    lib = _lib.load()
+    dev = gathered.device
+    parts, stride = gathered.shape[0], gathered.stride(0)
+    out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    status = torch.zeros(8, dtype=torch.int32, device=dev)
+    base = gathered.data_ptr()
+    with torch.cuda.device(dev):
+        rc = lib.mmsim_knn_merge_certified(base, base + nq * kp * 4, stride, bases.data_ptr(), parts, nq, kp, k,
+                                           base + 2 * nq * kp * 4, stride, out_d.data_ptr(), out_i.data_ptr(),
+                                           status.data_ptr(), stream_handle(dev))
+    _lib.check(rc, "mmsim_knn_merge_certified")
+    return out_d, out_i, status
 
 
 class ShardedGallery:
@@ -63,8 +172,10 @@ class ShardedGallery:
         self.shard = self._to_device(shard, device)
         self.hi = self.lo + int(self.shard.shape[0])
         self.dim = int(gallery.shape[1])
+        self._reduced = None
+        self.last_protocol = None
 
-    # -- the three steps; tests on CPU boxes replace _to_device/_local/_merge to exercise the sharding logic under gloo
+    # -- steps of the exact-shards protocol; tests on CPU boxes replace them to exercise the sharding logic under gloo
     def _to_device(self, x, device):
         return to_cuda_f32(x, device)
 
@@ -83,12 +194,11 @@ class ShardedGallery:
     def _merge(self, gathered, bases, k):
         return merge_parts(gathered[:, 0].view(torch.float32), gathered[:, 1], bases, k)
 
-    def retrieve(self, queries, k, *, exclude_self=False, self_offset=0, check=True):
-        as_numpy = is_numpy_like(queries)
-        q = self._to_device(queries, self.shard.device)
-        if q.shape[1] != self.dim:
-            raise ValueError(f"queries are {q.shape[1]}-d but the gallery is {self.dim}-d")
-        k = int(k)
+    def _bases(self, device):
+        per = -(-self.total // self.world)
+        return torch.tensor([min(self.total, r * per) for r in range(self.world)], dtype=torch.int64, device=device)
+
+    def _retrieve_exact_shards(self, q, k, exclude_self, self_offset, check):
         packed, status = self._local(q, k, exclude_self, self_offset)
         if self.world > 1:
             # dim-0 concatenation layout (accepted by both NCCL and gloo), viewed as [world, 2, Q, k] afterwards
@@ -97,11 +207,52 @@ class ShardedGallery:
             gathered = flat.view((self.world,) + tuple(packed.shape))
         else:
             gathered = packed.unsqueeze(0)
-        per = -(-self.total // self.world)
-        bases = torch.tensor([min(self.total, r * per) for r in range(self.world)], dtype=torch.int64, device=packed.device)
-        out_d, out_i = self._merge(gathered, bases, k)
+        out = self._merge(gathered, self._bases(packed.device), k)
         if check and status is not None:
             check_status(status)
+        return out
+
+    def _retrieve_reduced(self, q, k, exclude_self, self_offset):
+        """Returns (dist, idx) or None when a query could not be certified (caller falls back to exact-shards)."""
+        nq = q.shape[0]
+        kp = reduced_kp(self.world, k)
+        if self._reduced is None:
+            self._reduced = ReducedShard(self.shard, self.lo)
+        rs = self._reduced
+        dev = q.device
+        packed = torch.empty(ReducedShard.packed_elems(nq, kp), dtype=torch.int32, device=dev)
+        piv = rs.stage1(q, k, kp, packed)
+        rows = -(-nq // 128) * 128
+        mine = piv if piv is not None else torch.full((rows, 16), float("inf"), device=dev)
+        allpiv = torch.empty((self.world * rows, 16), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allpiv, mine.contiguous(), group=self.group)
+        if piv is not None:
+            merge_pivots_into(allpiv.view(self.world, rows, 16), piv)
+        rs.stage2(q, k, kp, exclude_self, self_offset, packed)
+        gathered = torch.empty((self.world, packed.numel()), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(gathered.view(-1), packed, group=self.group)
+        out_d, out_i, status = merge_certified(gathered, self._bases(dev), nq, kp, k)
+        if int(status[0]) != 0:          # identical on every rank (same inputs, same kernel): no extra collective needed
+            return None
+        return out_d, out_i
+
+    def retrieve(self, queries, k, *, exclude_self=False, self_offset=0, check=True, protocol="auto"):
+        as_numpy = is_numpy_like(queries)
+        q = self._to_device(queries, self.shard.device)
+        if q.shape[1] != self.dim:
+            raise ValueError(f"queries are {q.shape[1]}-d but the gallery is {self.dim}-d")
+        if protocol not in ("auto", "reduced", "exact-shards"):
+            raise ValueError("protocol must be auto, reduced or exact-shards")
+        k = int(k)
+        out = None
+        self.last_protocol = "exact-shards"
+        if protocol != "exact-shards" and self.world > 1 and q.is_cuda and reduced_kp(self.world, k) < 128:
+            out = self._retrieve_reduced(q, k, exclude_self, self_offset)
+            if out is not None:
+                self.last_protocol = "reduced"
+        if out is None:
+            out = self._retrieve_exact_shards(q, k, exclude_self, self_offset, check)
+        out_d, out_i = out
         if as_numpy:
             return out_d.cpu().numpy(), out_i.cpu().numpy()
         return out_d, out_i

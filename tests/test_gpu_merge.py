@@ -43,3 +43,52 @@ def test_sharded_gallery_single_process(rs):
     d, i = sg.retrieve(x[:50], 10)
     ref_d, ref_i = O.knn(x[:50], x, 10)
     assert np.array_equal(d, ref_d) and i.dtype == np.int64
+
+
+def _simulate_reduced(g, q, k, R, exclude_self):
+    """The reduced sharded protocol with R simulated ranks in one process (collectives replaced by torch.stack)."""
+    from multimodal_similarity_b200.sharded import ReducedShard, merge_certified, merge_pivots_into, reduced_kp, shard_bounds
+    n, nq = g.shape[0], q.shape[0]
+    kp = reduced_kp(R, k)
+    shards, packed, pivs, bases = [], [], [], []
+    for r in range(R):
+        lo, hi = shard_bounds(n, R, r)
+        shards.append(ReducedShard(g[lo:hi].contiguous(), lo))
+        packed.append(torch.empty(ReducedShard.packed_elems(nq, kp), dtype=torch.int32, device="cuda"))
+        bases.append(lo)
+    for r in range(R):
+        pivs.append(shards[r].stage1(q, k, kp, packed[r]))
+    allpiv = torch.stack(pivs)                       # the all-gather
+    for r in range(R):
+        merge_pivots_into(allpiv, pivs[r])
+    for r in range(R):
+        shards[r].stage2(q, k, kp, exclude_self, 0, packed[r])
+    gathered = torch.stack(packed)                   # the second all-gather
+    return merge_certified(gathered, torch.tensor(bases, device="cuda"), nq, kp, k), kp
+
+
+@pytest.mark.parametrize("R", [2, 4, 8])
+@pytest.mark.parametrize("exclude_self", [False, True])
+def test_reduced_protocol_equals_unsharded(R, exclude_self, rs):
+    import multimodal_similarity_b200 as mm
+    x, _ = clustered(rs, 40000, 128, 50)
+    g = torch.from_numpy(x).cuda()
+    q = g[:500].clone() if exclude_self else torch.from_numpy(clustered(rs, 500, 128, 50)[0]).cuda()
+    k = 100
+    (md, mi, status), kp = _simulate_reduced(g, q, k, R, exclude_self)
+    assert kp < 128
+    assert int(status[0]) == 0, f"{int(status[0])} uncertified queries with randomly ordered rows"
+    full_d, full_i = mm.retrieve(q, g, k, exclude_self=exclude_self)
+    assert torch.equal(md, full_d) and torch.equal(mi, full_i)
+
+
+def test_reduced_protocol_certificate_catches_adversarial_order(rs):
+    """Gallery sorted by cluster: all neighbours of a query live in ONE shard, which re-ranks only kp < k of them.
+    The global certificate must flag those queries (the caller then falls back to the exact-shards protocol)."""
+    cent = rs.randn(8, 128).astype(np.float32) * 3
+    lab = np.repeat(np.arange(8), 1500)
+    x = cent[lab] + 0.3 * rs.randn(lab.size, 128).astype(np.float32)
+    g = torch.from_numpy(x).cuda()
+    q = torch.from_numpy(cent[[0, 3, 7]] + 0.3 * rs.randn(3, 128).astype(np.float32)).cuda()
+    (md, mi, status), kp = _simulate_reduced(g, q, 100, 8, False)
+    assert kp < 100 and int(status[0]) == 3
