@@ -126,9 +126,8 @@ struct Smem {
   static constexpr int B_OFF = A_OFF + KATOMS * A_ATOM_BYTES;
   static constexpr int NORM_OFF = B_OFF + NS * B_STAGE_BYTES;
   static constexpr int TAU_OFF = NORM_OFF + NT * NPACK * 4;   // float [BM]   current threshold of each row
-  static constexpr int CNT_OFF = TAU_OFF + BM * 4;            // u64   [BM]   low word: log cursor; high word: three 10-bit
-                                                              //              counters of logged entries below ladder pivot b
-  static constexpr int PV_OFF = CNT_OFF + BM * 8;             // float [4][NPSUB][BM] pivot pre-pass: per-warp sorted sub-lists
+  static constexpr int CNT_OFF = TAU_OFF + BM * 4;            // u32   [BM]   packed log cursor + ladder counters
+  static constexpr int PV_OFF = CNT_OFF + BM * 4;             // float [4][NPSUB][BM] pivot pre-pass: per-warp sorted sub-lists
   static constexpr int BAR_OFF = PV_OFF + 4 * NPSUB * BM * 4;
   static constexpr int NUM_BARS = 2 * NS + 2 + 2 + 2 + NT;
   static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
@@ -155,29 +154,37 @@ __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(
 
 
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ unsigned long long atoms_add64(uint32_t addr, unsigned long long v) {
-  unsigned long long old;
-  asm volatile("atom.shared.add.u64 %0, [%1], %2;" : "=l"(old) : "r"(addr), "l"(v) : "memory");
+__device__ __forceinline__ uint32_t atoms_add32(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
   return old;
 }
 
+// Per-row state word (one native 32-bit shared atomic per candidate; a 64-bit shared add would be a CAS loop):
+//   bits [ 0,14)  log cursor          bits [14,23)  logged entries below ladder pivot 1 (8th smallest sampled key)
+//   bits [23,32)  logged entries below ladder pivot 0 (4th smallest sampled key)
+// A counter only moves while its pivot is still below the row threshold, so it stays below KPT + one tile of columns
+// (< 512); the cursor is kept below 2^14 by closing the row (threshold = -inf) once its log is full.
+constexpr uint32_t CUR_MASK = 0x3FFFu;
+constexpr int CN1_SHIFT = 14, CN0_SHIFT = 23;
+
 // Rare path of the sweep, out of line to keep the hot loop small: the 8 keys of one column group that has at least one
-// candidate in the warp.  Every key below the row threshold is appended to the row's log; ONE 64-bit shared atomic per
-// candidate claims the log slot (low word) and bumps the ladder counters (high word: 10-bit fields, one per pivot that
-// is still below the threshold -- a counter stops moving once the threshold has reached its pivot, so it stays far
-// below 1024: at most KPT plus one tile's worth of columns).
+// candidate in the warp.  Every key below the row threshold is appended to the row's log.
 __device__ __noinline__ void sweep_group8(float k0, float k1, float k2, float k3, float k4, float k5, float k6, float k7,
-                                          int cbase, float tau, float piv0, float piv1, float piv2, uint2* mylog, int logcap,
-                                          uint32_t cnt_addr) {
+                                          int cbase, float tau, float piv0, float piv1, uint2* mylog, int logcap,
+                                          uint32_t cnt_addr, uint32_t tau_addr) {
   const float key[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (key[j] < tau) {
-      const unsigned long long inc = 1ull | (key[j] < piv0 && piv0 < tau ? (1ull << 32) : 0ull) |
-                                     (key[j] < piv1 && piv1 < tau ? (1ull << 42) : 0ull) |
-                                     (key[j] < piv2 && piv2 < tau ? (1ull << 52) : 0ull);
-      const int slot = int(uint32_t(atoms_add64(cnt_addr, inc)));
-      if (slot < logcap) mylog[slot] = make_uint2(__float_as_uint(key[j]), uint32_t(cbase + j));
+      const uint32_t inc = 1u | (key[j] < piv1 && piv1 < tau ? (1u << CN1_SHIFT) : 0u) |
+                           (key[j] < piv0 && piv0 < tau ? (1u << CN0_SHIFT) : 0u);
+      const int slot = int(atoms_add32(cnt_addr, inc) & CUR_MASK);
+      if (slot < logcap) {
+        mylog[slot] = make_uint2(__float_as_uint(key[j]), uint32_t(cbase + j));
+      } else {
+        sts_f32(tau_addr, -kInf);   // log full: the row is uncertifiable from here on, stop accepting candidates
+      }
     }
   }
 }
@@ -220,7 +227,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   uint8_t* smem_b = smem + S::B_OFF;
   float* norm_ring = reinterpret_cast<float*>(smem + S::NORM_OFF);
   float* s_tau = reinterpret_cast<float*>(smem + S::TAU_OFF);
-  unsigned long long* s_cnt = reinterpret_cast<unsigned long long*>(smem + S::CNT_OFF);
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + S::CNT_OFF);
   float* s_pv = reinterpret_cast<float*>(smem + S::PV_OFF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* full = bars;                 // [NS]  TMA -> MMA
@@ -344,16 +351,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       const int grow = qb * BM + row;          // global query row (may be >= nq in the last block)
       const bool valid = grow < a.nq;
 
-      float piv0 = -kInf, piv1 = -kInf, piv2 = -kInf;   // MODE_SWEEP: ladder below the initial threshold
+      float piv0 = -kInf, piv1 = -kInf;                 // MODE_SWEEP: ladder below the initial threshold
       float pv_thr = kInf;                              // MODE_PIVOT: current NPIV-th smallest sampled key of the row
       uint2* mylog = nullptr;
-      const uint32_t cnt_addr = ptx::smem_u32(s_cnt + row);
+      const uint32_t cnt_addr = ptx::smem_u32(s_cnt + row), tau_addr = ptx::smem_u32(s_tau + row);
       const uint32_t pv_addr = ptx::smem_u32(s_pv + (h * NPSUB) * BM + row);
       if (MODE == MODE_SWEEP) {
         float tau0 = kInf;
         if (a.use_pivots) {
           const float4 pp = *reinterpret_cast<const float4*>(a.ladder + size_t(grow) * 4);
-          piv0 = pp.x; piv1 = pp.y; piv2 = pp.z; tau0 = pp.w;
+          piv0 = pp.y; piv1 = pp.z; tau0 = pp.w;        // 4th / 8th / 16th smallest sampled key
         }
         // A finished sweep of another gallery split of the same query ended with a threshold that is usually much
         // tighter than the sampled one: start from it.  Items are ordered split-major, so with more query blocks than
@@ -369,7 +376,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         epi_bar_sync(EPI_THREADS);             // every epilogue warp is done with the previous item
         if (h == 0) {
           s_tau[row] = valid ? tau0 : -kInf;   // rows past the last query never accept a candidate
-          s_cnt[row] = 0ull;
+          s_cnt[row] = 0u;
         }
         epi_bar_sync(EPI_THREADS);
         mylog = a.log + (size_t(grow) * a.n_splits + split) * a.logcap;
@@ -404,8 +411,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           const float k0 = v[g * 8 + 0] + n0.x, k1 = v[g * 8 + 1] + n0.y, k2 = v[g * 8 + 2] + n0.z, k3 = v[g * 8 + 3] + n0.w;
           const float k4 = v[g * 8 + 4] + n1.x, k5 = v[g * 8 + 5] + n1.y, k6 = v[g * 8 + 6] + n1.z, k7 = v[g * 8 + 7] + n1.w;
           if (MODE == MODE_SWEEP) {
-            sweep_group8(k0, k1, k2, k3, k4, k5, k6, k7, col0 + c * 32 + g * 8, tau, piv0, piv1, piv2, mylog, a.logcap,
-                         cnt_addr);
+            sweep_group8(k0, k1, k2, k3, k4, k5, k6, k7, col0 + c * 32 + g * 8, tau, piv0, piv1, mylog, a.logcap, cnt_addr,
+                         tau_addr);
           } else {
             const float key[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
 #pragma unroll
@@ -454,11 +461,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         }
         if (MODE == MODE_SWEEP && h == 0) {
           // tighten: once KPT logged entries lie below a pivot, the KPT smallest keys all lie below it
-          const uint32_t cn = uint32_t(s_cnt[row] >> 32);
+          const uint32_t cn = s_cnt[row];
           float nt_ = s_tau[row];
-          if (((cn >> 20) & 1023u) >= KPT) nt_ = fminf(nt_, piv2);
-          if (((cn >> 10) & 1023u) >= KPT) nt_ = fminf(nt_, piv1);
-          if ((cn & 1023u) >= KPT) nt_ = fminf(nt_, piv0);
+          if (((cn >> CN1_SHIFT) & 511u) >= KPT) nt_ = fminf(nt_, piv1);
+          if (((cn >> CN0_SHIFT) & 511u) >= KPT) nt_ = fminf(nt_, piv0);
           s_tau[row] = nt_;
         }
         ptx::mbar_arrive(&nempty[tc % NT]);
@@ -468,7 +474,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         epi_bar_sync(EPI_THREADS);             // all appends of this item are done
         if (h == 0) {
           const size_t o = size_t(grow) * a.n_splits + split;
-          a.log_cnt[o] = int(uint32_t(s_cnt[row]));
+          a.log_cnt[o] = int(s_cnt[row] & CUR_MASK);
           a.log_tau[o] = s_tau[row];
           if (a.n_splits > 1) {
             // Thresholds only steer how many candidates are kept: the final certificate (rerank kernel) bounds every
