@@ -317,17 +317,55 @@ def main():
            "ms_per_step": ms_e2e / e2e_steps}
 
     # ---- roofline of the dominant kernel (knn_tc_kernel), timed alone on its stream via the phase mask
-    d0, i0, st0 = knn_raw(queries, sg.shard, k)          # leaves a consistent workspace behind
-    outbuf = (d0, i0, st0)
-    for _ in range(2):
-        knn_raw(queries, sg.shard, k, phases=2, out=outbuf)
     tc_reps = max(3, min(a.steps, 10))
-    ms_tc, _ = timed(lambda: knn_raw(queries, sg.shard, k, phases=2, out=outbuf), tc_reps)
-    ms_tc /= tc_reps
     phase_ms = {}
-    for name, mask in (("prep", 1), ("pivot_prepass", 16), ("select_rerank", 4), ("fallback", 8)):
-        m_, _ = timed(lambda: knn_raw(queries, sg.shard, k, phases=mask, out=outbuf), 3)
-        phase_ms[name] = m_ / 3
+    if world == 1:
+        d0, i0, st0 = knn_raw(queries, sg.shard, k)          # leaves a consistent workspace behind
+        outbuf = (d0, i0, st0)
+        for _ in range(2):
+            knn_raw(queries, sg.shard, k, phases=2, out=outbuf)
+        ms_tc, _ = timed(lambda: knn_raw(queries, sg.shard, k, phases=2, out=outbuf), tc_reps)
+        ms_tc /= tc_reps
+        for name, mask in (("prep", 1), ("pivot_prepass", 16), ("ladder", 32), ("select_rerank", 4), ("fallback", 8)):
+            m_, _ = timed(lambda: knn_raw(queries, sg.shard, k, phases=mask, out=outbuf), 3)
+            phase_ms[name] = m_ / 3
+    else:
+        # the reduced sharded protocol, stage by stage (same calls ShardedGallery.retrieve makes)
+        from multimodal_similarity_b200.sharded import ReducedShard, merge_certified, merge_pivots_into, reduced_kp
+        kp = reduced_kp(world, k)
+        rs_ = ReducedShard(sg.shard, lo)
+        packed = torch.empty(ReducedShard.packed_elems(Q, kp), dtype=torch.int32, device=dev)
+        rows = -(-Q // 128) * 128
+        piv = rs_.stage1(queries, k, kp, packed)
+        allpiv = torch.empty((world * rows, 16), dtype=torch.float32, device=dev)
+        gathered = torch.empty((world, packed.numel()), dtype=torch.int32, device=dev)
+        views = ReducedShard._views(packed, Q, kp)
+
+        def ag_piv():
+            dist.all_gather_into_tensor(allpiv, piv.contiguous())
+            merge_pivots_into(allpiv.view(world, rows, 16), piv)
+
+        def ag_res():
+            dist.all_gather_into_tensor(gathered.view(-1), packed)
+
+        ag_piv()
+        rs_.stage2(queries, k, kp, False, 0, packed)
+        ag_res()
+        stages = (("prep", lambda: rs_._call(queries, k, kp, False, 0, 1, views)),
+                  ("pivot_prepass", lambda: rs_._call(queries, k, kp, False, 0, 16, views)),
+                  ("allgather_merge_pivots", ag_piv),
+                  ("ladder", lambda: rs_._call(queries, k, kp, False, 0, 32, views)),
+                  ("select_rerank_kp%d" % kp, lambda: rs_._call(queries, k, kp, False, 0, 4, views)),
+                  ("allgather_results", ag_res),
+                  ("merge_certified", lambda: merge_certified(gathered, sg._bases(dev), Q, kp, k)))
+        for name, fn in stages:
+            fn()
+            m_, _ = timed(fn, 3)
+            phase_ms[name] = m_ / 3
+        sweep = lambda: rs_._call(queries, k, kp, False, 0, 2, views)  # noqa: E731
+        sweep()
+        ms_tc, _ = timed(sweep, tc_reps)
+        ms_tc /= tc_reps
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -347,7 +385,7 @@ def main():
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f16 tensor-core filter + f32 exact re-rank", "data": "synthetic", "config": config_of(a, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": (8 if world == 1 else 9) * a.steps, "roofline": roofline,
-        "exact_fallback_queries": fell_back,
+        "exact_fallback_queries": fell_back, "protocol": sg.last_protocol if world > 1 else "single",
     }
 
     if rank == 0 and world == 1 and not a.no_extras:

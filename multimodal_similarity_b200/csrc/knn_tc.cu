@@ -430,9 +430,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         const uint32_t nrm = ring_u32 + (tc % NT) * NPACK * 4;
         const uint32_t taddr = tmem_base + ((q * 32) << 16) + as * BN;
         const int col0 = t * BN;
-        // MODE_PIVOT samples either whole tiles or ONE 32-column chunk per sampled tile (rotating over the tile's 8
-        // chunks so the epilogue warps share the work)
-        const int only_chunk = (MODE == MODE_PIVOT && a.sample_cols < BN) ? (i & 7) : -1;
+        // MODE_PIVOT samples whole tiles or a window of sample_cols/32 chunks per sampled tile (the window rotates over the
+        // tile's 8 chunks from one sampled tile to the next, so the epilogue warps share the work)
+        const int win = MODE == MODE_PIVOT ? a.sample_cols / 32 : 8, rot = i & 7;
+        auto sampled = [&](int c) { return ((c - rot) & 7) < win; };
         constexpr int CPW = (BN / 32) / NH;    // chunks per warp and tile (even)
         // Two register buffers.  Both loads of a pair are issued before either chunk is scanned, and the TMEM stage is
         // handed back to the MMA warp as soon as this warp's LAST load has landed -- before scanning -- so the next
@@ -450,9 +451,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[as]);
           }
-          if (only_chunk < 0 || c0 == only_chunk) scan_chunk(va, c0, nrm, col0);
+          if (sampled(c0)) scan_chunk(va, c0, nrm, col0);
           if (!last) ptx::tmem_ld32(taddr + (c1 + NH) * 32, va);
-          if (only_chunk < 0 || c1 == only_chunk) scan_chunk(vb, c1, nrm, col0);
+          if (sampled(c1)) scan_chunk(vb, c1, nrm, col0);
           if (!last) ptx::tmem_ld32(taddr + (c1 + 2 * NH) * 32, vb);
           if (last && (a.flags & 1)) {
             ptx::tc_fence_before();
@@ -841,7 +842,7 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   double best_eff = 0;
   for (int s = 1; s <= 8; ++s) {
     const int tps = (p.n_tiles + s - 1) / s;
-    if (s > 1 && tps < 256) break;
+    if (s > 1 && tps < 64) break;
     const int s_eff = (p.n_tiles + tps - 1) / tps;
     const int64_t items = int64_t(p.n_qblocks) * s_eff;
     const int64_t waves = (items + num_sms - 1) / num_sms;
@@ -866,8 +867,10 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   p.sample_cols = BN;
   p.n_sample_tiles = 0;
   if (p.use_pivots) {
+    // about 1/64 of the gallery, as few MMA tiles as possible while still spread over >= 8 places of the gallery
     const int64_t target = std::max<int64_t>(ng / 64, 32);
-    p.sample_cols = target >= 8 * BN ? BN : 32;
+    p.sample_cols = 32;
+    while (p.sample_cols < BN && target / (2 * p.sample_cols) >= 8) p.sample_cols *= 2;
     p.n_sample_tiles = int(std::min<int64_t>(p.n_tiles, std::max<int64_t>(1, (target + p.sample_cols / 2) / p.sample_cols)));
     p.pivot_grid = std::min(num_sms, p.n_qblocks);
   }
