@@ -664,10 +664,11 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
   }
   __syncwarp();
 
-  // ---- bitonic sort of KP pairs in shared memory by (distance, index)
-  for (int size = 2; size <= KP; size <<= 1) {
+  // ---- bitonic sort of the candidate slots (padded to a power of two >= kp) in shared memory by (distance, index)
+  const int SP = kp <= 32 ? 32 : (kp <= 64 ? 64 : KP);
+  for (int size = 2; size <= SP; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = lane; t < KP / 2; t += 32) {
+      for (int t = lane; t < SP / 2; t += 32) {
         const int lo = 2 * t - (t & (stride - 1));
         const int hi = lo + stride;
         const bool asc = (lo & size) == 0;

@@ -45,6 +45,7 @@ struct Params {
   float* row_loss;                // [N] l_i * w_i
   float* row_active;              // [N]
   unsigned int* sync;             // [0] barrier counter, [1] done counter
+  unsigned long long* trace;      // [8] globaltimer stamps of CTA 0 at the phase boundaries (diagnostics, ~free)
   int NBI, NBJ, Npad;
 };
 
@@ -115,6 +116,14 @@ __device__ float seq_sqdist(const float* __restrict__ a, const float* __restrict
   return acc;
 }
 
+__device__ __forceinline__ void stamp(const Params& p, int slot) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[slot] = t;
+  }
+}
+
 template <int MI, int MJ>
 __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
   constexpr int TI = 8 * MI, TJ = 16 * MJ;
@@ -138,6 +147,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
   const int ti = t >> 4, tj = t & 15;
   const unsigned int G = gridDim.x;
 
+  stamp(p, 0);
   // ---- zero this CTA's slice of dE (ordered before phase 2 by the grid barrier)
   if (p.dE) {
     const int64_t total = int64_t(N) * D;
@@ -171,6 +181,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
   if (t < TJ) pid_j[t] = j0 + t < N ? p.pids[j0 + t] : 0.f;
   __syncthreads();
 
+  stamp(p, 1);
   // ---- phase 1a: MI x MJ squared distances per thread, difference form
   float acc[MI][MJ];
 #pragma unroll
@@ -195,6 +206,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
       }
   }
 
+  stamp(p, 2);
   // ---- phase 1b: masked row reductions over this tile's columns
 #pragma unroll
   for (int a = 0; a < MI; ++a) {
@@ -248,7 +260,9 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
     }
   }
 
+  stamp(p, 3);
   grid_barrier(&p.sync[0], G);
+  stamp(p, 4);
 
   // ---- phase 2a: W = sum_i (#negatives_i) * [pid_i != 0], exact in integers (every CTA, fixed order)
   {
@@ -273,6 +287,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
     return wn / Wf;
   };
 
+  stamp(p, 5);
   // ---- phase 2b: row owners -- one warp per row, fixed combine order over the NBJ partials
   {
     const int warp = t >> 5, lane = t & 31;
@@ -428,6 +443,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
     }
   }
 
+  stamp(p, 6);
   // ---- last CTA: deterministic sum of the per-row terms
   __threadfence();
   __syncthreads();
@@ -458,6 +474,11 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
       p.sync[1] = 0;   // next launch (contract: zero-filled before the first call, left zero-filled by every call)
     }
     for (int i = t; i < N; i += THREADS) p.same_cnt[i] = 0;
+    if (t == 0) {
+      unsigned long long tt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+      p.trace[7] = tt;
+    }
   }
 }
 
@@ -522,6 +543,7 @@ static Layout compute_layout(int64_t N, int64_t D) {
   for (int x = 0; x < 8; ++x) L.off_tab[x] = take(tab);
   L.off_row_loss = take(size_t(N) * 4);
   L.off_row_active = take(size_t(N) * 4);
+  L.off_trace = take(64);
   L.total_bytes = off;
   L.smem_bytes = smem_for(L.TI, L.TJ, D);
   return L;
@@ -569,6 +591,7 @@ int run(int kind, const float* E, const float* pids, int64_t N, int64_t D, int s
   p.p_ca = reinterpret_cast<int*>(b + L.off_tab[6]); p.p_cb = reinterpret_cast<int*>(b + L.off_tab[7]);
   p.row_loss = reinterpret_cast<float*>(b + L.off_row_loss);
   p.row_active = reinterpret_cast<float*>(b + L.off_row_active);
+  p.trace = reinterpret_cast<unsigned long long*>(b + L.off_trace);
   p.NBI = L.NBI; p.NBJ = L.NBJ; p.Npad = L.Npad;
 
   void* args[] = {const_cast<Params*>(&p)};

@@ -9,7 +9,7 @@ namespace loss {
 
 struct Layout {
   int shape, TI, TJ, NBI, NBJ, Npad;
-  size_t off_sync, off_same, zero_bytes, off_tab[8], off_row_loss, off_row_active, total_bytes, smem_bytes;
+  size_t off_sync, off_same, zero_bytes, off_tab[8], off_row_loss, off_row_active, off_trace, total_bytes, smem_bytes;
 };
 // Workspace layout for a batch of N rows of width D (grid shape depends on the device: pass its co-resident CTA capacity).
 Layout make_layout(int64_t N, int64_t D);
