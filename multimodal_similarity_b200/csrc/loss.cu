@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -501,6 +502,10 @@ static const void* kernel_for(int shape) {
 
 // Pick the smallest tile whose grid fits co-resident on the device (a cooperative launch requires it).
 static int pick_shape(int64_t N, int64_t D) {
+  if (const char* e = getenv("MMSIM_LOSS_SHAPE")) {   // experiment switch: force tile shape 0 / 1 / 2
+    const int s = atoi(e);
+    if (s >= 0 && s <= 2) return s;
+  }
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;

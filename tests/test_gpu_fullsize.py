@@ -116,12 +116,10 @@ def test_cfg1_cfg2_losses_at_config_size_are_consistent():
         out = fn(x, pids, margin)
         out[0].backward()
         g = x.grad
-        torch.manual_seed(0)
-        v = torch.randn_like(e)
-        v /= v.norm()
+        v = g / g.norm()                      # steepest direction: the directional derivative is ||g||, well above fp32 noise
         eps = 1e-3
         lp = float(fn(e + eps * v, pids, margin)[0])
         lm = float(fn(e - eps * v, pids, margin)[0])
         fd = (lp - lm) / (2 * eps)
         an = float((g * v).sum())
-        assert an == pytest.approx(fd, rel=2e-2, abs=2e-4), (kind, an, fd)
+        assert an > 0 and an == pytest.approx(fd, rel=2e-2), (kind, an, fd)
