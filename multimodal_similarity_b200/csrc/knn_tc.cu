@@ -108,7 +108,8 @@ struct SweepArgs {
   // MODE_SWEEP: item = (split, query block); contiguous tile range per split
   int n_splits, tiles_per_split;
   int use_pivots;            // 0: threshold +inf (everything is logged; small galleries)
-  int flags;                 // experiment switches (MMSIM_SWEEP_FLAGS): 1 = release TMEM after the scan instead of before
+  int flags;                 // experiment switches (MMSIM_SWEEP_FLAGS): 1 = release TMEM after the scan instead of before,
+                             // 2 = never log a candidate (fast path only), 4 = skip the scan (TMEM drain only); 2/4 give wrong results
   uint2* log;                // [(row * n_splits + split) * logcap] {key bits, gallery row}
   int logcap;
   int* log_cnt;              // [row * n_splits + split] entries appended (may exceed logcap: overflow)
@@ -161,8 +162,8 @@ __device__ __forceinline__ uint32_t atoms_add32(uint32_t addr, uint32_t v) {
 }
 
 // Per-row state word (one native 32-bit shared atomic per candidate; a 64-bit shared add would be a CAS loop):
-//   bits [ 0,14)  log cursor          bits [14,23)  logged entries below ladder pivot 1 (8th smallest sampled key)
-//   bits [23,32)  logged entries below ladder pivot 0 (4th smallest sampled key)
+//   bits [ 0,14)  log cursor          bits [14,23)  logged entries below ladder pivot 1 (6th smallest sampled key)
+//   bits [23,32)  logged entries below ladder pivot 0 (3rd smallest sampled key)
 // A counter only moves while its pivot is still below the row threshold, so it stays below KPT + one tile of columns
 // (< 512); the cursor is kept below 2^14 by closing the row (threshold = -inf) once its log is full.
 constexpr uint32_t CUR_MASK = 0x3FFFu;
@@ -360,7 +361,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         float tau0 = kInf;
         if (a.use_pivots) {
           const float4 pp = *reinterpret_cast<const float4*>(a.ladder + size_t(grow) * 4);
-          piv0 = pp.y; piv1 = pp.z; tau0 = pp.w;        // 4th / 8th / 16th smallest sampled key
+          piv0 = pp.y; piv1 = pp.z; tau0 = pp.w;        // 3rd / 6th / 12th smallest sampled key
         }
         // A finished sweep of another gallery split of the same query ended with a threshold that is usually much
         // tighter than the sampled one: start from it.  Items are ordered split-major, so with more query blocks than
@@ -390,6 +391,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
       // one 32-column chunk of the accumulator, already in registers
       auto scan_chunk = [&](float (&v)[32], int c, uint32_t nrm, int col0) {
+        if (a.flags & 4) return;                       // experiment: accumulator drain only
         // early out on the raw accumulator: key_j = acc_j + |g_j|^2 >= acc_j + (min |g|^2 over the 8-column group)
         const float tau = MODE == MODE_SWEEP ? s_tau[row] : pv_thr;
         const float4 nm8 = lds_f32x4(nrm + (BN + c * 4) * 4);
@@ -400,7 +402,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                        fminf(v[g * 8 + 6], v[g * 8 + 7]));
         const uint32_t mine = (gm[0] < tau - nm8.x ? 1u : 0u) | (gm[1] < tau - nm8.y ? 2u : 0u) |
                               (gm[2] < tau - nm8.z ? 4u : 0u) | (gm[3] < tau - nm8.w ? 8u : 0u);
-        if (!__any_sync(0xffffffffu, mine != 0)) return;
+        if (!__any_sync(0xffffffffu, mine != 0) || (a.flags & 2)) return;   // flags & 2: experiment, never log
         const uint32_t groups = __reduce_or_sync(0xffffffffu, mine);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -515,17 +517,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------ threshold ladder
-// piv16 -> ladder: the 2nd / 4th / 8th smallest sampled keys and, as the initial threshold, the 16th (or the largest
-// finite one when the sample was tiny).  A separate step so that the gallery-sharded path can first merge the shards'
-// lists into the list of the whole gallery's sample (all shards then filter with the same per-query threshold).
+// piv16 -> ladder.  The sample is about 1/64 of the gallery, so the j-th smallest sampled key has about 64 j gallery rows
+// below it (Gamma(j) spread).  Initial threshold = 12th smallest (768 expected, P(fewer than 128) ~ 1e-6; or the largest
+// finite key when the sample was tiny), ladder pivots = 6th and 3rd smallest (384 / 192 expected): the sweep moves the
+// threshold down a rung once KPT logged rows lie below it.  A separate step so that the gallery-sharded path can first
+// merge the shards' lists into the list of the whole gallery's sample (all shards then use the same thresholds).
 __global__ void make_ladder_kernel(const float* __restrict__ piv16, int rows, float* __restrict__ ladder) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const float* m = piv16 + size_t(r) * NPIV;
   float top = m[0];
-  for (int i = 1; i < NPIV; ++i) top = m[i] < kInf ? m[i] : top;
+  for (int i = 1; i < 12; ++i) top = m[i] < kInf ? m[i] : top;
   *reinterpret_cast<float4*>(ladder + size_t(r) * 4) =
-      make_float4(m[1] < top ? m[1] : -kInf, m[3] < top ? m[3] : -kInf, m[7] < top ? m[7] : -kInf, top);
+      make_float4(-kInf, m[2] < top ? m[2] : -kInf, m[5] < top ? m[5] : -kInf, top);
 }
 
 __global__ void fill_f32_kernel(float* __restrict__ p, int64_t n, float v) {

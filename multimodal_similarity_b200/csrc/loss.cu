@@ -117,6 +117,31 @@ __device__ float seq_sqdist(const float* __restrict__ a, const float* __restrict
   return acc;
 }
 
+// Combine one row's NBJ online-logsumexp partials in the fixed order b = 0 .. NBJ-1.  Loads are issued eight partials
+// at a time, ahead of the (sequential) merges, so a row costs NBJ/8 memory round trips instead of NBJ.
+__device__ __forceinline__ void combine_lse_row(const Params& p, int i, Lse& lp, Lse& ln) {
+  lp = Lse{-kInf, 0.f};
+  ln = Lse{-kInf, 0.f};
+  constexpr int B = 8;
+  for (int b0 = 0; b0 < p.NBJ; b0 += B) {
+    float va[B], vb[B], vc[B], vd[B];
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      const bool in = b0 + u < p.NBJ;
+      const int slot = (in ? b0 + u : 0) * p.Npad + i;
+      va[u] = in ? __ldcg(&p.p_a[slot]) : -kInf;
+      vb[u] = in ? __ldcg(&p.p_b[slot]) : 0.f;
+      vc[u] = in ? __ldcg(&p.p_c[slot]) : -kInf;
+      vd[u] = in ? __ldcg(&p.p_d[slot]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < B; ++u) {
+      lp = lse_merge(lp, Lse{va[u], vb[u]});
+      ln = lse_merge(ln, Lse{vc[u], vd[u]});
+    }
+  }
+}
+
 __device__ __forceinline__ void stamp(const Params& p, int slot) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long t;
@@ -159,23 +184,39 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
   {
     const int Q4 = D4 >> 2;                       // float4 slots per row
     const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.E) & 15) == 0);
-    for (int r = t / Q4, c4 = t % Q4; r < TI + TJ; r += THREADS / Q4 > 0 ? THREADS / Q4 : 1) {
-      // (THREADS / Q4 == 0 only for D > 512, which run() rejects)
-      const bool is_i = r < TI;
-      const int gr = is_i ? i0 + r : j0 + (r - TI);
-      float* dst = (is_i ? Ei + r * DP : Ej + (r - TI) * DP) + c4 * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gr < N) {
-        const float* src = p.E + size_t(gr) * D + c4 * 4;
-        if (vec) {
-          v = *reinterpret_cast<const float4*>(src);
-        } else {
-          const int c = c4 * 4;
-          v.x = c + 0 < D ? src[0] : 0.f; v.y = c + 1 < D ? src[1] : 0.f;
-          v.z = c + 2 < D ? src[2] : 0.f; v.w = c + 3 < D ? src[3] : 0.f;
+    // all loads of a batch are issued before the first store so that they overlap (one memory round trip per batch)
+    const int total4 = (TI + TJ) * Q4;
+    constexpr int UNR = 4;
+    for (int base = t; base < total4; base += THREADS * UNR) {
+      float4 v[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int x = base + u * THREADS;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x < total4) {
+          const int r = x / Q4, c4 = x - r * Q4;
+          const int gr = r < TI ? i0 + r : j0 + (r - TI);
+          if (gr < N) {
+            const float* src = p.E + size_t(gr) * D + c4 * 4;
+            if (vec) {
+              v[u] = *reinterpret_cast<const float4*>(src);
+            } else {
+              const int c = c4 * 4;
+              v[u].x = c + 0 < D ? src[0] : 0.f; v[u].y = c + 1 < D ? src[1] : 0.f;
+              v[u].z = c + 2 < D ? src[2] : 0.f; v[u].w = c + 3 < D ? src[3] : 0.f;
+            }
+          }
         }
       }
-      *reinterpret_cast<float4*>(dst) = v;
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int x = base + u * THREADS;
+        if (x < total4) {
+          const int r = x / Q4, c4 = x - r * Q4;
+          float* dst = (r < TI ? Ei + r * DP : Ej + (r - TI) * DP) + c4 * 4;
+          *reinterpret_cast<float4*>(dst) = v[u];
+        }
+      }
     }
   }
   if (t < TI) pid_i[t] = i0 + t < N ? p.pids[i0 + t] : 0.f;
@@ -368,13 +409,9 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
           }
         }
       } else {
-        Lse lp{-kInf, 0.f}, ln{-kInf, 0.f};
+        Lse lp, ln;
         if (lane == 0) {
-          for (int b = 0; b < p.NBJ; ++b) {  // sequential: the tile CTAs below combine in the same order
-            const int slot = b * p.Npad + i;
-            lp = lse_merge(lp, Lse{__ldcg(&p.p_a[slot]), __ldcg(&p.p_b[slot])});
-            ln = lse_merge(ln, Lse{__ldcg(&p.p_c[slot]), __ldcg(&p.p_d[slot])});
-          }
+          combine_lse_row(p, i, lp, ln);     // same fixed order as the tile CTAs below: identical bits
           const float fp = lse_value(lp), cn = lse_value(ln);
           const float l = (cn > -kInf) ? fmaxf(fp + cn, 0.f) : 0.f;
           p.diff[i] = l; p.w[i] = wi; p.fp[i] = fp; p.cn[i] = cn;
@@ -393,12 +430,8 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
       const int i = r < TI ? i0 + r : j0 + (r - TI);
       float fp = 0.f, cn = -kInf, coef = 0.f;
       if (i < N) {
-        Lse lp{-kInf, 0.f}, ln{-kInf, 0.f};
-        for (int b = 0; b < p.NBJ; ++b) {
-          const int slot = b * p.Npad + i;
-          lp = lse_merge(lp, Lse{__ldcg(&p.p_a[slot]), __ldcg(&p.p_b[slot])});
-          ln = lse_merge(ln, Lse{__ldcg(&p.p_c[slot]), __ldcg(&p.p_d[slot])});
-        }
+        Lse lp, ln;
+        combine_lse_row(p, i, lp, ln);
         fp = lse_value(lp);
         cn = lse_value(ln);
         coef = (cn > -kInf && fp + cn >= 0.f) ? weight_of(i) : 0.f;  // w_i * [l_i active]
