@@ -372,10 +372,18 @@ def main():
     except OSError:
         pass
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        ent = tr.get(f"knn_tc_kernel q={Q} g={G} d={D} k={k} gpus={world}")
+        traffic = ent["traffic_bytes"] if ent else None
+    except (OSError, ValueError, KeyError):
+        pass
     flops = 2.0 * Q * (hi - lo) * D
     achieved = flops / (ms_tc / 1e3) / 1e12
     roofline = {"bound": "tensor", "kernel": "knn_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "DRAM bytes per launch from the ncu --set full capture summarised in profiles/r1_traffic.json (null: no capture for this config)",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)",
                 "kernel_ms": ms_tc, "other_kernels_ms": phase_ms,
                 "algorithmic_flops_per_launch": flops}
@@ -389,6 +397,20 @@ def main():
     }
 
     if rank == 0 and world == 1 and not a.no_extras:
+        try:   # BASELINE configs[4] as written (256-d): same workload at the wider embedding
+            g2 = synth_torch(G, 256, WORKLOAD["clusters"], SEED, dev)
+            q2 = synth_torch(Q, 256, WORKLOAD["clusters"], SEED + 1, dev)
+            o2 = knn_raw(q2, g2, k)
+            for _ in range(2):
+                knn_raw(q2, g2, k, out=o2)
+            m2, _ = timed(lambda: knn_raw(q2, g2, k, out=o2), 3)
+            mk, _ = timed(lambda: knn_raw(q2, g2, k, phases=2, out=o2), 3)
+            result["also_dim256"] = {"value": Q * 3 / (m2 / 1e3), "unit": "queries/s", "ms_per_step": m2 / 3, "kernel_ms": mk / 3,
+                                     "roofline_frac": 2.0 * Q * G * 256 / (mk / 3 / 1e3) / 1e12 / peak,
+                                     "exact_fallback_queries": check_status(o2[2])}
+            del g2, q2, o2
+        except Exception as e:  # noqa: BLE001
+            result["also_dim256_error"] = repr(e)[:200]
         try:
             result.update(time_losses(torch, mm))
         except Exception as e:  # noqa: BLE001

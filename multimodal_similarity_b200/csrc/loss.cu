@@ -86,6 +86,11 @@ __device__ __forceinline__ Lse lse_merge(Lse a, Lse b) {
 }
 __device__ __forceinline__ float lse_value(Lse a) { return a.s > 0.f ? a.m + logf(a.s) : -kInf; }
 
+__device__ __noinline__ void barrier_timeout() {
+  printf("mmsim: loss grid barrier timed out\n");
+  __trap();
+}
+
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int expected) {
   __threadfence();
   __syncthreads();
@@ -97,10 +102,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
       unsigned int v;
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
       if (v >= expected) break;
-      if (clock64() - t0 > 4000000000LL) {
-        printf("mmsim: loss grid barrier timed out\n");
-        __trap();
-      }
+      if (clock64() - t0 > 4000000000LL) barrier_timeout();
     }
   }
   __syncthreads();
@@ -108,8 +110,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 
 // distance of row i to row j in the tile kernel's arithmetic (sequential fmaf over d) -- used by the tie path so
 // that equality tests against the mined extreme reproduce bit for bit
-__device__ float seq_sqdist(const float* __restrict__ a, const float* __restrict__ b, int D) {
+__device__ __noinline__ float seq_sqdist(const float* __restrict__ a, const float* __restrict__ b, int D) {
   float acc = 0.f;
+#pragma unroll 1
   for (int d = 0; d < D; ++d) {
     const float x = a[d] - b[d];
     acc = fmaf(x, x, acc);
@@ -142,6 +145,35 @@ __device__ __forceinline__ void combine_lse_row(const Params& p, int i, Lse& lp,
   }
 }
 
+// Rare path of the batch-hard gradient, out of line: exact distance ties.  TF splits the gradient of reduce_max /
+// reduce_min evenly over the tied entries (math_grad._MinOrMaxGrad).  One warp; distances are recomputed in the tile
+// kernel's arithmetic so the equality tests against the mined extremes reproduce bit for bit.
+__device__ __noinline__ void bh_tie_backward(const Params& p, int i, int lane, float c, float fp, float cn, bool use_pos,
+                                             int n_pos_ties, int n_neg_ties) {
+  const int N = p.N, D = p.D;
+  const float* ei = p.E + size_t(i) * D;
+#pragma unroll 1
+  for (int j = 0; j < N; ++j) {
+    if (j == i) continue;
+    const bool same_id = __ldcg(&p.pids[j]) == __ldcg(&p.pids[i]);
+    float dist = 0.f;
+    if (lane == 0) dist = seq_sqdist(ei, p.E + size_t(j) * D, D);
+    dist = __shfl_sync(0xffffffffu, dist, 0);
+    float g = 0.f;
+    if (same_id && use_pos && dist == fp) g = c / float(n_pos_ties);
+    if (!same_id && dist == cn) g = -c / float(n_neg_ties);
+    if (g != 0.f) {
+      const float* ej = p.E + size_t(j) * D;
+#pragma unroll 1
+      for (int d = lane; d < D; d += 32) {
+        const float dv = 2.f * g * (ei[d] - ej[d]);
+        atomicAdd(&p.dE[size_t(i) * D + d], dv);
+        atomicAdd(&p.dE[size_t(j) * D + d], -dv);
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void stamp(const Params& p, int slot) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long t;
@@ -150,7 +182,9 @@ __device__ __forceinline__ void stamp(const Params& p, int slot) {
   }
 }
 
-template <int MI, int MJ>
+// KIND (0 batch-hard, 1 lifted) is a template parameter: the kernel runs once per SM with cold instruction caches, so
+// dead code of the other loss is pure instruction-fetch latency.
+template <int MI, int MJ, int KIND>
 __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
   constexpr int TI = 8 * MI, TJ = 16 * MJ;
   extern __shared__ __align__(16) float sm[];
@@ -265,7 +299,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
       const bool pos = same_id && (i != j);
       const float dist = acc[a][b];
       same += same_id ? 1 : 0;
-      if (p.kind == 0) {
+      if (KIND == 0) {
         if (pos) hp = arg_max(hp, Arg{dist, j, 1});
         if (!same_id) hn = arg_min(hn, Arg{dist, j, 1});
       } else {
@@ -277,7 +311,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) {
       same += __shfl_xor_sync(0xffffffffu, same, o);
-      if (p.kind == 0) {
+      if (KIND == 0) {
         Arg o1{__shfl_xor_sync(0xffffffffu, hp.v, o), __shfl_xor_sync(0xffffffffu, hp.i, o), __shfl_xor_sync(0xffffffffu, hp.c, o)};
         Arg o2{__shfl_xor_sync(0xffffffffu, hn.v, o), __shfl_xor_sync(0xffffffffu, hn.i, o), __shfl_xor_sync(0xffffffffu, hn.c, o)};
         hp = arg_max(hp, o1);
@@ -291,7 +325,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
     }
     if (tj == 0 && i < N) {
       const int slot = bj * p.Npad + i;
-      if (p.kind == 0) {
+      if (KIND == 0) {
         p.p_a[slot] = hp.v; p.p_ia[slot] = hp.i; p.p_ca[slot] = hp.c;
         p.p_b[slot] = hn.v; p.p_ib[slot] = hn.i; p.p_cb[slot] = hn.c;
       } else {
@@ -336,7 +370,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
     for (int i = blockIdx.x * (THREADS / 32) + warp; i < N; i += G * (THREADS / 32)) {
       const float wi = weight_of(i);
       const float fg = __ldcg(&p.pids[i]) != 0.f ? 1.f : 0.f;
-      if (p.kind == 0) {
+      if (KIND == 0) {
         Arg hp{-1.f, -1, 0}, hn{kInf, -1, 0};
         if (lane < p.NBJ) {
           const int slot = lane * p.Npad + i;
@@ -387,25 +421,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
               atomicAdd(&p.dE[size_t(hn.i) * D + d], 2.f * c * (vi - vn));
             }
           } else {
-            // exact ties: TF splits the gradient evenly over the tied entries (math_grad._MinOrMaxGrad)
-            for (int j = 0; j < N; ++j) {
-              if (j == i) continue;
-              const bool same_id = __ldcg(&p.pids[j]) == __ldcg(&p.pids[i]);
-              float dist = 0.f;
-              if (lane == 0) dist = seq_sqdist(ei, p.E + size_t(j) * D, D);
-              dist = __shfl_sync(0xffffffffu, dist, 0);
-              float g = 0.f;
-              if (same_id && use_pos && dist == fp) g = c / float(hp.c);
-              if (!same_id && dist == cn) g = -c / float(hn.c);
-              if (g != 0.f) {
-                const float* ej = p.E + size_t(j) * D;
-                for (int d = lane; d < D; d += 32) {
-                  const float dv = 2.f * g * (ei[d] - ej[d]);
-                  atomicAdd(&p.dE[size_t(i) * D + d], dv);
-                  atomicAdd(&p.dE[size_t(j) * D + d], -dv);
-                }
-              }
-            }
+            bh_tie_backward(p, i, lane, c, fp, cn, use_pos, hp.c, hn.c);
           }
         }
       } else {
@@ -424,7 +440,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
   }
 
   // ---- phase 2c (lifted): dense gradient from the distances still held in registers
-  if (p.kind == 1 && p.dE) {
+  if (KIND == 1 && p.dE) {
     // stats of the TI rows (as anchors) and the TJ rows (as anchors of the transposed entries)
     for (int r = t; r < TI + TJ; r += THREADS) {
       const int i = r < TI ? i0 + r : j0 + (r - TI);
@@ -503,7 +519,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
     }
     if (t == 0) {
       *p.loss = s_l[0];
-      *p.num_active = p.kind == 0 ? s_a[0] / s_f[0] : 1.0f;
+      *p.num_active = KIND == 0 ? s_a[0] / s_f[0] : 1.0f;
       p.sync[0] = 0;   // every CTA has passed the barrier and finished phase 2: leave the workspace ready for the
       p.sync[1] = 0;   // next launch (contract: zero-filled before the first call, left zero-filled by every call)
     }
@@ -525,11 +541,14 @@ static size_t smem_for(int TI, int TJ, int64_t D) {
   return size_t(TI + TJ) * (D4 + 4) * 4 + size_t(TI + TJ) * 4 + size_t(3) * (TI + TJ) * 4 + size_t(TI) * (TJ + 1) * 4;
 }
 
-static const void* kernel_for(int shape) {
-  switch (shape) {
-    case 0: return reinterpret_cast<const void*>(loss_kernel<2, 2>);
-    case 1: return reinterpret_cast<const void*>(loss_kernel<4, 4>);
-    default: return reinterpret_cast<const void*>(loss_kernel<8, 8>);
+static const void* kernel_for(int shape, int kind) {
+  switch (shape * 2 + kind) {
+    case 0: return reinterpret_cast<const void*>(loss_kernel<2, 2, 0>);
+    case 1: return reinterpret_cast<const void*>(loss_kernel<2, 2, 1>);
+    case 2: return reinterpret_cast<const void*>(loss_kernel<4, 4, 0>);
+    case 3: return reinterpret_cast<const void*>(loss_kernel<4, 4, 1>);
+    case 4: return reinterpret_cast<const void*>(loss_kernel<8, 8, 0>);
+    default: return reinterpret_cast<const void*>(loss_kernel<8, 8, 1>);
   }
 }
 
@@ -552,8 +571,12 @@ static int pick_shape(int64_t N, int64_t D) {
     const int64_t grid = ((N + TI - 1) / TI) * ((N + TJ - 1) / TJ);
     int per_sm = 0;
     if (num_sms > 0) {
-      cudaFuncSetAttribute(kernel_for(s), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_for(s), THREADS, smem) != cudaSuccess) per_sm = 0;
+      int per_kind[2] = {0, 0};
+      for (int kd = 0; kd < 2; ++kd) {
+        cudaFuncSetAttribute(kernel_for(s, kd), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_kind[kd], kernel_for(s, kd), THREADS, smem) != cudaSuccess) per_kind[kd] = 0;
+      }
+      per_sm = per_kind[0] < per_kind[1] ? per_kind[0] : per_kind[1];
     } else {
       per_sm = int((227 * 1024) / (smem + 1024));  // no device (layout queries on a CPU box): assume 148 SMs
     }
@@ -597,7 +620,9 @@ Layout make_layout(int64_t N, int64_t D) {
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   Layout L = compute_layout(N, D);
-  if (L.shape >= 0) cudaFuncSetAttribute(kernel_for(L.shape), cudaFuncAttributeMaxDynamicSharedMemorySize, int(L.smem_bytes));
+  if (L.shape >= 0)
+    for (int kd = 0; kd < 2; ++kd)
+      cudaFuncSetAttribute(kernel_for(L.shape, kd), cudaFuncAttributeMaxDynamicSharedMemorySize, int(L.smem_bytes));
   cache.emplace(key, L);
   return L;
 }
@@ -634,7 +659,7 @@ int run(int kind, const float* E, const float* pids, int64_t N, int64_t D, int s
 
   void* args[] = {const_cast<Params*>(&p)};
   const dim3 grid(unsigned(L.NBI * L.NBJ)), block(THREADS);
-  const void* fn = kernel_for(L.shape);
+  const void* fn = kernel_for(L.shape, kind);
   MMSIM_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, grid, block, args, L.smem_bytes, stream));
   return MMSIM_OK;
 }
