@@ -127,6 +127,11 @@ MMSIM_API int mmsim_knn_shard_f32(const float* Q, int64_t nq, const float* G, in
                         int64_t self_offset, float* out_dist, int32_t* out_idx, float* out_lb, int32_t* status, void* ws,
                         size_t ws_bytes, mmsim_stream_t stream, int phases);
 MMSIM_API int mmsim_knn_pivot_region(int64_t nq, int64_t ng, int64_t D, int k, size_t* offset, size_t* bytes);
+/* Introspection (tests): the launch geometry chosen for a problem on a device with num_sms SMs.
+ * out[0..12) = padded width, K atoms, 128-query blocks, 256-row gallery tiles, gallery splits, tiles per split, grid,
+ * log capacity per (query, split), pivot pre-pass used, sampled tiles, sampled columns per tile, workspace bytes,
+ * [12], [13] (if n_out >= 14): workspace offsets of the per-(query, split) candidate counts (int32) and final thresholds. */
+MMSIM_API int mmsim_knn_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, int64_t* out, int n_out);
 MMSIM_API int mmsim_knn_merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t rows, float* out,
                            mmsim_stream_t stream);
 MMSIM_API int mmsim_knn_merge_certified(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride,

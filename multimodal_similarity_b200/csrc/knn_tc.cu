@@ -92,7 +92,6 @@ __global__ void __launch_bounds__(BN) pack_min_kernel(float* __restrict__ pack) 
 }
 
 // ------------------------------------------------------------------------------------------------ fused kernel
-constexpr int NS = 4;                      // gallery smem stages (one K atom of one tile each)
 constexpr int NT = 4;                      // norm-pack ring slots
 constexpr int A_ATOM_BYTES = BM * 128;     // 16 KiB
 constexpr int B_STAGE_BYTES = BN * 128;    // 32 KiB
@@ -123,6 +122,7 @@ struct SweepArgs {
 
 template <int KATOMS>
 struct Smem {
+  static constexpr int NS = KATOMS <= 2 ? 5 : 4;               // gallery smem stages (one 32 KiB K atom of one tile each)
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = A_OFF + KATOMS * A_ATOM_BYTES;
   static constexpr int NORM_OFF = B_OFF + NS * B_STAGE_BYTES;
@@ -217,6 +217,7 @@ template <int KATOMS, int NEPI, int MODE>
 __global__ void __launch_bounds__(64 + NEPI * 32, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_g, const SweepArgs a) {
   using S = Smem<KATOMS>;
+  constexpr int NS = S::NS;
   constexpr int NH = NEPI / 4;            // epilogue warps per TMEM lane quarter; each takes every NH-th 32-column chunk
   constexpr int EPI_THREADS = NEPI * 32;
   // No static shared memory in this kernel, so the dynamic window starts at the CTA's shared base and the declared
@@ -362,6 +363,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         if (a.use_pivots) {
           const float4 pp = *reinterpret_cast<const float4*>(a.ladder + size_t(grow) * 4);
           piv0 = pp.y; piv1 = pp.z; tau0 = pp.w;        // 3rd / 6th / 12th smallest sampled key
+          if (a.flags & 8) tau0 = piv1;                  // experiments: start lower on the ladder (more fallbacks)
+          if (a.flags & 16) tau0 = piv0;
         }
         // A finished sweep of another gallery split of the same query ended with a threshold that is usually much
         // tighter than the sampled one: start from it.  Items are ordered split-major, so with more query blocks than
@@ -857,6 +860,10 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
       best_eff = eff;
       best_s = s_eff;
     }
+  }
+  if (const char* e = getenv("MMSIM_KNN_SPLITS")) {   // experiment switch
+    const int v = atoi(e);
+    if (v >= 1 && v <= 16) best_s = std::min(v, p.n_tiles);
   }
   p.n_splits = best_s;
   p.tiles_per_split = (p.n_tiles + p.n_splits - 1) / p.n_splits;

@@ -149,3 +149,24 @@ def test_random_shape_sweep(rs):
         kk = min(k, ng)
         ref_d, ref_i = O.knn(q, g, kk)
         assert_knn_equal(dist[:, :kk], idx[:, :kk], ref_d, ref_i)
+
+
+@pytest.mark.parametrize("normalize", [True, False])
+def test_unclustered_data_certifies(normalize):
+    """Isotropic Gaussian data: distances concentrate, so the tcgen05 filter has the least slack.  The certificate must
+    still pass for (nearly) every query, and the results must be exact either way."""
+    from multimodal_similarity_b200.retrieval import knn_raw, check_status
+    gen = torch.Generator(device="cuda"); gen.manual_seed(5)
+    g = torch.randn(200_000, 128, generator=gen, device="cuda")
+    q = torch.randn(4096, 128, generator=gen, device="cuda")
+    if normalize:
+        g = g / g.norm(dim=1, keepdim=True)
+        q = q / q.norm(dim=1, keepdim=True)
+    g, q = g.contiguous(), q.contiguous()
+    d, i, status = knn_raw(q, g, 100)
+    fb = check_status(status)
+    print("normalize", normalize, "exact-fallback queries:", fb)
+    assert fb <= 40
+    rows = [0, 1, 77, 4095]
+    ref_d, ref_i = O.knn(q[rows].cpu().numpy(), g.cpu().numpy(), 100)
+    assert_knn_equal(d[rows].cpu().numpy(), i[rows].cpu().numpy().astype(np.int64), ref_d, ref_i)
