@@ -138,6 +138,20 @@ MMSIM_API int mmsim_knn_merge_certified(const float* dist_parts, const int32_t* 
                               const int64_t* idx_base, int parts, int64_t nq, int k_in, int k, const float* lb_parts,
                               int64_t lb_stride, float* out_dist, int64_t* out_idx, int32_t* status, mmsim_stream_t stream);
 
+/* Semi-hard (FaceNet) negative mining -- the inner test of utils.select_triplets_facenet (src/utils.py:474-480) for m
+ * (anchor, positive) pairs at once.  dist is the [n, n] distance matrix (row pitch ld, e.g. from mmsim_sqdist_f32),
+ * labels[n] the int()-converted labels (:445), pairs[2*i], pairs[2*i+1] = anchor, positive.  Row j is a semi-hard
+ * negative of pair i iff labels[j] != labels[anchor] (the NaN mask of :475), pos_dist < dist[anchor, j] and
+ * fl32(dist[anchor, j] - pos_dist) < alpha (:477-478).  count[i] = how many there are (the reference's len(all_neg));
+ * mask (nullable) gets the set itself: bit b of mask[i * ceil(n/32) + w] is row 32 w + b. */
+MMSIM_API int mmsim_semihard_mask_f32(const float* dist, int64_t n, int64_t ld, const int32_t* labels, const int32_t* pairs,
+                            int64_t m, float alpha, uint32_t* mask, int32_t* count, mmsim_stream_t stream);
+
+/* The reference's all_neg[r] (src/utils.py:484) for p picks: picks[3*i .. 3*i+2] = anchor, positive, r;
+ * neg_idx[i] = row of the r-th (0-based, ascending row order = np.where order) semi-hard negative, -1 if r >= count. */
+MMSIM_API int mmsim_semihard_pick_f32(const float* dist, int64_t n, int64_t ld, const int32_t* labels, const int32_t* picks,
+                            int64_t p, float alpha, int32_t* neg_idx, mmsim_stream_t stream);
+
 /* Leave-one-out retrieval evaluation -- the loop body of utils.evaluate / utils.evaluate_simple
  * (src/utils.py:83-229) for the query rows listed in `queries` (the rows with label > 0, :114,171).
  * labels[N] are the raw int32 labels, cls[N] their dense class ids in [0, C).  Per query q (row i = queries[q]):

@@ -6,6 +6,7 @@ Function-level drop-ins for the reference's leaf functions (same names, argument
     losses     batch_hard / lifted_loss (fused forward + backward)                 src/networks.py:797-870
     retrieval  retrieve / retrieve_one / evaluate / evaluate_simple /
                recall_at_K / precision_at_recall / late_fusion                     src/utils.py:55-266
+    mining     select_triplets_facenet (semi-hard negatives counted and picked on device)  src/utils.py:430-496
     sharded    ShardedGallery (gallery rows split over ranks, NCCL merge)          (new)
 
 Everything runs through the C-ABI library libmmsim.so (include/mmsim.h); there is no CPU fallback.
@@ -17,6 +18,7 @@ from .retrieval import (  # noqa: F401
     average_precision, evaluate, evaluate_simple, full_ranking, late_fusion, precision_at_recall, recall_at_K, retrieve,
     retrieve_one,
 )
+from .mining import select_triplets_facenet, semihard_counts  # noqa: F401
 from .sharded import ShardedGallery  # noqa: F401
 
 __version__ = "0.1.0"

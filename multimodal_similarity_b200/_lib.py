@@ -33,6 +33,9 @@ SIGNATURES = {
     "mmsim_knn_merge_pivots": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
     "mmsim_knn_merge_certified": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_int, c_void_p,
                                           c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmsim_semihard_mask_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p,
+                                        c_void_p]),
+    "mmsim_semihard_pick_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p]),
     "mmsim_evaluate_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_double, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmsim_knn_merge": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

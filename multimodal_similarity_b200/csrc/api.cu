@@ -11,6 +11,7 @@
 #include "knn.h"
 #include "loss.h"
 #include "merge.h"
+#include "mining.h"
 #include "sqdist.h"
 
 namespace mmsim {
@@ -129,6 +130,16 @@ MMSIM_API int mmsim_knn_merge_certified(const float* dist_parts, const int32_t* 
                               int64_t lb_stride, float* out_dist, int64_t* out_idx, int32_t* status, mmsim_stream_t stream) {
   return merge::run(dist_parts, idx_parts, part_stride, idx_base, parts, nq, k_in, k, lb_parts, lb_stride, out_dist, out_idx,
                     status, reinterpret_cast<cudaStream_t>(stream));
+}
+
+MMSIM_API int mmsim_semihard_mask_f32(const float* dist, int64_t n, int64_t ld, const int32_t* labels, const int32_t* pairs,
+                            int64_t m, float alpha, uint32_t* mask, int32_t* count, mmsim_stream_t stream) {
+  return mining::run_mask(dist, n, ld, labels, pairs, m, alpha, mask, count, reinterpret_cast<cudaStream_t>(stream));
+}
+
+MMSIM_API int mmsim_semihard_pick_f32(const float* dist, int64_t n, int64_t ld, const int32_t* labels, const int32_t* picks,
+                            int64_t p, float alpha, int32_t* neg_idx, mmsim_stream_t stream) {
+  return mining::run_pick(dist, n, ld, labels, picks, p, alpha, neg_idx, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
