@@ -56,23 +56,34 @@ def config_of(a, n_gpus):
 
 
 # ----------------------------------------------------------------------------------------------- synthetic data
-def synth_numpy(n, dim, clusters, seed):
-    """Cluster centroids + noise, L2-normalised."""
-    rs = np.random.RandomState(seed)
-    cent = rs.randn(clusters, dim).astype(np.float32)
+def synth_numpy(n, dim, clusters, seed, centroid_seed=None):
+    """Cluster centroids + noise, L2-normalised.  Gallery and queries are drawn from the SAME
+    mixture: both calls pass the same centroid_seed and different sample seeds."""
+    cent = np.random.RandomState(seed if centroid_seed is None else centroid_seed).randn(clusters, dim).astype(np.float32)
+    rs = np.random.RandomState(seed + 7919)
     x = cent[rs.randint(0, clusters, size=n)] + 0.5 * rs.randn(n, dim).astype(np.float32)
     x /= np.linalg.norm(x, axis=1, keepdims=True)
     return x.astype(np.float32)
 
 
-def synth_torch(n, dim, clusters, seed, device):
+def synth_torch(n, dim, clusters, seed, device, centroid_seed=None, return_labels=False):
     import torch
+    gc = torch.Generator(device=device)
+    gc.manual_seed(seed if centroid_seed is None else centroid_seed)
+    cent = torch.randn(clusters, dim, generator=gc, device=device)
     g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    cent = torch.randn(clusters, dim, generator=g, device=device)
+    g.manual_seed(seed + 7919)
     lab = torch.randint(0, clusters, (n,), generator=g, device=device)
     x = cent[lab] + 0.5 * torch.randn(n, dim, generator=g, device=device)
-    return (x / x.norm(dim=1, keepdim=True)).contiguous()
+    x = (x / x.norm(dim=1, keepdim=True)).contiguous()
+    return (x, lab) if return_labels else x
+
+
+def synth_pair_torch(n_gallery, n_queries, dim, clusters, seed, device, return_labels=False):
+    """Gallery and queries of the benchmark: one mixture (centroids from `seed`), independent samples."""
+    g = synth_torch(n_gallery, dim, clusters, seed, device, centroid_seed=seed)
+    q = synth_torch(n_queries, dim, clusters, seed + 1, device, centroid_seed=seed, return_labels=return_labels)
+    return (g, q[0], q[1]) if return_labels else (g, q)
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -148,8 +159,8 @@ def run_reference(a):
         return
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, 32))
-    g = synth_numpy(a.gallery, a.dim, WORKLOAD["clusters"], SEED)
-    q = synth_numpy(4 * threads, a.dim, WORKLOAD["clusters"], SEED + 1)
+    g = synth_numpy(a.gallery, a.dim, WORKLOAD["clusters"], SEED, centroid_seed=SEED)
+    q = synth_numpy(4 * threads, a.dim, WORKLOAD["clusters"], SEED + 1, centroid_seed=SEED)
     per_step = threads  # bounded sample of the 100k-query batch: one query per worker thread per step
     for _ in range(max(1, min(a.warmup, 2))):
         cpu_queries_per_s(q, g, per_step, threads)
@@ -251,7 +262,7 @@ def main():
     gallery_full = synth_torch(G, D, WORKLOAD["clusters"], SEED, dev)
     shard = gallery_full[lo:hi].clone()
     del gallery_full
-    queries = synth_torch(Q, D, WORKLOAD["clusters"], SEED + 1, dev)
+    queries = synth_torch(Q, D, WORKLOAD["clusters"], SEED + 1, dev, centroid_seed=SEED)   # same mixture as the gallery
     sg = ShardedGallery(shard, presharded=True, row_offset=lo, total_rows=G)
     torch.cuda.synchronize()
 
@@ -399,7 +410,7 @@ def main():
     if rank == 0 and world == 1 and not a.no_extras:
         try:   # BASELINE configs[4] as written (256-d): same workload at the wider embedding
             g2 = synth_torch(G, 256, WORKLOAD["clusters"], SEED, dev)
-            q2 = synth_torch(Q, 256, WORKLOAD["clusters"], SEED + 1, dev)
+            q2 = synth_torch(Q, 256, WORKLOAD["clusters"], SEED + 1, dev, centroid_seed=SEED)
             o2 = knn_raw(q2, g2, k)
             for _ in range(2):
                 knn_raw(q2, g2, k, out=o2)

@@ -6,7 +6,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmsim.so")
+LIB_PATH = os.environ.get("MMSIM_LIB") or os.path.join(_HERE, "libmmsim.so")   # MMSIM_LIB: experiment builds
 
 METRICS = {"squaredeuclidean": 0, "euclidean": 1, "l1": 2}
 LOSS_BATCH_HARD, LOSS_LIFTED = 0, 1

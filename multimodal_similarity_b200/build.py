@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libmmsim.so")
+LIB = os.environ.get("MMSIM_LIB_OUT") or os.path.join(HERE, "libmmsim.so")
 SOURCES = ["api.cu", "knn_tc.cu", "loss.cu", "sqdist.cu", "merge.cu", "eval.cu", "mining.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
@@ -42,6 +42,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         objs.append(obj)
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        if os.environ.get("MMSIM_DEBUG_BUILD") == "1":      # experiment counters in the kNN sweep (scripts/sweep_debug.py)
+            cmd.insert(1, "-DMMSIM_SWEEP_DEBUG")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

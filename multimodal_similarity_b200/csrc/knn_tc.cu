@@ -18,12 +18,16 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
 #include "exact.cuh"
 #include "knn.h"
 #include "ptx.cuh"
+
+// the ablation instantiations of the sweep (ABL != 0) return early from the scan on purpose
+#pragma nv_diag_suppress 128
 
 namespace mmsim {
 namespace knn {
@@ -34,47 +38,77 @@ constexpr int BN = 256;                    // gallery rows per tile (UMMA N)
 constexpr int KATOM = 64;                  // fp16 elements per 128-byte swizzle atom
 constexpr int NPACK = 320;                 // floats per gallery tile in the norm pack: 256 norms | 32 min8 | 8 min32 | pad
 
-// One warp per row.  xh[row, 0..Dp) = fp16(x) * scale (zero padded), norm = sum fp16(x)^2 (unscaled, fp32),
+// One warp per row, grid-stride.  xh[row, 0..Dp) = fp16(x) * scale (zero padded), norm = sum fp16(x)^2 (unscaled, fp32),
 // err[row] = ||x - fp16(x)||_2.  With tile_pack != 0 (gallery) the norm goes to the per-tile pack
 // norm[(row / 256) * 320 + row % 256] and rows in [n, n_pad) get +inf (masks padded gallery columns).
-__global__ void prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int D, int Dp, float scale,
-                                 __half* __restrict__ xh, float* __restrict__ norm, float* __restrict__ err, int tile_pack,
-                                 unsigned int* __restrict__ max_stats /* [0]=max err bits, [1]=max norm bits, or null */) {
-  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+// HBM-bound: 4 D bytes read + 2 Dp bytes written per row; a lane moves 16 bytes in / 8 bytes out per step when
+// D % 4 == 0 (VEC), and the running maxima reach global memory as ONE atomic pair per block.
+constexpr int PREP_THREADS = 256;
+
+template <bool VEC>
+__global__ void __launch_bounds__(PREP_THREADS)
+prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int D, int Dp, float scale,
+                 __half* __restrict__ xh, float* __restrict__ norm, float* __restrict__ err, int tile_pack,
+                 unsigned int* __restrict__ max_stats /* [0]=max err bits, [1]=max norm bits, or null */) {
   const uint32_t lane = threadIdx.x & 31;
-  if (row >= n_pad) return;
-  const int64_t nslot = tile_pack ? (row / BN) * NPACK + (row % BN) : row;
-  if (row >= n) {
-    if (lane == 0) norm[nslot] = kInf;
-    return;
-  }
-  const float* xr = x + row * D;
-  __half* hr = xh + row * Dp;
-  float s = 0.f, e = 0.f;
-  for (int c = lane; c < Dp; c += 32) {
-    float v = c < D ? xr[c] : 0.f;
-    const __half h = __float2half_rn(v);
-    const float r = __half2float(h);
-    s = fmaf(r, r, s);
-    const float d = v - r;
-    e = fmaf(d, d, e);
-    hr[c] = __float2half_rn(r * scale);  // scale is a power of two: exact unless it overflows (then err = inf below)
-    if (isinf(r * scale) || isinf(r)) e = kInf;
-  }
+  const int64_t warp0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float max_e = 0.f, max_s = 0.f;
+  for (int64_t row = warp0; row < n_pad; row += nwarps) {
+    const int64_t nslot = tile_pack ? (row / BN) * NPACK + (row % BN) : row;
+    if (row >= n) {
+      if (lane == 0) norm[nslot] = kInf;
+      continue;
+    }
+    const float* xr = x + row * D;
+    __half* hr = xh + row * Dp;
+    float s = 0.f, e = 0.f;
+    auto one = [&](float v) {
+      const __half h = __float2half_rn(v);
+      const float r = __half2float(h);
+      s = fmaf(r, r, s);
+      const float d = v - r;
+      e = fmaf(d, d, e);
+      const __half o = __float2half_rn(r * scale);  // scale is a power of two: exact unless it overflows (then err = inf)
+      if (isinf(r * scale) || isinf(r)) e = kInf;
+      return o;
+    };
+    if (VEC) {
+      for (int c = lane * 4; c < Dp; c += 128) {
+        const float4 v = c < D ? __ldcs(reinterpret_cast<const float4*>(xr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const __half2 lo = __halves2half2(one(v.x), one(v.y)), hi = __halves2half2(one(v.z), one(v.w));
+        uint2 w;
+        w.x = *reinterpret_cast<const uint32_t*>(&lo);
+        w.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(hr + c) = w;
+      }
+    } else {
+      for (int c = lane; c < Dp; c += 32) hr[c] = one(c < D ? xr[c] : 0.f);
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    e += __shfl_xor_sync(0xffffffffu, e, o);
-  }
-  if (lane == 0) {
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      e += __shfl_xor_sync(0xffffffffu, e, o);
+    }
     // inflate by a few ulps so the values are upper bounds despite fp32 summation error
     const float en = sqrtf(e) * 1.0001f;
-    norm[nslot] = s;
-    if (err) err[row] = en;
-    if (max_stats) {
-      atomicMax(&max_stats[0], __float_as_uint(en));
-      atomicMax(&max_stats[1], __float_as_uint(s));
+    if (lane == 0) {
+      norm[nslot] = s;
+      if (err) err[row] = en;
     }
+    max_e = fmaxf(max_e, en);    // NaN-free: e >= 0 or +inf
+    max_s = fmaxf(max_s, s);
+  }
+  if (max_stats) {
+    __shared__ unsigned int sm[2];
+    if (threadIdx.x < 2) sm[threadIdx.x] = 0u;
+    __syncthreads();
+    if (lane == 0) {
+      atomicMax(&sm[0], __float_as_uint(max_e));   // non-negative floats order like their bit patterns
+      atomicMax(&sm[1], __float_as_uint(max_s));
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) atomicMax(&max_stats[threadIdx.x], sm[threadIdx.x]);
   }
 }
 
@@ -101,19 +135,29 @@ constexpr int KPT = KP;                    // candidates that must lie below a p
 
 enum { MODE_PIVOT = 0, MODE_SWEEP = 1 };
 
+// Experiment counters (MMSIM_DEBUG_BUILD=1 builds only; scripts/sweep_debug.py): [5] 8-column groups handed to the
+// candidate path, [6] epilogue warp cycles (sum over warps), [7] 32-column warp chunks with a hit
+#ifdef MMSIM_SWEEP_DEBUG
+__device__ unsigned long long g_dbg[8];
+#define DBG_ADD(i, v) atomicAdd(&g_dbg[i], (unsigned long long)(v))
+#else
+#define DBG_ADD(i, v) ((void)0)
+#endif
+
 struct SweepArgs {
   const float* gpack;        // [n_tiles][NPACK]
   int nq, n_qblocks, n_tiles;
   // MODE_SWEEP: item = (split, query block); contiguous tile range per split
   int n_splits, tiles_per_split;
   int use_pivots;            // 0: threshold +inf (everything is logged; small galleries)
-  int flags;                 // experiment switches (MMSIM_SWEEP_FLAGS): 1 = release TMEM after the scan instead of before,
-                             // 2 = never log a candidate (fast path only), 4 = skip the scan (TMEM drain only); 2/4 give wrong results
+  int close_rows;            // experiment (MMSIM_SWEEP_FLAGS=8): every row starts closed (threshold -inf): the product
+                             // kernel's fast path with no candidate ever found (wrong results)
   uint2* log;                // [(row * n_splits + split) * logcap] {key bits, gallery row}
   int logcap;
   int* log_cnt;              // [row * n_splits + split] entries appended (may exceed logcap: overflow)
   float* log_tau;            // [row * n_splits + split] final threshold of the sweep
-  int* split_done;           // [row * n_splits + split] 1 once log_tau is published (later splits start from it)
+  int* split_done;           // [row * n_splits + split] bit 0: log_tau is published (later splits start from it);
+                             // bits [1,16) / [16,31): rows this split logged below ladder rung piv1 / piv0
   // MODE_PIVOT: item = query block; n_sample_tiles evenly spaced tiles, first sample_cols columns of each
   int n_sample_tiles, sample_cols;
   float* piv16;              // MODE_PIVOT out: [row][16] the smallest sampled keys, ascending (+inf where missing)
@@ -170,7 +214,10 @@ constexpr uint32_t CUR_MASK = 0x3FFFu;
 constexpr int CN1_SHIFT = 14, CN0_SHIFT = 23;
 
 // Rare path of the sweep, out of line to keep the hot loop small: the 8 keys of one column group that has at least one
-// candidate in the warp.  Every key below the row threshold is appended to the row's log.
+// candidate in the warp.  Every key below the row threshold is appended to the row's log: ONE native 32-bit shared
+// atomic claims the slot and bumps the ladder counters, one 8-byte store.
+// (Tried and dropped, both slower on B200: a logger warp fed through shared-memory queues -- a single consumer saturates,
+// gpurun_out/sweep_debug.log -- and warp-private candidate rings drained in batches, gpurun_out/grouped_ring.log.)
 __device__ __noinline__ void sweep_group8(float k0, float k1, float k2, float k3, float k4, float k5, float k6, float k7,
                                           int cbase, float tau, float piv0, float piv1, uint2* mylog, int logcap,
                                           uint32_t cnt_addr, uint32_t tau_addr) {
@@ -213,8 +260,10 @@ __device__ __forceinline__ int tile_of(const SweepArgs& a, int t0, int i) {
   return int((int64_t(2 * i + 1) * a.n_tiles) / (2 * a.n_sample_tiles));
 }
 
-template <int KATOMS, int NEPI, int MODE>
-__global__ void __launch_bounds__(64 + NEPI * 32, 1)
+// ABL: ablation variants for scripts/sweep_ablate.py (wrong results by construction): 0 = product, 2 = never log a
+// candidate (first-level test only), 4 = drain the accumulator without scanning it.
+template <int KATOMS, int NEPI, int MODE, int ABL>
+__global__ void __launch_bounds__(128 + NEPI * 32, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_g, const SweepArgs a) {
   using S = Smem<KATOMS>;
   constexpr int NS = S::NS;
@@ -278,6 +327,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     }
   };
 
+  const uint32_t wg = __shfl_sync(0xffffffffu, threadIdx.x >> 7, 0);   // warpgroup, provably uniform
+  if (wg == 0) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // =============================================================== TMA producer (one thread)
     if (lane == 0) {
@@ -340,13 +392,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       if (lane == 0) ptx::umma_commit(aempty);
       __syncwarp();
     }
+  }
   } else {
     // =============================================================== epilogue warps: TMEM -> candidates
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const uint32_t q = warp & 3;              // TMEM lane quarter this warp may read
-    const uint32_t h = (warp - 2) >> 2;       // which of the NH warps of this quarter
+    const uint32_t h = (warp - 4) >> 2;       // which of the NH warps of this quarter
     const int row = q * 32 + lane;            // row of the CTA tile == TMEM lane
     const uint32_t ring_u32 = ptx::smem_u32(norm_ring);
+#ifdef MMSIM_SWEEP_DEBUG
+    const long long t_epi0 = clock64();
+#endif
     uint32_t tc = 0;
+
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int qb, split, t0, nt;
       item_range(item, qb, split, t0, nt);
@@ -354,36 +412,41 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       const bool valid = grow < a.nq;
 
       float piv0 = -kInf, piv1 = -kInf;                 // MODE_SWEEP: ladder below the initial threshold
+      uint32_t carry = 0;                               // MODE_SWEEP: rows finished splits logged below piv1 | piv0 << 15
       float pv_thr = kInf;                              // MODE_PIVOT: current NPIV-th smallest sampled key of the row
-      uint2* mylog = nullptr;
-      const uint32_t cnt_addr = ptx::smem_u32(s_cnt + row), tau_addr = ptx::smem_u32(s_tau + row);
+      const uint32_t tau_addr = ptx::smem_u32(s_tau + row), cnt_addr = ptx::smem_u32(s_cnt + row);
+      uint2* const mylog = a.log + (size_t(grow) * a.n_splits + split) * a.logcap;
       const uint32_t pv_addr = ptx::smem_u32(s_pv + (h * NPSUB) * BM + row);
       if (MODE == MODE_SWEEP) {
         float tau0 = kInf;
         if (a.use_pivots) {
           const float4 pp = *reinterpret_cast<const float4*>(a.ladder + size_t(grow) * 4);
-          piv0 = pp.y; piv1 = pp.z; tau0 = pp.w;        // 3rd / 6th / 12th smallest sampled key
-          if (a.flags & 8) tau0 = piv1;                  // experiments: start lower on the ladder (more fallbacks)
-          if (a.flags & 16) tau0 = piv0;
+          piv0 = pp.y; piv1 = pp.z; tau0 = pp.w;        // ladder rungs and initial threshold (make_ladder_kernel)
         }
         // A finished sweep of another gallery split of the same query ended with a threshold that is usually much
         // tighter than the sampled one: start from it.  Items are ordered split-major, so with more query blocks than
         // SMs the earlier splits of this block finished waves ago.  (Thresholds only steer how many candidates are
         // kept; the certificate in the rerank kernel bounds every unlogged row by the smallest threshold in force.)
+        // It also publishes how many rows it logged below each rung: the ladder counters continue across splits instead
+        // of restarting (a split on its own rarely sees KPT rows below the lower rung).
         for (int s2 = 0; s2 < a.n_splits; ++s2) {
           if (s2 == split) continue;
           const size_t o = size_t(grow) * a.n_splits + s2;
-          int done;
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.split_done + o) : "memory");
-          if (done) tau0 = fminf(tau0, __ldcg(a.log_tau + o));
+          uint32_t done;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(a.split_done + o) : "memory");
+          if (done) {
+            tau0 = fminf(tau0, __ldcg(a.log_tau + o));
+            carry += done >> 1;                // two 15-bit fields, each at most 511 per split and at most 8 splits
+          }
         }
+        carry = min(carry & 0x7fffu, uint32_t(KPT)) | (min(carry >> 15, uint32_t(KPT)) << 15);
+        if (a.close_rows) tau0 = -kInf;
         epi_bar_sync(EPI_THREADS);             // every epilogue warp is done with the previous item
         if (h == 0) {
           s_tau[row] = valid ? tau0 : -kInf;   // rows past the last query never accept a candidate
-          s_cnt[row] = 0u;
+          s_cnt[row] = ((carry & 0x7fffu) << CN1_SHIFT) | ((carry >> 15) << CN0_SHIFT);
         }
         epi_bar_sync(EPI_THREADS);
-        mylog = a.log + (size_t(grow) * a.n_splits + split) * a.logcap;
       } else {
         static_assert(MODE == MODE_SWEEP || NH <= 4, "pivot sub-lists are laid out for at most 4 warps per quarter");
         epi_bar_sync(EPI_THREADS);             // the previous item's merge has read every sub-list
@@ -392,34 +455,50 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         for (int i = 0; i < NPSUB; ++i) s_pv[(h * NPSUB + i) * BM + row] = pv_thr;
       }
 
-      // one 32-column chunk of the accumulator, already in registers
-      auto scan_chunk = [&](float (&v)[32], int c, uint32_t nrm, int col0) {
-        if (a.flags & 4) return;                       // experiment: accumulator drain only
-        // early out on the raw accumulator: key_j = acc_j + |g_j|^2 >= acc_j + (min |g|^2 over the 8-column group)
-        const float tau = MODE == MODE_SWEEP ? s_tau[row] : pv_thr;
-        const float4 nm8 = lds_f32x4(nrm + (BN + c * 4) * 4);
+      // One 32-column chunk of the accumulator, already in registers.  Level 1 (every chunk): minimum of the raw
+      // accumulator over the chunk against tau - (smallest |g|^2 of the chunk): key_j = acc_j + |g_j|^2 >= acc_j + min |g|^2,
+      // so no key of the chunk can be below tau when the test fails -- 18 FMNMX3, one LDS, one FADD, one FSETP, one vote
+      // per 32 columns.  Level 2 (warp has a hit): the same test per 8-column group.  Level 3 (out of line): the 8 keys.
+      auto scan_chunk = [&](float (&v)[32], int c, uint32_t nrm, int col0, float tau) {
+        if (ABL == 4) return;
         float gm[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           gm[g] = min3(min3(v[g * 8], v[g * 8 + 1], v[g * 8 + 2]), min3(v[g * 8 + 3], v[g * 8 + 4], v[g * 8 + 5]),
                        fminf(v[g * 8 + 6], v[g * 8 + 7]));
-        const uint32_t mine = (gm[0] < tau - nm8.x ? 1u : 0u) | (gm[1] < tau - nm8.y ? 2u : 0u) |
-                              (gm[2] < tau - nm8.z ? 4u : 0u) | (gm[3] < tau - nm8.w ? 8u : 0u);
-        if (!__any_sync(0xffffffffu, mine != 0) || (a.flags & 2)) return;   // flags & 2: experiment, never log
-        const uint32_t groups = __reduce_or_sync(0xffffffffu, mine);
+        const float m = fminf(min3(gm[0], gm[1], gm[2]), gm[3]);
+        const float nm32 = lds_f32(nrm + (BN + 32 + c) * 4);
+        const float bound = tau - nm32;
+        if (!__any_sync(0xffffffffu, m < bound) || ABL == 2) return;
+        if (MODE == MODE_SWEEP) {
+          // Level 2 (warp has a hit): the same test per 8-column group; level 3 (out of line): the 8 keys of a group.
+          // (The query operand was pre-scaled by -2: acc = -2 q.g, key = |g|^2 - 2 q.g.)
+          const float4 nm8 = lds_f32x4(nrm + (BN + c * 4) * 4);
+          const uint32_t mine = (gm[0] < tau - nm8.x ? 1u : 0u) | (gm[1] < tau - nm8.y ? 2u : 0u) |
+                                (gm[2] < tau - nm8.z ? 4u : 0u) | (gm[3] < tau - nm8.w ? 8u : 0u);
+          const uint32_t groups = __reduce_or_sync(0xffffffffu, mine);
+          if (lane == 0) { DBG_ADD(7, 1); DBG_ADD(5, __popc(groups)); }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (!(groups & (1u << g))) continue;
-          const float4 n0 = lds_f32x4(nrm + (c * 32 + g * 8) * 4);
-          const float4 n1 = lds_f32x4(nrm + (c * 32 + g * 8 + 4) * 4);
-          // the query operand was pre-scaled by -2, so acc = -2 q.g and key = |g|^2 - 2 q.g
-          const float k0 = v[g * 8 + 0] + n0.x, k1 = v[g * 8 + 1] + n0.y, k2 = v[g * 8 + 2] + n0.z, k3 = v[g * 8 + 3] + n0.w;
-          const float k4 = v[g * 8 + 4] + n1.x, k5 = v[g * 8 + 5] + n1.y, k6 = v[g * 8 + 6] + n1.z, k7 = v[g * 8 + 7] + n1.w;
-          if (MODE == MODE_SWEEP) {
-            sweep_group8(k0, k1, k2, k3, k4, k5, k6, k7, col0 + c * 32 + g * 8, tau, piv0, piv1, mylog, a.logcap, cnt_addr,
-                         tau_addr);
-          } else {
-            const float key[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
+          for (int g = 0; g < 4; ++g) {
+            if (!(groups & (1u << g))) continue;
+            const float4 n0 = lds_f32x4(nrm + (c * 32 + g * 8) * 4);
+            const float4 n1 = lds_f32x4(nrm + (c * 32 + g * 8 + 4) * 4);
+            sweep_group8(v[g * 8 + 0] + n0.x, v[g * 8 + 1] + n0.y, v[g * 8 + 2] + n0.z, v[g * 8 + 3] + n0.w,
+                         v[g * 8 + 4] + n1.x, v[g * 8 + 5] + n1.y, v[g * 8 + 6] + n1.z, v[g * 8 + 7] + n1.w,
+                         col0 + c * 32 + g * 8, tau, piv0, piv1, mylog, a.logcap, cnt_addr, tau_addr);
+          }
+        } else {
+          const float4 nm8 = lds_f32x4(nrm + (BN + c * 4) * 4);
+          const uint32_t mine = (gm[0] < tau - nm8.x ? 1u : 0u) | (gm[1] < tau - nm8.y ? 2u : 0u) |
+                                (gm[2] < tau - nm8.z ? 4u : 0u) | (gm[3] < tau - nm8.w ? 8u : 0u);
+          const uint32_t groups = __reduce_or_sync(0xffffffffu, mine);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (!(groups & (1u << g))) continue;
+            const float4 n0 = lds_f32x4(nrm + (c * 32 + g * 8) * 4);
+            const float4 n1 = lds_f32x4(nrm + (c * 32 + g * 8 + 4) * 4);
+            const float key[8] = {v[g * 8 + 0] + n0.x, v[g * 8 + 1] + n0.y, v[g * 8 + 2] + n0.z, v[g * 8 + 3] + n0.w,
+                                  v[g * 8 + 4] + n1.x, v[g * 8 + 5] + n1.y, v[g * 8 + 6] + n1.z, v[g * 8 + 7] + n1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               if (key[j] < pv_thr) pv_thr = pivot_insert(key[j], pv_addr);
@@ -427,51 +506,52 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         }
       };
 
+      const uint32_t taddr0 = tmem_base + ((q * 32) << 16) + h * 32;   // this warp's first chunk of accumulator stage 0
+      constexpr int CPW = (BN / 32) / NH;    // chunks per warp and tile (even)
       for (int i = 0; i < nt; ++i, ++tc) {
-        const int t = tile_of<MODE>(a, t0, i);
         const uint32_t as = tc & 1;
         ptx::mbar_wait(&tfull[as], (tc >> 1) & 1);
         ptx::tc_fence_after();
         const uint32_t nrm = ring_u32 + (tc % NT) * NPACK * 4;
-        const uint32_t taddr = tmem_base + ((q * 32) << 16) + as * BN;
-        const int col0 = t * BN;
+        const uint32_t taddr = taddr0 + as * BN;
+        const int col0 = tile_of<MODE>(a, t0, i) * BN;
         // MODE_PIVOT samples whole tiles or a window of sample_cols/32 chunks per sampled tile (the window rotates over the
         // tile's 8 chunks from one sampled tile to the next, so the epilogue warps share the work)
         const int win = MODE == MODE_PIVOT ? a.sample_cols / 32 : 8, rot = i & 7;
-        auto sampled = [&](int c) { return ((c - rot) & 7) < win; };
-        constexpr int CPW = (BN / 32) / NH;    // chunks per warp and tile (even)
+        auto sampled = [&](int c) { return MODE == MODE_SWEEP || ((c - rot) & 7) < win; };
         // Two register buffers.  Both loads of a pair are issued before either chunk is scanned, and the TMEM stage is
-        // handed back to the MMA warp as soon as this warp's LAST load has landed -- before scanning -- so the next
-        // tile's MMAs never wait on the scan (with 16 epilogue warps a warp owns exactly two chunks per tile).
+        // handed back to the MMA warp as soon as this warp's LAST load has landed -- before anything is scanned: the
+        // MMA warp and the epilogue warps wait on each other once per tile, and whatever sits between the accumulator
+        // becoming ready and its release (a scan, worse: a scan that finds candidates) is on the critical path of the
+        // whole SM (profiles/r1_e_sweep.txt: the MMA warp spends 39% of its time waiting for this release).
         float va[32], vb[32];
-        ptx::tmem_ld32(taddr + h * 32, va);
-        ptx::tmem_ld32(taddr + (h + NH) * 32, vb);
+        ptx::tmem_ld32(taddr, va);
+        ptx::tmem_ld32(taddr + NH * 32, vb);
 #pragma unroll 1
         for (int cp = 0; cp < CPW; cp += 2) {
           const int c0 = h + cp * NH, c1 = c0 + NH;
+          const bool last = cp + 2 >= CPW;
           ptx::tmem_ld_wait(va);
           ptx::tmem_ld_wait(vb);
-          const bool last = cp + 2 >= CPW;
-          if (last && !(a.flags & 1)) {
+          if (last) {
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[as]);
           }
-          if (sampled(c0)) scan_chunk(va, c0, nrm, col0);
-          if (!last) ptx::tmem_ld32(taddr + (c1 + NH) * 32, va);
-          if (sampled(c1)) scan_chunk(vb, c1, nrm, col0);
-          if (!last) ptx::tmem_ld32(taddr + (c1 + 2 * NH) * 32, vb);
-          if (last && (a.flags & 1)) {
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(&tempty[as]);
-          }
+          const float tau = MODE == MODE_SWEEP ? lds_f32(tau_addr) : pv_thr;
+          if (sampled(c0)) scan_chunk(va, c0, nrm, col0, tau);
+          if (!last) ptx::tmem_ld32(taddr + (cp + 2) * NH * 32, va);
+          if (sampled(c1)) scan_chunk(vb, c1, nrm, col0, MODE == MODE_SWEEP ? tau : pv_thr);
+          if (!last) ptx::tmem_ld32(taddr + (cp + 3) * NH * 32, vb);
         }
-        if (MODE == MODE_SWEEP && h == 0) {
-          // tighten: once KPT logged entries lie below a pivot, the KPT smallest keys all lie below it
+        if (MODE == MODE_SWEEP && h == (tc & (NH - 1))) {
+          // tighten (the NH warps of a row take turns): once KPT logged entries lie below a pivot, the KPT smallest
+          // keys all lie below it
           const uint32_t cn = s_cnt[row];
-          float nt_ = s_tau[row];
+          const float ot = s_tau[row];
+          float nt_ = ot;
           if (((cn >> CN1_SHIFT) & 511u) >= KPT) nt_ = fminf(nt_, piv1);
           if (((cn >> CN0_SHIFT) & 511u) >= KPT) nt_ = fminf(nt_, piv0);
-          s_tau[row] = nt_;
+          if (nt_ < ot) s_tau[row] = nt_;
         }
         ptx::mbar_arrive(&nempty[tc % NT]);
       }
@@ -480,13 +560,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         epi_bar_sync(EPI_THREADS);             // all appends of this item are done
         if (h == 0) {
           const size_t o = size_t(grow) * a.n_splits + split;
-          a.log_cnt[o] = int(s_cnt[row] & CUR_MASK);
+          const uint32_t cn = s_cnt[row];
+          a.log_cnt[o] = int(cn & CUR_MASK);
           a.log_tau[o] = s_tau[row];
           if (a.n_splits > 1) {
             // Thresholds only steer how many candidates are kept: the final certificate (rerank kernel) bounds every
             // unlogged row by the smallest threshold in force, so a shared threshold can cost a fallback, never exactness.
+            const uint32_t own1 = ((cn >> CN1_SHIFT) & 511u) - (carry & 0x7fffu), own0 = ((cn >> CN0_SHIFT) & 511u) - (carry >> 15);
             __threadfence();
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.split_done + o), "r"(1) : "memory");
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.split_done + o), "r"(1u | (own1 << 1) | (own0 << 16))
+                         : "memory");
           }
         }
       } else {
@@ -512,6 +595,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         }
       }
     }
+#ifdef MMSIM_SWEEP_DEBUG
+    if (lane == 0) DBG_ADD(6, clock64() - t_epi0);
+#endif
   }
 
   ptx::tc_fence_before();
@@ -521,18 +607,30 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------------ threshold ladder
 // piv16 -> ladder.  The sample is about 1/64 of the gallery, so the j-th smallest sampled key has about 64 j gallery rows
-// below it (Gamma(j) spread).  Initial threshold = 12th smallest (768 expected, P(fewer than 128) ~ 1e-6; or the largest
-// finite key when the sample was tiny), ladder pivots = 6th and 3rd smallest (384 / 192 expected): the sweep moves the
-// threshold down a rung once KPT logged rows lie below it.  A separate step so that the gallery-sharded path can first
-// merge the shards' lists into the list of the whole gallery's sample (all shards then use the same thresholds).
-__global__ void make_ladder_kernel(const float* __restrict__ piv16, int rows, float* __restrict__ ladder) {
+// below it (Gamma(j) spread).  Initial threshold = 12th smallest (768 expected, P(fewer than KPT = 128) ~ 1e-6; or the
+// largest finite key when the sample was tiny), ladder rungs = 6th and 3rd smallest (384 / 192 expected): the sweep moves
+// the threshold down a rung once KPT logged rows lie below it.  MMSIM_LADDER="init,mid,low" overrides the ranks
+// (scripts/ladder_ablate.py: starting at the 8th saves 1.3 ms of a 28 ms sweep but sends ~23 of 100k queries to the exact
+// fallback, which costs more than that; gpurun_out/ladder_ablate.log).  A separate step so
+// that the gallery-sharded path can first merge the shards' lists into the list of the whole gallery's sample (all shards
+// then use the same thresholds).
+struct LadderRanks { int init, mid, low; };
+static LadderRanks ladder_ranks() {
+  LadderRanks r{12, 6, 3};
+  if (const char* e = getenv("MMSIM_LADDER")) {
+    int a = 0, b = 0, c = 0;
+    if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && a >= b && b >= c && c >= 1 && a <= NPIV) r = LadderRanks{a, b, c};
+  }
+  return r;
+}
+__global__ void make_ladder_kernel(const float* __restrict__ piv16, int rows, float* __restrict__ ladder, LadderRanks rk) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const float* m = piv16 + size_t(r) * NPIV;
   float top = m[0];
-  for (int i = 1; i < 12; ++i) top = m[i] < kInf ? m[i] : top;
-  *reinterpret_cast<float4*>(ladder + size_t(r) * 4) =
-      make_float4(-kInf, m[2] < top ? m[2] : -kInf, m[5] < top ? m[5] : -kInf, top);
+  for (int i = 1; i < rk.init; ++i) top = m[i] < kInf ? m[i] : top;
+  const float low = m[rk.low - 1], mid = m[rk.mid - 1];
+  *reinterpret_cast<float4*>(ladder + size_t(r) * 4) = make_float4(-kInf, low < top ? low : -kInf, mid < top ? mid : -kInf, top);
 }
 
 __global__ void fill_f32_kernel(float* __restrict__ p, int64_t n, float v) {
@@ -911,34 +1009,33 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   return p;
 }
 
-// epilogue warps of the sweep (NEPI / 4 per TMEM lane quarter).  16 measured best on B200 (60.6% of the dense bf16 peak
-// vs 47.7% with 8, profiles/); MMSIM_NEPI=8 keeps the smaller variant reachable for experiments.
-static int nepi_sweep() {
-  static int v = 0;
-  if (!v) {
-    const char* e = getenv("MMSIM_NEPI");
-    v = (e && atoi(e) == 8) ? 8 : 16;
-  }
-  return v;
+// Epilogue warps (NEPI / 4 per TMEM lane quarter): 16 measured best on B200 (60.6% of the dense bf16 peak vs 47.7% with 8,
+// profiles/r1_b_log_epilogue_nepi8.txt, r1_c_nepi16.txt).
+constexpr int NEPI_SWEEP = 16;
+
+// MMSIM_SWEEP_FLAGS (scripts/sweep_ablate.py): 2 = never log a candidate, 4 = TMEM drain only.  Ablations, wrong results.
+static int sweep_ablation() {
+  const char* e = getenv("MMSIM_SWEEP_FLAGS");
+  return e ? atoi(e) : 0;
 }
 
-template <int KATOMS, int NEPI, int MODE>
+template <int KATOMS, int NEPI, int MODE, int ABL>
 static int launch_tc(int grid, const CUtensorMap& tq, const CUtensorMap& tg, const SweepArgs& args, cudaStream_t stream) {
   using S = Smem<KATOMS>;
-  auto kern = knn_tc_kernel<KATOMS, NEPI, MODE>;
+  auto kern = knn_tc_kernel<KATOMS, NEPI, MODE, ABL>;
   MMSIM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
-  kern<<<grid, 64 + NEPI * 32, S::DYN_BYTES, stream>>>(tq, tg, args);
+  kern<<<grid, 128 + NEPI * 32, S::DYN_BYTES, stream>>>(tq, tg, args);
   MMSIM_CUDA_CHECK(cudaGetLastError());
   return MMSIM_OK;
 }
 
-template <int MODE, int NEPI>
+template <int MODE, int ABL>
 static int launch_mode(int katoms, int grid, const CUtensorMap& tq, const CUtensorMap& tg, const SweepArgs& args, cudaStream_t s) {
   switch (katoms) {
-    case 1: return launch_tc<1, NEPI, MODE>(grid, tq, tg, args, s);
-    case 2: return launch_tc<2, NEPI, MODE>(grid, tq, tg, args, s);
-    case 3: return launch_tc<3, NEPI, MODE>(grid, tq, tg, args, s);
-    default: return launch_tc<4, NEPI, MODE>(grid, tq, tg, args, s);
+    case 1: return launch_tc<1, NEPI_SWEEP, MODE, ABL>(grid, tq, tg, args, s);
+    case 2: return launch_tc<2, NEPI_SWEEP, MODE, ABL>(grid, tq, tg, args, s);
+    case 3: return launch_tc<3, NEPI_SWEEP, MODE, ABL>(grid, tq, tg, args, s);
+    default: return launch_tc<4, NEPI_SWEEP, MODE, ABL>(grid, tq, tg, args, s);
   }
 }
 
@@ -989,16 +1086,19 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   // 1. operand copies: fp16 rows, norm pack (+ per-8 / per-32 column minima), rounding-error norms
   if (phases & kPhasePrep) {
     MMSIM_CUDA_CHECK(cudaMemsetAsync(gstats, 0, 64, stream));
-    const int threads = 256;
     const int64_t g_pad = int64_t(p.n_tiles) * BN;
-    const int64_t gb = (g_pad * 32 + threads - 1) / threads;
-    prep_rows_kernel<<<unsigned(gb), threads, 0, stream>>>(G, ng, g_pad, int(D), p.Dp, 1.0f, gh, gpack, nullptr, 1,
-                                                           reinterpret_cast<unsigned int*>(gstats));
+    const bool vec = D % 4 == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0;
+    auto prep = vec ? prep_rows_kernel<true> : prep_rows_kernel<false>;
+    const int warps_per_block = PREP_THREADS / 32;
+    const int64_t cap = int64_t(num_sms) * 16;     // grid-stride: a few resident waves, one atomic pair per block
+    const unsigned gb = unsigned(std::min<int64_t>((g_pad + warps_per_block - 1) / warps_per_block, cap));
+    prep<<<gb, PREP_THREADS, 0, stream>>>(G, ng, g_pad, int(D), p.Dp, 1.0f, gh, gpack, nullptr, 1,
+                                          reinterpret_cast<unsigned int*>(gstats));
     MMSIM_CUDA_CHECK(cudaGetLastError());
     pack_min_kernel<<<unsigned(p.n_tiles), BN, 0, stream>>>(gpack);
     MMSIM_CUDA_CHECK(cudaGetLastError());
-    const int64_t qb = (nq * 32 + threads - 1) / threads;
-    prep_rows_kernel<<<unsigned(qb), threads, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, 0, nullptr);
+    const unsigned qb = unsigned(std::min<int64_t>((nq + warps_per_block - 1) / warps_per_block, cap));
+    prep<<<qb, PREP_THREADS, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, 0, nullptr);
     MMSIM_CUDA_CHECK(cudaGetLastError());
   }
 
@@ -1015,7 +1115,6 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     args.nq = int(nq); args.n_qblocks = p.n_qblocks; args.n_tiles = p.n_tiles;
     args.n_splits = p.n_splits; args.tiles_per_split = p.tiles_per_split;
     args.use_pivots = p.use_pivots;
-    { const char* e = getenv("MMSIM_SWEEP_FLAGS"); args.flags = e ? atoi(e) : 0; }
     args.log = log; args.logcap = p.logcap; args.log_cnt = log_cnt; args.log_tau = log_tau; args.split_done = split_done;
     args.n_sample_tiles = p.n_sample_tiles; args.sample_cols = p.sample_cols;
     args.piv16 = piv16; args.ladder = ladder;
@@ -1025,19 +1124,22 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
       MMSIM_CUDA_CHECK(cudaGetLastError());
     }
     if ((phases & kPhasePivot) && p.use_pivots) {
-      rc = launch_mode<MODE_PIVOT, 16>(p.katoms, p.pivot_grid, tq, tg, args, stream);
+      rc = launch_mode<MODE_PIVOT, 0>(p.katoms, p.pivot_grid, tq, tg, args, stream);
       if (rc) return rc;
     }
     if ((phases & kPhaseLadder) && p.use_pivots) {
       const int rows = p.n_qblocks * BM;
-      make_ladder_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(piv16, rows, ladder);
+      make_ladder_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(piv16, rows, ladder, ladder_ranks());
       MMSIM_CUDA_CHECK(cudaGetLastError());
     }
     if (phases & kPhaseTensor) {
       if (p.n_splits > 1)
         MMSIM_CUDA_CHECK(cudaMemsetAsync(split_done, 0, size_t(p.n_qblocks) * BM * p.n_splits * 4, stream));
-      rc = nepi_sweep() == 16 ? launch_mode<MODE_SWEEP, 16>(p.katoms, p.grid, tq, tg, args, stream)
-                              : launch_mode<MODE_SWEEP, 8>(p.katoms, p.grid, tq, tg, args, stream);
+      const int abl = sweep_ablation();
+      args.close_rows = abl == 8;
+      rc = abl == 2   ? launch_mode<MODE_SWEEP, 2>(p.katoms, p.grid, tq, tg, args, stream)
+           : abl == 4 ? launch_mode<MODE_SWEEP, 4>(p.katoms, p.grid, tq, tg, args, stream)
+                      : launch_mode<MODE_SWEEP, 0>(p.katoms, p.grid, tq, tg, args, stream);
       if (rc) return rc;
     }
   }
@@ -1080,3 +1182,17 @@ int merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t ro
 
 }  // namespace knn
 }  // namespace mmsim
+
+#ifdef MMSIM_SWEEP_DEBUG
+// experiment builds only (MMSIM_DEBUG_BUILD=1 python -m multimodal_similarity_b200.build --force); not part of the C-ABI
+extern "C" __attribute__((visibility("default"))) int mmsim_debug_counters(unsigned long long* out, int n, int reset) {
+  unsigned long long h[8] = {};
+  if (cudaMemcpyFromSymbol(h, mmsim::knn::g_dbg, sizeof(h)) != cudaSuccess) return -1;
+  for (int i = 0; i < n && i < 8; ++i) out[i] = h[i];
+  if (reset) {
+    unsigned long long z[8] = {};
+    if (cudaMemcpyToSymbol(mmsim::knn::g_dbg, z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+#endif

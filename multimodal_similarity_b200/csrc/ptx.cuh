@@ -57,7 +57,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a trap (a CUDA error the host reports), never as a hung GPU.
 // The slow path is out of line so the many wait sites stay a TRYWAIT + branch (instruction-cache footprint).
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2-3 s at 1.3-1.9 GHz

@@ -11,7 +11,7 @@ from multimodal_similarity_b200.sharded import ReducedShard, merge_pivots_into, 
 lib = _lib.load()
 dev = torch.device("cuda")
 gfull = synth_torch(1_000_000, 128, 1000, 12345, dev)
-q = synth_torch(100_000, 128, 1000, 12346, dev)
+q = synth_torch(100_000, 128, 1000, 12346, dev, centroid_seed=12345)   # same mixture as the gallery
 
 
 def counts(ws, nq, ng):

@@ -7,7 +7,7 @@ from multimodal_similarity_b200.retrieval import knn_raw, check_status
 
 dev = torch.device("cuda")
 gfull = synth_torch(1_000_000, 128, 1000, 12345, dev)
-q = synth_torch(100_000, 128, 1000, 12346, dev)
+q = synth_torch(100_000, 128, 1000, 12346, dev, centroid_seed=12345)   # same mixture as the gallery
 for G in (1_000_000, 500_000, 250_000, 125_000):
     g = gfull[:G].contiguous()
     for flags in (0, 2, 4):

@@ -7,7 +7,7 @@ from multimodal_similarity_b200.retrieval import knn_raw, check_status
 
 dev = torch.device("cuda")
 g = synth_torch(1_000_000, 128, 1000, 12345, dev)
-q = synth_torch(100_000, 128, 1000, 12346, dev)
+q = synth_torch(100_000, 128, 1000, 12346, dev, centroid_seed=12345)   # same mixture as the gallery
 for S in (0, 1, 2, 3, 4, 6, 8, 12, 16):
     if S:
         os.environ["MMSIM_KNN_SPLITS"] = str(S)
