@@ -39,7 +39,7 @@ constexpr int KATOM = 64;                  // fp16 elements per 128-byte swizzle
 constexpr int NPACK = 320;                 // floats per gallery tile in the norm pack: 256 norms | 32 min8 | 8 min32 | pad
 
 // One warp per row, grid-stride.  xh[row, 0..Dp) = fp16(x) * scale (zero padded), norm = sum fp16(x)^2 (unscaled, fp32),
-// err[row] = ||x - fp16(x)||_2.  With tile_pack != 0 (gallery) the norm goes to the per-tile pack
+// err[row] = ||x - fp16(x)||_2 (row = OUTPUT row).  With tile_pack != 0 (gallery) the norm goes to the per-tile pack
 // norm[(row / 256) * 320 + row % 256] and rows in [n, n_pad) get +inf (masks padded gallery columns).
 // HBM-bound: 4 D bytes read + 2 Dp bytes written per row; a lane moves 16 bytes in / 8 bytes out per step when
 // D % 4 == 0 (VEC), and the running maxima reach global memory as ONE atomic pair per block.
@@ -49,7 +49,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(PREP_THREADS)
 prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int D, int Dp, float scale,
                  __half* __restrict__ xh, float* __restrict__ norm, float* __restrict__ err, int tile_pack,
-                 unsigned int* __restrict__ max_stats /* [0]=max err bits, [1]=max norm bits, or null */) {
+                 unsigned int* __restrict__ max_stats /* [0]=max err bits, [1]=max norm bits, or null */,
+                 const int* __restrict__ gather /* output row r is input row gather[r], or null: identity */) {
   const uint32_t lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -60,7 +61,7 @@ prep_rows_kernel(const float* __restrict__ x, int64_t n, int64_t n_pad, int D, i
       if (lane == 0) norm[nslot] = kInf;
       continue;
     }
-    const float* xr = x + row * D;
+    const float* xr = x + (gather ? int64_t(gather[row]) : row) * D;
     __half* hr = xh + row * Dp;
     float s = 0.f, e = 0.f;
     auto one = [&](float v) {
@@ -133,7 +134,7 @@ constexpr int NPIV = 16;                   // pivot pre-pass: the 16 smallest sa
 constexpr int NPSUB = 8;                   // ... gathered from per-warp sub-lists of 8 (each warp scans a quarter of the columns)
 constexpr int KPT = KP;                    // candidates that must lie below a pivot before it becomes the threshold
 
-enum { MODE_PIVOT = 0, MODE_SWEEP = 1 };
+enum { MODE_PIVOT = 0, MODE_SWEEP = 1, MODE_ASSIGN = 2 };
 
 // Experiment counters (MMSIM_DEBUG_BUILD=1 builds only; scripts/sweep_debug.py): [5] 8-column groups handed to the
 // candidate path, [6] epilogue warp cycles (sum over warps), [7] 32-column warp chunks with a hit
@@ -161,6 +162,7 @@ struct SweepArgs {
   // MODE_PIVOT: item = query block; n_sample_tiles evenly spaced tiles, first sample_cols columns of each
   int n_sample_tiles, sample_cols;
   float* piv16;              // MODE_PIVOT out: [row][16] the smallest sampled keys, ascending (+inf where missing)
+  int* assign;               // MODE_ASSIGN out: [row] nearest row of the (small) "gallery" given -- the query's anchor
   const float* ladder;       // MODE_SWEEP in:  [row][4] = ladder pivots (ascending) and the initial threshold
 };
 
@@ -256,7 +258,7 @@ __device__ __noinline__ float pivot_insert(float x, uint32_t pv_addr) {
 
 template <int MODE>
 __device__ __forceinline__ int tile_of(const SweepArgs& a, int t0, int i) {
-  if (MODE == MODE_SWEEP) return t0 + i;
+  if (MODE != MODE_PIVOT) return t0 + i;
   return int((int64_t(2 * i + 1) * a.n_tiles) / (2 * a.n_sample_tiles));
 }
 
@@ -414,6 +416,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       float piv0 = -kInf, piv1 = -kInf;                 // MODE_SWEEP: ladder below the initial threshold
       uint32_t carry = 0;                               // MODE_SWEEP: rows finished splits logged below piv1 | piv0 << 15
       float pv_thr = kInf;                              // MODE_PIVOT: current NPIV-th smallest sampled key of the row
+      float as_best = kInf;                             // MODE_ASSIGN: smallest key of the row so far in this thread's chunks,
+      int as_col = 0x7fffffff;                          //              and its column
       const uint32_t tau_addr = ptx::smem_u32(s_tau + row), cnt_addr = ptx::smem_u32(s_cnt + row);
       uint2* const mylog = a.log + (size_t(grow) * a.n_splits + split) * a.logcap;
       const uint32_t pv_addr = ptx::smem_u32(s_pv + (h * NPSUB) * BM + row);
@@ -447,12 +451,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           s_cnt[row] = ((carry & 0x7fffu) << CN1_SHIFT) | ((carry >> 15) << CN0_SHIFT);
         }
         epi_bar_sync(EPI_THREADS);
-      } else {
+      } else if (MODE == MODE_PIVOT) {
         static_assert(MODE == MODE_SWEEP || NH <= 4, "pivot sub-lists are laid out for at most 4 warps per quarter");
         epi_bar_sync(EPI_THREADS);             // the previous item's merge has read every sub-list
         pv_thr = valid ? kInf : -kInf;
 #pragma unroll
         for (int i = 0; i < NPSUB; ++i) s_pv[(h * NPSUB + i) * BM + row] = pv_thr;
+      } else {
+        epi_bar_sync(EPI_THREADS);             // the previous item's merge has read every partial result
       }
 
       // One 32-column chunk of the accumulator, already in registers.  Level 1 (every chunk): minimum of the raw
@@ -460,6 +466,17 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       // so no key of the chunk can be below tau when the test fails -- 18 FMNMX3, one LDS, one FADD, one FSETP, one vote
       // per 32 columns.  Level 2 (warp has a hit): the same test per 8-column group.  Level 3 (out of line): the 8 keys.
       auto scan_chunk = [&](float (&v)[32], int c, uint32_t nrm, int col0, float tau) {
+        if (MODE == MODE_ASSIGN) {             // running argmin of key = |g|^2 - 2 q.g over this thread's columns
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 n = lds_f32x4(nrm + (c * 32 + g * 4) * 4);
+            const float k4[4] = {v[g * 4] + n.x, v[g * 4 + 1] + n.y, v[g * 4 + 2] + n.z, v[g * 4 + 3] + n.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (k4[j] < as_best) { as_best = k4[j]; as_col = col0 + c * 32 + g * 4 + j; }   // ascending columns: ties keep the first
+          }
+          return;
+        }
         if (ABL == 4) return;
         float gm[4];
 #pragma unroll
@@ -518,7 +535,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         // MODE_PIVOT samples whole tiles or a window of sample_cols/32 chunks per sampled tile (the window rotates over the
         // tile's 8 chunks from one sampled tile to the next, so the epilogue warps share the work)
         const int win = MODE == MODE_PIVOT ? a.sample_cols / 32 : 8, rot = i & 7;
-        auto sampled = [&](int c) { return MODE == MODE_SWEEP || ((c - rot) & 7) < win; };
+        auto sampled = [&](int c) { return MODE != MODE_PIVOT || ((c - rot) & 7) < win; };
         // Two register buffers.  Both loads of a pair are issued before either chunk is scanned, and the TMEM stage is
         // handed back to the MMA warp as soon as this warp's LAST load has landed -- before anything is scanned: the
         // MMA warp and the epilogue warps wait on each other once per tile, and whatever sits between the accumulator
@@ -572,6 +589,21 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
                          : "memory");
           }
         }
+      } else if (MODE == MODE_ASSIGN) {
+        // merge the NH partial results of a row: smallest (key, column)
+        s_pv[(2 * h) * BM + row] = as_best;
+        reinterpret_cast<int*>(s_pv)[(2 * h + 1) * BM + row] = as_col;
+        epi_bar_sync(EPI_THREADS);
+        if (h == 0 && valid) {
+          float b = kInf;
+          int bc = 0x7fffffff;
+          for (int e = 0; e < NH; ++e) {
+            const float x = s_pv[(2 * e) * BM + row];
+            const int xc = reinterpret_cast<const int*>(s_pv)[(2 * e + 1) * BM + row];
+            if (x < b || (x == b && xc < bc)) { b = x; bc = xc; }
+          }
+          a.assign[grow] = bc == 0x7fffffff ? 0 : bc;
+        }
       } else {
         // merge the NH sub-lists: the ladder is the 2nd / 4th / 8th / 16th smallest of their union.  (A sub-list keeps
         // only 8 keys, so the union can miss a few of the true 16 smallest: the pivots are steering values, not bounds.)
@@ -603,6 +635,81 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// ------------------------------------------------------------------------------------------------ query grouping
+// The sweep tests 32 query rows x 32 gallery columns per warp step, and a step that finds a candidate costs several times
+// a step that finds none.  With queries in arbitrary order about 40% of the steps find one (every query has its own ~700
+// candidates); with similar queries side by side their candidates are the same gallery rows and the share drops to 4%
+// (gpurun_out/sweep_debug2.log) -- 27.0 -> 21.8 ms on the benchmark (gpurun_out/ladder_v4.log).  So the queries are
+// sorted by their nearest ANCHOR before the sweep: anchors = n_anchor evenly spaced query rows, nearest anchor found by
+// the tensor-core kernel in MODE_ASSIGN (the anchors are its "gallery": a few tiles), then a stable counting sort.  The
+// permutation depends on the queries only (deterministic: every gallery shard derives the same one), results are
+// scattered back to the caller's order by the re-rank kernel, and nothing about exactness changes.
+constexpr int GROUP_BLOCK = 1024;          // queries per block of the counting sort
+
+__global__ void anchor_index_kernel(int* __restrict__ idx, int n_anchor, int64_t nq) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_anchor) idx[j] = int((int64_t(j) * nq) / n_anchor);
+}
+
+// blockhist[bin * gridDim.x + block] = queries of this block's chunk assigned to anchor `bin`
+__global__ void __launch_bounds__(GROUP_BLOCK)
+group_hist_kernel(const int* __restrict__ assign, int nq, int n_anchor, int* __restrict__ blockhist) {
+  extern __shared__ int gh_smem[];
+  for (int b = threadIdx.x; b < n_anchor; b += blockDim.x) gh_smem[b] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * GROUP_BLOCK + threadIdx.x;
+  if (i < nq) atomicAdd(&gh_smem[assign[i]], 1);
+  __syncthreads();
+  for (int b = threadIdx.x; b < n_anchor; b += blockDim.x) blockhist[size_t(b) * gridDim.x + blockIdx.x] = gh_smem[b];
+}
+
+// in-place exclusive scan of n ints, one block
+__global__ void __launch_bounds__(1024) group_scan_kernel(int* __restrict__ v, int n) {
+  __shared__ int part[1024];
+  const int per = (n + 1023) / 1024, lo = min(n, int(threadIdx.x) * per), hi = min(n, lo + per);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += v[i];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int x = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __syncthreads();
+    part[threadIdx.x] += x;
+    __syncthreads();
+  }
+  int run = part[threadIdx.x] - sum;
+  for (int i = lo; i < hi; ++i) {
+    const int x = v[i];
+    v[i] = run;
+    run += x;
+  }
+}
+
+// perm[position] = query; stable: queries of one anchor keep their order (warps of a block take turns)
+__global__ void __launch_bounds__(GROUP_BLOCK)
+group_scatter_kernel(const int* __restrict__ assign, int nq, int n_anchor, const int* __restrict__ blockhist, int* __restrict__ perm) {
+  extern __shared__ int gs_smem[];
+  for (int b = threadIdx.x; b < n_anchor; b += blockDim.x) gs_smem[b] = blockhist[size_t(b) * gridDim.x + blockIdx.x];
+  __syncthreads();
+  const int i = blockIdx.x * GROUP_BLOCK + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bin = i < nq ? assign[i] : -1;
+  for (int w = 0; w < GROUP_BLOCK / 32; ++w) {
+    if (warp == w) {
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      int base = 0;
+      if (bin >= 0) base = gs_smem[bin];
+      __syncwarp();
+      if (bin >= 0) {
+        perm[base + rank] = i;
+        if (rank == 0) gs_smem[bin] = base + __popc(peers);
+      }
+    }
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ threshold ladder
@@ -676,19 +783,21 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
                   int n_splits, const float* __restrict__ qnorm, const float* __restrict__ qerr,
                   const float* __restrict__ gstats, float delta_coeff, int k, int kp, int exclude_self, int64_t self_offset,
                   float* __restrict__ out_dist, int* __restrict__ out_idx, float* __restrict__ out_lb,
-                  int* __restrict__ status, int* __restrict__ unc_query, float* __restrict__ unc_bound, int unc_cap) {
+                  int* __restrict__ status, int* __restrict__ unc_query, float* __restrict__ unc_bound, int unc_cap,
+                  const int* __restrict__ perm /* sweep position -> query (query grouping), or null: identity */) {
   // kp <= KP candidates are re-ranked.  out_lb == nullptr: emit the top-k and certify locally (k <= kp).
   // out_lb != nullptr (gallery-shard mode): emit all kp re-ranked candidates (k == kp) plus the lower bound on the
   // true distance of every row of this shard that is NOT among them; the certificate is evaluated after the merge.
   extern __shared__ float rr_smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qi = blockIdx.x * RR_WARPS + warp;
+  const int qi = blockIdx.x * RR_WARPS + warp;       // position in the sweep's order: logs, norms
   if (qi >= nq) return;
+  const int qo = perm ? perm[qi] : qi;                // the caller's query index: Q rows, outputs
   float* qs = rr_smem + warp * (D + 2 * KP);      // query vector, then candidate / sort scratch
   float* sk = qs + D;
   int* sv = reinterpret_cast<int*>(sk + KP);
 
-  for (int c = lane; c < D; c += 32) qs[c] = Q[size_t(qi) * D + c];
+  for (int c = lane; c < D; c += 32) qs[c] = Q[size_t(qo) * D + c];
   for (int c = lane; c < KP; c += 32) { sk[c] = kInf; sv[c] = -1; }
 
   // ---- gather the KP smallest logged keys (all of them when there are fewer)
@@ -751,7 +860,7 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
   const float tau = total > kp ? fminf(tau_min, unsortable(ustar)) : tau_min;
 
   // ---- exact distances (reference arithmetic): 8 lanes per candidate, 4 candidates per round
-  const int self = exclude_self ? int(self_offset + qi) : -1;
+  const int self = exclude_self ? int(self_offset + qo) : -1;
   {
     const int sub = lane & 7, grp = lane >> 3;
 #pragma unroll 1
@@ -791,8 +900,8 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
 
   for (int r = lane; r < k; r += 32) {
     const float d = sk[r];
-    out_dist[size_t(qi) * k + r] = d;
-    out_idx[size_t(qi) * k + r] = (d < kInf) ? sv[r] : -1;
+    out_dist[size_t(qo) * k + r] = d;
+    out_idx[size_t(qo) * k + r] = (d < kInf) ? sv[r] : -1;
   }
 
   // ---- certificate: lower bound on the true distance of every row that is not a candidate
@@ -811,13 +920,13 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
       if (!(lb == lb)) lb = -kInf;    // NaN inputs certify nothing
     }
     if (out_lb) {
-      out_lb[qi] = lb;
+      out_lb[qo] = lb;
     } else {
       const float dk = sk[k - 1];
       if (!(dk < lb)) {
         const int slot = atomicAdd(&status[0], 1);
         if (slot < unc_cap) {
-          unc_query[slot] = qi;
+          unc_query[slot] = qo;
           unc_bound[slot] = dk;
         } else {
           status[2] = 1;
@@ -985,6 +1094,15 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
     p.pivot_grid = std::min(num_sms, p.n_qblocks);
   }
 
+  // query grouping (see "query grouping" above): worth it when the sweep is long and there are enough queries to form
+  // groups of a warp's size around each anchor
+  p.n_anchor = 0;
+  if (p.use_pivots && p.n_tiles >= 256) p.n_anchor = nq >= 65536 ? 4096 : nq >= 16384 ? 2048 : nq >= 4096 ? 1024 : 0;
+  if (const char* e = getenv("MMSIM_KNN_GROUP")) {     // experiment switch: 0 = off
+    if (atoi(e) == 0) p.n_anchor = 0;
+  }
+  p.group_blocks = int((nq + GROUP_BLOCK - 1) / GROUP_BLOCK);
+
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   const size_t q_rows = size_t(p.n_qblocks) * BM;
@@ -1005,6 +1123,12 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   p.off_fb_count = take(size_t(p.unc_cap) * 4);
   p.off_fb_dist = take(size_t(p.unc_cap) * FB_CAP * 4);
   p.off_fb_idx = take(size_t(p.unc_cap) * FB_CAP * 4);
+  p.off_ah = take(size_t(p.n_anchor) * p.Dp * 2);
+  p.off_apack = take(size_t(p.n_anchor / BN + 1) * NPACK * 4);
+  p.off_aidx = take(size_t(p.n_anchor) * 4);
+  p.off_assign = take(p.n_anchor ? q_rows * 4 : 0);
+  p.off_perm = take(p.n_anchor ? q_rows * 4 : 0);
+  p.off_ghist = take(size_t(p.n_anchor) * p.group_blocks * 4);
   p.total_bytes = off;
   return p;
 }
@@ -1077,6 +1201,12 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   int* fb_count = reinterpret_cast<int*>(w + p.off_fb_count);
   float* fb_dist = reinterpret_cast<float*>(w + p.off_fb_dist);
   int* fb_idx = reinterpret_cast<int*>(w + p.off_fb_idx);
+  __half* ah = reinterpret_cast<__half*>(w + p.off_ah);
+  float* apack = reinterpret_cast<float*>(w + p.off_apack);
+  int* aidx = reinterpret_cast<int*>(w + p.off_aidx);
+  int* assign = reinterpret_cast<int*>(w + p.off_assign);
+  int* perm = p.n_anchor ? reinterpret_cast<int*>(w + p.off_perm) : nullptr;
+  int* ghist = reinterpret_cast<int*>(w + p.off_ghist);
 
   if (phases & kPhaseRerank) {
     MMSIM_CUDA_CHECK(cudaMemsetAsync(status, 0, 8 * sizeof(int), stream));
@@ -1093,13 +1223,45 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     const int64_t cap = int64_t(num_sms) * 16;     // grid-stride: a few resident waves, one atomic pair per block
     const unsigned gb = unsigned(std::min<int64_t>((g_pad + warps_per_block - 1) / warps_per_block, cap));
     prep<<<gb, PREP_THREADS, 0, stream>>>(G, ng, g_pad, int(D), p.Dp, 1.0f, gh, gpack, nullptr, 1,
-                                          reinterpret_cast<unsigned int*>(gstats));
+                                          reinterpret_cast<unsigned int*>(gstats), nullptr);
     MMSIM_CUDA_CHECK(cudaGetLastError());
     pack_min_kernel<<<unsigned(p.n_tiles), BN, 0, stream>>>(gpack);
     MMSIM_CUDA_CHECK(cudaGetLastError());
     const unsigned qb = unsigned(std::min<int64_t>((nq + warps_per_block - 1) / warps_per_block, cap));
-    prep<<<qb, PREP_THREADS, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, 0, nullptr);
+    prep<<<qb, PREP_THREADS, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, 0, nullptr, nullptr);
     MMSIM_CUDA_CHECK(cudaGetLastError());
+    if (p.n_anchor) {
+      // query grouping: anchors = evenly spaced query rows -> nearest anchor of every query (tensor cores) -> stable
+      // counting sort -> operand copies of the queries again, in the sweep's order
+      const int a_tiles = p.n_anchor / BN;
+      anchor_index_kernel<<<(p.n_anchor + 255) / 256, 256, 0, stream>>>(aidx, p.n_anchor, nq);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
+      prep<<<unsigned((p.n_anchor + warps_per_block - 1) / warps_per_block), PREP_THREADS, 0, stream>>>(
+          Q, p.n_anchor, p.n_anchor, int(D), p.Dp, 1.0f, ah, apack, nullptr, 1, nullptr, aidx);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
+      CUtensorMap tq0, ta;
+      int rc0 = make_tmap(&tq0, qh, nq, p.Dp, BM);
+      if (rc0) return rc0;
+      rc0 = make_tmap(&ta, ah, p.n_anchor, p.Dp, BN);
+      if (rc0) return rc0;
+      SweepArgs aa{};
+      aa.gpack = apack;
+      aa.nq = int(nq); aa.n_qblocks = p.n_qblocks; aa.n_tiles = a_tiles;
+      aa.n_splits = 1; aa.tiles_per_split = a_tiles;
+      aa.n_sample_tiles = a_tiles; aa.sample_cols = BN;
+      aa.assign = assign;
+      rc0 = launch_mode<MODE_ASSIGN, 0>(p.katoms, std::min(num_sms, p.n_qblocks), tq0, ta, aa, stream);
+      if (rc0) return rc0;
+      const size_t hsm = size_t(p.n_anchor) * 4;
+      group_hist_kernel<<<p.group_blocks, GROUP_BLOCK, hsm, stream>>>(assign, int(nq), p.n_anchor, ghist);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
+      group_scan_kernel<<<1, 1024, 0, stream>>>(ghist, p.n_anchor * p.group_blocks);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
+      group_scatter_kernel<<<p.group_blocks, GROUP_BLOCK, hsm, stream>>>(assign, int(nq), p.n_anchor, ghist, perm);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
+      prep<<<qb, PREP_THREADS, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, 0, nullptr, perm);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
+    }
   }
 
   // 2. pivot pre-pass (sampled gallery tiles) + fused distance / candidate sweep
@@ -1154,7 +1316,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
                                                                p.n_splits, qnorm, qerr, gstats, delta_coeff, shard_kp ? shard_kp : k,
                                                                shard_kp ? shard_kp : KP, exclude_self, self_offset, out_dist,
                                                                out_idx, shard_kp ? out_lb : nullptr, status, unc_query,
-                                                               unc_bound, p.unc_cap);
+                                                               unc_bound, p.unc_cap, perm);
     MMSIM_CUDA_CHECK(cudaGetLastError());
   }
 
