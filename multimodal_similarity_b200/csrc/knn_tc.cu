@@ -467,6 +467,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       // per 32 columns.  Level 2 (warp has a hit): the same test per 8-column group.  Level 3 (out of line): the 8 keys.
       auto scan_chunk = [&](float (&v)[32], int c, uint32_t nrm, int col0, float tau) {
         if (MODE == MODE_ASSIGN) {             // running argmin of key = |g|^2 - 2 q.g over this thread's columns
+          // chunk-level early out like the sweep's: no key of the chunk is below min(acc) + min |g|^2
+          float m = v[0];
+#pragma unroll
+          for (int j = 1; j < 31; j += 2) m = min3(m, v[j], v[j + 1]);
+          m = fminf(m, v[31]);
+          if (!(m + lds_f32(nrm + (BN + 32 + c) * 4) < as_best)) return;
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const float4 n = lds_f32x4(nrm + (c * 32 + g * 4) * 4);
@@ -541,6 +547,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         // MMA warp and the epilogue warps wait on each other once per tile, and whatever sits between the accumulator
         // becoming ready and its release (a scan, worse: a scan that finds candidates) is on the critical path of the
         // whole SM (profiles/r1_e_sweep.txt: the MMA warp spends 39% of its time waiting for this release).
+        // (Tried and dropped: accumulating a tile as two 128 x 128 halves with their own ready / drained barriers, four
+        // half-accumulators in flight -- 29 ms instead of 20.6, gpurun_out/ablate_v6.log: N = 128 MMAs and twice the
+        // barrier traffic cost more than the finer hand-off saves.)
         float va[32], vb[32];
         ptx::tmem_ld32(taddr, va);
         ptx::tmem_ld32(taddr + NH * 32, vb);
@@ -665,6 +674,28 @@ group_hist_kernel(const int* __restrict__ assign, int nq, int n_anchor, int* __r
   for (int b = threadIdx.x; b < n_anchor; b += blockDim.x) blockhist[size_t(b) * gridDim.x + blockIdx.x] = gh_smem[b];
 }
 
+// one warp per anchor: in-place exclusive scan of its row of blockhist (over the sort's blocks) + the anchor's total
+__global__ void __launch_bounds__(256)
+group_binscan_kernel(int* __restrict__ blockhist, int nblk, int n_anchor, int* __restrict__ bin_total) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= n_anchor) return;
+  int* row = blockhist + size_t(b) * nblk;
+  int run = 0;
+  for (int base = 0; base < nblk; base += 32) {
+    const int i = base + lane;
+    const int x = i < nblk ? row[i] : 0;
+    int incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (i < nblk) row[i] = run + incl - x;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) bin_total[b] = run;
+}
+
 // in-place exclusive scan of n ints, one block
 __global__ void __launch_bounds__(1024) group_scan_kernel(int* __restrict__ v, int n) {
   __shared__ int part[1024];
@@ -689,9 +720,10 @@ __global__ void __launch_bounds__(1024) group_scan_kernel(int* __restrict__ v, i
 
 // perm[position] = query; stable: queries of one anchor keep their order (warps of a block take turns)
 __global__ void __launch_bounds__(GROUP_BLOCK)
-group_scatter_kernel(const int* __restrict__ assign, int nq, int n_anchor, const int* __restrict__ blockhist, int* __restrict__ perm) {
+group_scatter_kernel(const int* __restrict__ assign, int nq, int n_anchor, const int* __restrict__ blockhist,
+                     const int* __restrict__ bin_start, int* __restrict__ perm) {
   extern __shared__ int gs_smem[];
-  for (int b = threadIdx.x; b < n_anchor; b += blockDim.x) gs_smem[b] = blockhist[size_t(b) * gridDim.x + blockIdx.x];
+  for (int b = threadIdx.x; b < n_anchor; b += blockDim.x) gs_smem[b] = bin_start[b] + blockhist[size_t(b) * gridDim.x + blockIdx.x];
   __syncthreads();
   const int i = blockIdx.x * GROUP_BLOCK + threadIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -773,6 +805,7 @@ __global__ void merge_pivots_kernel(const float* __restrict__ parts, int nparts,
 // One warp per query: pick the KP smallest approximate keys from the sweep's candidate log, recompute those
 // candidates' distances exactly, sort by (distance, index), emit top-k, certify.
 constexpr int RR_WARPS = 4;
+constexpr int RR_STAGE = 1024;             // logged keys per query staged in shared memory for the selection
 
 __device__ __forceinline__ uint32_t sortable(uint32_t fbits) { return (fbits & 0x80000000u) ? ~fbits : (fbits | 0x80000000u); }
 __device__ __forceinline__ float unsortable(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
@@ -812,16 +845,34 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
     tau_min = fminf(tau_min, log_tau[l0 + s]);
   }
   uint32_t ustar = 0xffffffffu;   // KP-th smallest key in sortable-uint form
+  // The selection reads every logged key up to 34 times (32 radix passes + 2 gather passes): stage the keys in shared
+  // memory once when they fit (they do unless a log is nearly full), instead of streaming them from L2 every pass.
+  uint32_t* ek = reinterpret_cast<uint32_t*>(rr_smem + RR_WARPS * (D + 2 * KP)) + warp * RR_STAGE;
+  const bool staged = total > kp && total <= RR_STAGE;
+  if (staged) {
+    int base = 0;
+    for (int s = 0; s < n_splits; ++s) {
+      const uint2* ls = log + (l0 + s) * logcap;
+      const int c = min(log_cnt[l0 + s], logcap);
+      for (int e = lane; e < c; e += 32) ek[base + e] = sortable(__ldg(&ls[e].x));
+      base += c;
+    }
+    __syncwarp();
+  }
   if (total > kp) {
     // radix descent, one bit per pass: smallest value u with #{entries <= u} >= kp
     uint32_t prefix = 0;
     for (int bit = 31; bit >= 0; --bit) {
       const uint32_t mid = prefix | ((1u << bit) - 1u);
       int cnt = 0;
-      for (int s = 0; s < n_splits; ++s) {
-        const uint2* ls = log + (l0 + s) * logcap;
-        const int c = min(log_cnt[l0 + s], logcap);
-        for (int e = lane; e < c; e += 32) cnt += sortable(__ldg(&ls[e].x)) <= mid ? 1 : 0;
+      if (staged) {
+        for (int e = lane; e < total; e += 32) cnt += ek[e] <= mid ? 1 : 0;
+      } else {
+        for (int s = 0; s < n_splits; ++s) {
+          const uint2* ls = log + (l0 + s) * logcap;
+          const int c = min(log_cnt[l0 + s], logcap);
+          for (int e = lane; e < c; e += 32) cnt += sortable(__ldg(&ls[e].x)) <= mid ? 1 : 0;
+        }
       }
       cnt = __reduce_add_sync(0xffffffffu, cnt);
       if (cnt < kp) prefix |= (1u << bit);
@@ -832,26 +883,27 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
   int filled = 0;
   for (int pass = 0; pass < 2; ++pass) {        // pass 0: keys < u*, pass 1: keys == u* until kp slots are used
     if (pass == 1 && total <= kp) break;
+    int base = 0;
     for (int s = 0; s < n_splits; ++s) {
       const uint2* ls = log + (l0 + s) * logcap;
       const int c = min(log_cnt[l0 + s], logcap);
       for (int e0 = 0; e0 < c; e0 += 32) {
         const int e = e0 + lane;
-        uint2 ent = make_uint2(0, 0);
+        uint32_t u = 0;
         bool take = false;
         if (e < c) {
-          ent = __ldg(&ls[e]);
-          const uint32_t u = sortable(ent.x);
+          u = staged ? ek[base + e] : sortable(__ldg(&ls[e].x));
           take = total <= kp ? true : (pass == 0 ? u < ustar : u == ustar);
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, take);
         const int pos = filled + __popc(bal & ((1u << lane) - 1u));
         if (take && pos < kp) {
-          sk[pos] = __uint_as_float(ent.x);
-          sv[pos] = int(ent.y);
+          sk[pos] = unsortable(u);
+          sv[pos] = int(__ldg(&ls[e].y));
         }
         filled += __popc(bal);
       }
+      base += c;
     }
   }
   __syncwarp();
@@ -1128,7 +1180,7 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   p.off_aidx = take(size_t(p.n_anchor) * 4);
   p.off_assign = take(p.n_anchor ? q_rows * 4 : 0);
   p.off_perm = take(p.n_anchor ? q_rows * 4 : 0);
-  p.off_ghist = take(size_t(p.n_anchor) * p.group_blocks * 4);
+  p.off_ghist = take(size_t(p.n_anchor) * (p.group_blocks + 1) * 4);   // per (anchor, block) counts + per anchor totals
   p.total_bytes = off;
   return p;
 }
@@ -1255,9 +1307,12 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
       const size_t hsm = size_t(p.n_anchor) * 4;
       group_hist_kernel<<<p.group_blocks, GROUP_BLOCK, hsm, stream>>>(assign, int(nq), p.n_anchor, ghist);
       MMSIM_CUDA_CHECK(cudaGetLastError());
-      group_scan_kernel<<<1, 1024, 0, stream>>>(ghist, p.n_anchor * p.group_blocks);
+      int* bin_start = ghist + size_t(p.n_anchor) * p.group_blocks;
+      group_binscan_kernel<<<(p.n_anchor * 32 + 255) / 256, 256, 0, stream>>>(ghist, p.group_blocks, p.n_anchor, bin_start);
       MMSIM_CUDA_CHECK(cudaGetLastError());
-      group_scatter_kernel<<<p.group_blocks, GROUP_BLOCK, hsm, stream>>>(assign, int(nq), p.n_anchor, ghist, perm);
+      group_scan_kernel<<<1, 1024, 0, stream>>>(bin_start, p.n_anchor);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
+      group_scatter_kernel<<<p.group_blocks, GROUP_BLOCK, hsm, stream>>>(assign, int(nq), p.n_anchor, ghist, bin_start, perm);
       MMSIM_CUDA_CHECK(cudaGetLastError());
       prep<<<qb, PREP_THREADS, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, 0, nullptr, perm);
       MMSIM_CUDA_CHECK(cudaGetLastError());
@@ -1311,7 +1366,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   if (phases & kPhaseRerank) {
     const float delta_coeff = 4.0f * float(p.Dp + 8) * 5.9604645e-8f;
     const int blocks = int((nq + RR_WARPS - 1) / RR_WARPS);
-    const size_t smem = size_t(RR_WARPS) * (size_t(D) + 2 * KP) * 4;
+    const size_t smem = size_t(RR_WARPS) * (size_t(D) + 2 * KP + RR_STAGE) * 4;
     knn_rerank_kernel<<<blocks, RR_WARPS * 32, smem, stream>>>(Q, G, int(nq), ng, int(D), log, p.logcap, log_cnt, log_tau,
                                                                p.n_splits, qnorm, qerr, gstats, delta_coeff, shard_kp ? shard_kp : k,
                                                                shard_kp ? shard_kp : KP, exclude_self, self_offset, out_dist,
