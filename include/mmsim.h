@@ -165,6 +165,15 @@ MMSIM_API int mmsim_evaluate_f32(const float* E, const int32_t* labels, const in
                        const int32_t* queries, int64_t nq, double alpha, int aligned, double* ap, int32_t* npos,
                        int32_t* first, int32_t* depth, int32_t* hist, int32_t* rank, mmsim_stream_t stream);
 
+/* The same records for galleries of any size (N - 1 rows per ranking no longer fit in shared memory): exact distances,
+ * a segmented radix sort and one streaming pass per query, in batches that fit the caller's workspace
+ * (mmsim_evaluate_large_workspace_bytes; 256-byte aligned).  Same arguments and results as mmsim_evaluate_f32. */
+MMSIM_API int mmsim_evaluate_large_workspace_bytes(int64_t N, int64_t nq, size_t* bytes);
+MMSIM_API int mmsim_evaluate_large_f32(const float* E, const int32_t* labels, const int32_t* cls, int64_t N, int64_t D, int C,
+                             const int32_t* queries, int64_t nq, double alpha, int aligned, double* ap, int32_t* npos,
+                             int32_t* first, int32_t* depth, int32_t* hist, int32_t* rank, void* workspace,
+                             size_t workspace_bytes, mmsim_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("MMSIM_LIB") or os.path.join(_HERE, "libmmsim.so")   #
 METRICS = {"squaredeuclidean": 0, "euclidean": 1, "l1": 2}
 LOSS_BATCH_HARD, LOSS_LIFTED = 0, 1
 KNN_MAX_K = 112
+EVAL_SMEM_MAX_N = 16385     # largest N whose leave-one-out ranking fits the one-CTA-per-query kernel (csrc/eval.cu)
 
 # name -> (restype, argtypes); mirrors include/mmsim.h one to one (tests/test_abi.py checks the header against this)
 SIGNATURES = {
@@ -38,6 +39,9 @@ SIGNATURES = {
     "mmsim_semihard_pick_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p]),
     "mmsim_evaluate_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_double, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmsim_evaluate_large_workspace_bytes": (c_int, [c_int64, c_int64, POINTER(c_size_t)]),
+    "mmsim_evaluate_large_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_double, c_int,
+                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mmsim_knn_merge": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -142,4 +142,16 @@ MMSIM_API int mmsim_semihard_pick_f32(const float* dist, int64_t n, int64_t ld, 
   return mining::run_pick(dist, n, ld, labels, picks, p, alpha, neg_idx, reinterpret_cast<cudaStream_t>(stream));
 }
 
+MMSIM_API int mmsim_evaluate_large_workspace_bytes(int64_t N, int64_t nq, size_t* bytes) {
+  return eval::large_workspace_bytes(N, nq, bytes);
+}
+
+MMSIM_API int mmsim_evaluate_large_f32(const float* E, const int32_t* labels, const int32_t* cls, int64_t N, int64_t D, int C,
+                             const int32_t* queries, int64_t nq, double alpha, int aligned, double* ap, int32_t* npos,
+                             int32_t* first, int32_t* depth, int32_t* hist, int32_t* rank, void* workspace,
+                             size_t workspace_bytes, mmsim_stream_t stream) {
+  return eval::run_large(E, labels, cls, N, D, C, queries, nq, alpha, aligned, ap, npos, first, depth, hist, rank, workspace,
+                         workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

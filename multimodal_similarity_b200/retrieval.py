@@ -162,8 +162,13 @@ def average_precision(y_true, score):
 
 
 # --------------------------------------------------------------------------- leave-one-out evaluation (K5)
-def _loo_records(embeddings, labels, normalize, standardize, alpha, aligned, want_rank=False):
-    """Run the fused per-query kernel (csrc/eval.cu) for every foreground row; returns host-side records."""
+EVAL_FORCE_LARGE = False    # tests: route every evaluation through the gallery-scale path (csrc/eval_large.cu)
+
+
+def _loo_records(embeddings, labels, normalize, standardize, alpha, aligned, want_rank=False, queries=None):
+    """Run the per-query evaluation kernels for every foreground row (or the rows in ``queries``); returns host-side
+    records.  Galleries whose ranking fits in shared memory (N <= 16385) take the fused one-CTA-per-query kernel
+    (csrc/eval.cu), larger ones the exact-distance + segmented-sort + streaming-metrics path (csrc/eval_large.cu)."""
     lib = _lib.load()
     lab_np = np.squeeze(labels.cpu().numpy() if torch.is_tensor(labels) else np.asarray(labels)).astype(np.int32)
     emb = to_cuda_f32(embeddings)
@@ -175,7 +180,10 @@ def _loo_records(embeddings, labels, normalize, standardize, alpha, aligned, wan
     n, d = emb.shape
     dev = emb.device
     classes, cls_np = np.unique(lab_np, return_inverse=True)
-    queries_np = np.nonzero(lab_np > 0)[0].astype(np.int32)          # only foreground rows are queries (:114,171)
+    if queries is None:
+        queries_np = np.nonzero(lab_np > 0)[0].astype(np.int32)      # only foreground rows are queries (:114,171)
+    else:
+        queries_np = np.asarray(queries, dtype=np.int32)
     nq, C = int(queries_np.size), int(classes.size)
     lab = torch.from_numpy(lab_np).to(dev)
     cls = torch.from_numpy(cls_np.astype(np.int32)).to(dev)
@@ -185,9 +193,18 @@ def _loo_records(embeddings, labels, normalize, standardize, alpha, aligned, wan
     hist = torch.empty((max(nq, 1), C), dtype=torch.int32, device=dev)
     rank = torch.empty((nq, n - 1), dtype=torch.int32, device=dev) if want_rank else None
     with torch.cuda.device(dev):
-        rc = lib.mmsim_evaluate_f32(emb.data_ptr(), lab.data_ptr(), cls.data_ptr(), n, d, C, queries.data_ptr(), nq,
-                                    float(alpha), int(bool(aligned)), ap.data_ptr(), ints[0].data_ptr(), ints[1].data_ptr(),
-                                    ints[2].data_ptr(), hist.data_ptr(), _lib.ptr(rank), stream_handle(dev))
+        if n > _lib.EVAL_SMEM_MAX_N or EVAL_FORCE_LARGE:
+            nbytes = ctypes.c_size_t()
+            _lib.check(lib.mmsim_evaluate_large_workspace_bytes(n, nq, ctypes.byref(nbytes)), "mmsim_evaluate_large_workspace_bytes")
+            ws = workspace("eval_large", nbytes.value, dev)
+            rc = lib.mmsim_evaluate_large_f32(emb.data_ptr(), lab.data_ptr(), cls.data_ptr(), n, d, C, queries.data_ptr(), nq,
+                                              float(alpha), int(bool(aligned)), ap.data_ptr(), ints[0].data_ptr(),
+                                              ints[1].data_ptr(), ints[2].data_ptr(), hist.data_ptr(), _lib.ptr(rank),
+                                              ws.data_ptr(), ws.numel(), stream_handle(dev))
+        else:
+            rc = lib.mmsim_evaluate_f32(emb.data_ptr(), lab.data_ptr(), cls.data_ptr(), n, d, C, queries.data_ptr(), nq,
+                                        float(alpha), int(bool(aligned)), ap.data_ptr(), ints[0].data_ptr(), ints[1].data_ptr(),
+                                        ints[2].data_ptr(), hist.data_ptr(), _lib.ptr(rank), stream_handle(dev))
     _lib.check(rc, "mmsim_evaluate_f32")
     ints = ints.cpu().numpy()
     rec = dict(classes=classes.tolist(), labels=lab_np, queries=queries_np, ap=ap.cpu().numpy(), npos=ints[0][:nq],

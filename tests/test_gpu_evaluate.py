@@ -77,3 +77,65 @@ def test_cub_shape_recall(rs):
     ref = O.evaluate(emb, lab)
     got = mm.evaluate(emb, lab)
     assert got[0] == pytest.approx(ref[0], abs=1e-12) and got[5] == ref[5]
+
+
+# ---------------------------------------------------------------------------------------------- gallery-scale path
+@pytest.fixture
+def force_large():
+    from multimodal_similarity_b200 import retrieval
+    retrieval.EVAL_FORCE_LARGE = True
+    yield
+    retrieval.EVAL_FORCE_LARGE = False
+
+
+@pytest.mark.parametrize("name", ["hdd", "cub", "fused"])
+def test_large_path_golden(name, force_large):
+    """csrc/eval_large.cu (exact distances + segmented sort + streaming metrics) against the reference's own outputs."""
+    import multimodal_similarity_b200 as mm
+    g = golden(f"eval_{name}.npz")
+    got = mm.evaluate(g["x"].copy(), g["labels"].copy(), alpha=float(g["alpha"]))
+    assert got[0] == pytest.approx(float(g["mAP"]), abs=1e-12) and got[2] == pytest.approx(float(g["mPrec"]), abs=1e-12)
+    np.testing.assert_array_equal(got[3]["confusion_matrix"], g["confusion"])
+    assert np.array_equal(got[4], g["count"]) and got[5] == g["recall"].tolist()
+    s = mm.evaluate_simple(g["x"].copy(), g["labels"].copy(), alpha=float(g["alpha"]))
+    assert np.allclose(s, g["simple"], atol=1e-12)
+
+
+@pytest.mark.parametrize("n,d,c,bg,alpha", [(64, 16, 3, 0.3, 0.5), (1300, 96, 6, 0.5, 1.0), (300, 256, 40, 0.1, 0.0)])
+def test_large_path_equals_fused_kernel(n, d, c, bg, alpha, rs, force_large):
+    from multimodal_similarity_b200 import retrieval
+    x, lab = clustered(rs, n, d, c, background=bg)
+    x[7] = x[3]; x[11] = x[3]                       # exact ties: both paths order by (distance, index)
+    for aligned in (False, True):
+        retrieval.EVAL_FORCE_LARGE = True
+        a = retrieval._loo_records(x, lab, False, False, alpha, aligned, want_rank=True)
+        retrieval.EVAL_FORCE_LARGE = False
+        b = retrieval._loo_records(x, lab, False, False, alpha, aligned, want_rank=True)
+        for key in ("npos", "first", "depth", "hist"):
+            assert np.array_equal(a[key], b[key]), key
+        assert np.allclose(a["ap"], b["ap"], rtol=0, atol=1e-12)
+        assert np.array_equal(a["rank"].cpu().numpy(), b["rank"].cpu().numpy())
+
+
+def test_large_gallery_vs_oracle(rs):
+    """BASELINE config 4's leave-one-out form: 20,000 fused 2 x 128-d rows, HDD-style labels -- beyond the shared-memory
+    kernel.  A handful of queries against the oracle's per-query arithmetic."""
+    from multimodal_similarity_b200 import retrieval
+    cam, lab = clustered(rs, 20000, 128, 7, first_label=0)          # label 0 = background
+    sens, _ = clustered(rs, 20000, 128, 7)
+    x = np.concatenate((cam, sens), axis=1)
+    qs = [int(q) for q in np.nonzero(lab > 0)[0][[0, 1, 777, 5000, -1]]]
+    for aligned in (False, True):
+        rec = retrieval._loo_records(x, lab, False, False, 0.5, aligned, queries=qs)
+        for n_, i in enumerate(qs):
+            gl = np.delete(lab, i)
+            dist, order, ap = O.retrieve_one(x[i], np.delete(x, i, 0), lab[i], gl)
+            ranked = O._ranked_labels(lab, gl, order, aligned)
+            assert rec["ap"][n_] == pytest.approx(ap, abs=1e-12)
+            first = int(np.argmax(ranked == lab[i])) if (ranked == lab[i]).any() else len(ranked)
+            assert rec["first"][n_] == first
+            p, conf = O.precision_at_recall(ranked, lab[i], 0.5)
+            depth = rec["depth"][n_]
+            assert rec["hist"][n_][rec["classes"].index(int(lab[i]))] / depth == pytest.approx(p, abs=1e-12)
+            for c, v in conf.items():
+                assert rec["hist"][n_][rec["classes"].index(int(c))] / depth == pytest.approx(v, abs=1e-12)
