@@ -915,16 +915,46 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
   const int self = exclude_self ? int(self_offset + qo) : -1;
   {
     const int sub = lane & 7, grp = lane >> 3;
+    // two independent candidates per lane group and round: twice the loads in flight (the gather is latency-bound:
+    // 61% of the stall samples were on the gallery-row loads, profiles/r1_g_rerank.txt)
 #pragma unroll 1
-    for (int r0 = 0; r0 < KP; r0 += 4) {
+    for (int r0 = 0; r0 < KP; r0 += 8) {
       if (r0 >= kp) break;                      // slots >= kp hold the (+inf, -1) padding
-      const int idx = sv[r0 + grp];
-      const bool live = idx >= 0 && idx != self;
-      const float s2 = exact_reduce_8<kSquaredEuclidean>(qs, G + size_t(live ? idx : 0) * D, D, sub);
+      const int ia = sv[r0 + grp], ib = sv[r0 + 4 + grp];
+      const bool la = ia >= 0 && ia != self, lb = ib >= 0 && ib != self;
+      const float* ga = G + size_t(la ? ia : 0) * D;
+      const float* gb = G + size_t(lb ? ib : 0) * D;
+      float sa, sb;
+      if (D <= 128 && D >= 8) {
+        // interleaved form of exact_leaf_8 (same operations per candidate in the same order)
+        sa = exact_term<kSquaredEuclidean>(qs[sub], ga[sub]);
+        sb = exact_term<kSquaredEuclidean>(qs[sub], gb[sub]);
+        int i = 8;
+#pragma unroll 8
+        for (; i + 8 <= D; i += 8) {
+          const float q = qs[i + sub];
+          sa = __fadd_rn(sa, exact_term<kSquaredEuclidean>(q, ga[i + sub]));
+          sb = __fadd_rn(sb, exact_term<kSquaredEuclidean>(q, gb[i + sub]));
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          sa = __fadd_rn(sa, __shfl_xor_sync(0xffffffffu, sa, o));
+          sb = __fadd_rn(sb, __shfl_xor_sync(0xffffffffu, sb, o));
+        }
+        for (; i < D; ++i) {
+          sa = __fadd_rn(sa, exact_term<kSquaredEuclidean>(qs[i], ga[i]));
+          sb = __fadd_rn(sb, exact_term<kSquaredEuclidean>(qs[i], gb[i]));
+        }
+      } else {
+        sa = exact_reduce_8<kSquaredEuclidean>(qs, ga, D, sub);
+        sb = exact_reduce_8<kSquaredEuclidean>(qs, gb, D, sub);
+      }
       __syncwarp();
       if (sub == 0) {
-        sk[r0 + grp] = live ? __fsqrt_rn(s2) : kInf;
-        sv[r0 + grp] = live ? idx : 0x7fffffff;
+        sk[r0 + grp] = la ? __fsqrt_rn(sa) : kInf;
+        sv[r0 + grp] = la ? ia : 0x7fffffff;
+        sk[r0 + 4 + grp] = lb ? __fsqrt_rn(sb) : kInf;
+        sv[r0 + 4 + grp] = lb ? ib : 0x7fffffff;
       }
     }
   }
