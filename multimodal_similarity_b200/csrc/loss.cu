@@ -532,6 +532,289 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ batch-hard, row-owned
+// K2': batch-hard forward + backward WITHOUT a grid barrier.  The tile kernel above spends most of its 19 us on L2 round
+// trips, not arithmetic (gpurun_out/loss_trace.log: staging 3.6, distances 1.2, partials 1.4, grid barrier 2.0, W 1.3,
+// row combine + gradient 6.2, last CTA 3.7).  Batch-hard needs none of the exchanges: if a CTA owns COMPLETE rows -- 4
+// anchors against all N columns, streamed through shared memory in 128-row tiles with cp.async double buffering (N/4
+// CTAs of 128 threads; fewer rows per CTA and the L2 -> SM traffic of every CTA streaming all of E dominates) -- the
+// hardest positive / negative of its rows are final inside the CTA, the weight normaliser W depends on the labels only
+// (every CTA counts it itself while the first tile is in flight), and the sparse gradient of an anchor touches rows
+// i, p, n with a coefficient that depends on row i alone.  What is left of the global synchronisation is the
+// deterministic sum of the per-row terms by the last CTA.  dE is zeroed by a memset node ahead of the launch (the
+// contributions arrive as atomics from arbitrary CTAs).  Distances use the tile kernel's arithmetic (sequential fmaf
+// over d), so values, mined indices and the tie path are bit-identical to it.
+constexpr int BR_THREADS = 128, BR_R = 4, BR_TJ = 128;
+constexpr int BR_HASH = 2048;              // label hash table slots (power of two, >= 2 N)
+
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+  const int n = valid ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+__global__ void __launch_bounds__(BR_THREADS) bh_rows_kernel(const Params p) {
+  extern __shared__ __align__(16) float sm[];
+  const int N = p.N, D = p.D;
+  const int D4 = (D + 3) & ~3, DP = D4 + 4, Q4 = D4 >> 2;
+  float* Ei = sm;                              // [BR_R][DP]   this CTA's anchors
+  float* Ej = Ei + BR_R * DP;                  // [2][BR_TJ][DP] streamed column tiles
+  float* pid_all = Ej + 2 * BR_TJ * DP;        // [Npad]
+  int* same_all = reinterpret_cast<int*>(pid_all + p.Npad);   // [Npad] same-label columns of every row (incl. self)
+  float* part = reinterpret_cast<float*>(same_all + p.Npad);  // [BR_R][warps][6] partial (hp, hn) of a row
+  int* hkey = reinterpret_cast<int*>(part + BR_R * (BR_THREADS / 32) * 6);   // [BR_HASH] label hash table
+  int* hcnt = hkey + BR_HASH;
+  __shared__ int s_red[BR_THREADS / 32];
+  __shared__ int s_W, s_last;
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int i0 = blockIdx.x * BR_R;
+  const unsigned int G = gridDim.x;
+  const int n_tiles = (N + BR_TJ - 1) / BR_TJ;
+  const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.E) & 15) == 0);
+
+  stamp(p, 0);
+  auto load_tile = [&](int tile, int buf) {
+    float* dst = Ej + buf * BR_TJ * DP;
+    const int j0 = tile * BR_TJ;
+    if (vec) {
+      for (int x = t; x < BR_TJ * Q4; x += BR_THREADS) {
+        const int r = x / Q4, c4 = x - r * Q4;
+        const bool in = j0 + r < N;
+        cp_async16(dst + r * DP + c4 * 4, p.E + size_t(in ? j0 + r : 0) * D + c4 * 4, in);
+      }
+    } else {
+      for (int x = t; x < BR_TJ * D4; x += BR_THREADS) {
+        const int r = x / D4, c = x - r * D4;
+        dst[r * DP + c] = (j0 + r < N && c < D) ? p.E[size_t(j0 + r) * D + c] : 0.f;
+      }
+    }
+    cp_async_commit();
+  };
+  load_tile(0, 0);
+  // anchors + labels (plain loads, overlapped with the first tile)
+  for (int x = t; x < BR_R * D4; x += BR_THREADS) {
+    const int r = x / D4, c = x - r * D4;
+    Ei[r * DP + c] = (i0 + r < N && c < D) ? p.E[size_t(i0 + r) * D + c] : 0.f;
+  }
+  for (int i = t; i < p.Npad; i += BR_THREADS) pid_all[i] = i < N ? p.pids[i] : 0.f;
+  __syncthreads();
+  // same-label counts of every row (a shared-memory hash table keyed by the label's bits: O(N) instead of N^2 compares,
+  // which alone took 6 us) and W = sum_i (#negatives_i) * [pid_i != 0], exact in integers
+  {
+    for (int x = t; x < BR_HASH; x += BR_THREADS) { hkey[x] = 0x7fc00123; hcnt[x] = 0; }   // empty = an unused NaN pattern
+    __syncthreads();
+    for (int i = t; i < N; i += BR_THREADS) {
+      const int key = __float_as_int(pid_all[i] + 0.f);          // -0 and +0 are the same label
+      int slot = (unsigned(key) * 2654435761u >> 16) & (BR_HASH - 1);
+      for (;;) {
+        const int prev = atomicCAS(&hkey[slot], 0x7fc00123, key);
+        if (prev == 0x7fc00123 || prev == key) break;
+        slot = (slot + 1) & (BR_HASH - 1);
+      }
+      atomicAdd(&hcnt[slot], 1);
+      same_all[i] = slot;
+    }
+    __syncthreads();
+    int part_w = 0;
+    for (int i = t; i < N; i += BR_THREADS) {
+      const int c = hcnt[same_all[i]];
+      part_w += pid_all[i] != 0.f ? N - c : 0;
+      same_all[i] = c;      // only this thread reads and writes entry i
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part_w += __shfl_xor_sync(0xffffffffu, part_w, o);
+    if (lane == 0) s_red[warp] = part_w;
+    __syncthreads();
+    if (t == 0) {
+      int tot = 0;
+      for (int x = 0; x < BR_THREADS / 32; ++x) tot += s_red[x];
+      s_W = tot;
+    }
+  }
+  stamp(p, 1);
+
+  // ---- distances + masked row extremes: a thread owns one column of every tile for the CTA's four anchors (the column
+  // values are read once for all of them; four independent fmaf chains)
+  float pr[BR_R];
+  Arg hp4[BR_R], hn4[BR_R];
+#pragma unroll
+  for (int r = 0; r < BR_R; ++r) {
+    pr[r] = i0 + r < N ? pid_all[i0 + r] : 0.f;
+    hp4[r] = Arg{-1.f, -1, 0};
+    hn4[r] = Arg{kInf, -1, 0};
+  }
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    if (tile + 1 < n_tiles) {
+      load_tile(tile + 1, (tile + 1) & 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* ej = Ej + (tile & 1) * BR_TJ * DP + t * DP;
+    float dd[BR_R];
+#pragma unroll
+    for (int r = 0; r < BR_R; ++r) dd[r] = 0.f;
+#pragma unroll 2
+    for (int d = 0; d < D4; d += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(ej + d);
+#pragma unroll
+      for (int r = 0; r < BR_R; ++r) {
+        const float4 a = *reinterpret_cast<const float4*>(Ei + r * DP + d);
+        float x;
+        x = a.x - v.x; dd[r] = fmaf(x, x, dd[r]);
+        x = a.y - v.y; dd[r] = fmaf(x, x, dd[r]);
+        x = a.z - v.z; dd[r] = fmaf(x, x, dd[r]);
+        x = a.w - v.w; dd[r] = fmaf(x, x, dd[r]);
+      }
+    }
+    const int j = tile * BR_TJ + t;
+    if (j < N) {
+      const float pj = pid_all[j];
+#pragma unroll
+      for (int r = 0; r < BR_R; ++r) {
+        if (i0 + r >= N) continue;
+        if (pj == pr[r]) { if (j != i0 + r) hp4[r] = arg_max(hp4[r], Arg{dd[r], j, 1}); } else hn4[r] = arg_min(hn4[r], Arg{dd[r], j, 1});
+      }
+    }
+    __syncthreads();   // the tile buffer is reloaded two iterations later
+  }
+  stamp(p, 2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    auto sh = [&](Arg x) { return Arg{__shfl_xor_sync(0xffffffffu, x.v, o), __shfl_xor_sync(0xffffffffu, x.i, o), __shfl_xor_sync(0xffffffffu, x.c, o)}; };
+#pragma unroll
+    for (int r = 0; r < BR_R; ++r) {
+      hp4[r] = arg_max(hp4[r], sh(hp4[r]));
+      hn4[r] = arg_min(hn4[r], sh(hn4[r]));
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < BR_R; ++r) {
+      float* q = part + (r * (BR_THREADS / 32) + warp) * 6;
+      q[0] = hp4[r].v; q[1] = __int_as_float(hp4[r].i); q[2] = __int_as_float(hp4[r].c);
+      q[3] = hn4[r].v; q[4] = __int_as_float(hn4[r].i); q[5] = __int_as_float(hn4[r].c);
+    }
+  }
+  __syncthreads();
+  stamp(p, 3);
+  stamp(p, 4);
+
+  // ---- per-row results and the sparse gradient: warp w owns anchor i0 + w
+  const float Wf = float(s_W), invN = 1.0f / float(N);
+  {
+    const int i = i0 + warp;
+    if (warp < BR_R && i < N) {
+      Arg hp{-1.f, -1, 0}, hn{kInf, -1, 0};
+#pragma unroll
+      for (int w2 = 0; w2 < BR_THREADS / 32; ++w2) {
+        const float* q = part + (warp * (BR_THREADS / 32) + w2) * 6;
+        hp = arg_max(hp, Arg{q[0], __float_as_int(q[1]), __float_as_int(q[2])});
+        hn = arg_min(hn, Arg{q[3], __float_as_int(q[4]), __float_as_int(q[5])});
+      }
+      const float pi = pid_all[i];
+      const float fg = pi != 0.f ? 1.f : 0.f;
+      const float wi = p.weighted ? (pi != 0.f ? float(N - same_all[i]) : 0.f) / Wf : invN;
+      const float fp = fmaxf(hp.v, 0.f);  // max_j(D_ij * pos_ij) >= 0: masked zeros take part (networks.py:808)
+      const float cn = hn.v;              // +inf when the row has no negatives
+      const float x = fp - cn;
+      float l, dl;
+      if (p.soft) {
+        l = softplus_f(x);
+        dl = 1.f / (1.f + expf(-x));
+      } else {
+        l = fmaxf(x + p.margin, 0.f);
+        dl = (x + p.margin >= 0.f) ? 1.f : 0.f;
+      }
+      if (hn.i < 0) { l = 0.f; dl = 0.f; }  // empty negative set: the term is exactly 0
+      if (lane == 0) {
+        p.diff[i] = l; p.w[i] = wi; p.fp[i] = fp; p.cn[i] = cn;
+        p.pos_idx[i] = hp.i; p.neg_idx[i] = hn.i;
+        p.row_loss[i] = l * wi;
+        p.row_active[i] = (l * fg > 1e-5f) ? 1.f : 0.f;
+      }
+      // sparse gradient: dL/dD_ip = +c/|P|, dL/dD_in = -c/|N| ; dD_ij/de_i = 2(e_i - e_j)
+      const float c = wi * dl;
+      if (p.dE && c != 0.f) {
+        const bool use_pos = hp.i >= 0 && fp > 0.f;  // fp == 0: every tied entry has zero derivative
+        if (hp.c <= 1 && hn.c <= 1) {
+          const float* ei = Ei + warp * DP;
+          const float* ep = p.E + size_t(use_pos ? hp.i : i) * D;
+          const float* en = p.E + size_t(hn.i) * D;
+          for (int d = lane; d < D; d += 32) {
+            const float vi = ei[d], vp = ep[d], vn = en[d];
+            float gi = -2.f * c * (vi - vn);
+            if (use_pos) {
+              gi += 2.f * c * (vi - vp);
+              atomicAdd(&p.dE[size_t(hp.i) * D + d], 2.f * c * (vp - vi));
+            }
+            atomicAdd(&p.dE[size_t(i) * D + d], gi);
+            atomicAdd(&p.dE[size_t(hn.i) * D + d], 2.f * c * (vi - vn));
+          }
+        } else {
+          bh_tie_backward(p, i, lane, c, fp, cn, use_pos, hp.c, hn.c);
+        }
+      }
+    }
+  }
+  stamp(p, 5);
+  stamp(p, 6);
+  // ---- last CTA: deterministic sum of the per-row terms
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&p.sync[1], 1u) == G - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    __shared__ float s_l[BR_THREADS], s_a[BR_THREADS], s_f[BR_THREADS];
+    float l = 0.f, a = 0.f, f = 0.f;
+    for (int i = t; i < N; i += BR_THREADS) {
+      l += __ldcg(&p.row_loss[i]);
+      a += __ldcg(&p.row_active[i]);
+      f += pid_all[i] != 0.f ? 1.f : 0.f;
+    }
+    s_l[t] = l; s_a[t] = a; s_f[t] = f;
+    __syncthreads();
+    for (int o = BR_THREADS / 2; o > 0; o >>= 1) {
+      if (t < o) { s_l[t] += s_l[t + o]; s_a[t] += s_a[t + o]; s_f[t] += s_f[t + o]; }
+      __syncthreads();
+    }
+    if (t == 0) {
+      *p.loss = s_l[0];
+      *p.num_active = s_a[0] / s_f[0];
+      p.sync[1] = 0;   // leave the workspace zero-filled for the next launch
+      unsigned long long tt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+      p.trace[7] = tt;
+    }
+  }
+}
+
+static size_t bh_rows_smem(int64_t N, int64_t D) {
+  const size_t D4 = size_t((D + 3) & ~int64_t(3)), DP = D4 + 4, Npad = align_up(size_t(N), 32);
+  return (BR_R * DP + 2 * BR_TJ * DP + 2 * Npad + BR_R * (BR_THREADS / 32) * 6 + 2 * BR_HASH) * 4;
+}
+// MMSIM_BH_ROWS=1 selects the row-owned kernel for batch-hard (A/B runs).  It is NOT the default: measured on B200 at
+// 256 x 128 it is no faster than the tile kernel (18.0 vs 19.3 us in-kernel, 20.7 vs 21.8 us per CUDA-graph replay, and
+// slower per eager call because of the extra memset launch; gpurun_out/loss_trace4.log) -- every CTA streaming all of E
+// through L2 costs what the grid barrier and the partial tables cost the tile kernel.
+static bool bh_rows_ok(int64_t N, int64_t D) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("MMSIM_BH_ROWS");
+    enabled = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  return enabled && bh_rows_smem(N, D) <= 200 * 1024;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 // Tile shapes (MI, MJ) -> TI = 8 MI rows x TJ = 16 MJ columns per CTA, smallest first.
 static const int kShapes[3][2] = {{2, 2}, {4, 4}, {8, 8}};
@@ -656,6 +939,18 @@ int run(int kind, const float* E, const float* pids, int64_t N, int64_t D, int s
   p.row_active = reinterpret_cast<float*>(b + L.off_row_active);
   p.trace = reinterpret_cast<unsigned long long*>(b + L.off_trace);
   p.NBI = L.NBI; p.NBJ = L.NBJ; p.Npad = L.Npad;
+
+  if (kind == 0 && bh_rows_ok(N, D)) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      MMSIM_CUDA_CHECK(cudaFuncSetAttribute(bh_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    if (dE) MMSIM_CUDA_CHECK(cudaMemsetAsync(dE, 0, size_t(N) * D * sizeof(float), stream));
+    bh_rows_kernel<<<unsigned((N + BR_R - 1) / BR_R), BR_THREADS, bh_rows_smem(N, D), stream>>>(p);
+    MMSIM_CUDA_CHECK(cudaGetLastError());
+    return MMSIM_OK;
+  }
 
   void* args[] = {const_cast<Params*>(&p)};
   const dim3 grid(unsigned(L.NBI * L.NBJ)), block(THREADS);
