@@ -52,7 +52,7 @@ def config_of(a, n_gpus):
                         f"(BASELINE configs[4] at the metric's 128-d), gallery rows split over {n_gpus} GPU(s)",
             "queries": a.queries, "gallery": a.gallery, "dim": a.dim, "k": a.k,
             "l2": f"inputs larger than L2 (fp32 gallery {a.gallery * a.dim * 4 / 1e6:.0f} MB + fp16 copy, 126 MB L2)",
-            "parallelism": f"gallery-sharded x{n_gpus}, queries replicated, NCCL all-gather merge" if n_gpus > 1 else "single GPU"}
+            "parallelism": f"gallery-sharded x{n_gpus}, queries replicated, NCCL all-to-all of candidate lists + merge by query slice + all-gather" if n_gpus > 1 else "single GPU"}
 
 
 # ----------------------------------------------------------------------------------------------- synthetic data
@@ -342,33 +342,47 @@ def main():
             phase_ms[name] = m_ / 3
     else:
         # the reduced sharded protocol, stage by stage (same calls ShardedGallery.retrieve makes)
-        from multimodal_similarity_b200.sharded import ReducedShard, merge_certified, merge_pivots_into, reduced_kp
+        from multimodal_similarity_b200.sharded import (ReducedShard, merge_certified_slice, merge_pivots_into, pack_slices,
+                                                        reduced_kp, slice_rows, unpack_merged)
         kp = reduced_kp(world, k)
         rs_ = ReducedShard(sg.shard, lo)
         packed = torch.empty(ReducedShard.packed_elems(Q, kp), dtype=torch.int32, device=dev)
         rows = -(-Q // 128) * 128
         piv = rs_.stage1(queries, k, kp, packed)
         allpiv = torch.empty((world * rows, 16), dtype=torch.float32, device=dev)
-        gathered = torch.empty((world, packed.numel()), dtype=torch.int32, device=dev)
+        S = slice_rows(Q, world)
+        send = pack_slices(packed, Q, kp, world)
+        recv = torch.empty_like(send)
+        mine = max(0, min(S, Q - rank * S))
+        res_holder = [merge_certified_slice(recv, sg._bases(dev), 0, S, kp, k)]
+        allres = torch.empty((world, res_holder[0].numel()), dtype=torch.int32, device=dev)
         views = ReducedShard._views(packed, Q, kp)
 
         def ag_piv():
             dist.all_gather_into_tensor(allpiv, piv.contiguous())
             merge_pivots_into(allpiv.view(world, rows, 16), piv)
 
+        def a2a_lists():
+            dist.all_to_all_single(recv.view(-1), pack_slices(packed, Q, kp, world).view(-1))
+
+        def merge_slice():
+            res_holder[0] = merge_certified_slice(recv, sg._bases(dev), mine, S, kp, k)
+
         def ag_res():
-            dist.all_gather_into_tensor(gathered.view(-1), packed)
+            dist.all_gather_into_tensor(allres.view(-1), res_holder[0])
+            unpack_merged(allres, Q, S, k)
 
         ag_piv()
         rs_.stage2(queries, k, kp, False, 0, packed)
-        ag_res()
+        a2a_lists(); merge_slice(); ag_res()
         stages = (("prep", lambda: rs_._call(queries, k, kp, False, 0, 1, views)),
                   ("pivot_prepass", lambda: rs_._call(queries, k, kp, False, 0, 16, views)),
                   ("allgather_merge_pivots", ag_piv),
                   ("ladder", lambda: rs_._call(queries, k, kp, False, 0, 32, views)),
                   ("select_rerank_kp%d" % kp, lambda: rs_._call(queries, k, kp, False, 0, 4, views)),
-                  ("allgather_results", ag_res),
-                  ("merge_certified", lambda: merge_certified(gathered, sg._bases(dev), Q, kp, k)))
+                  ("alltoall_candidate_lists", a2a_lists),
+                  ("merge_certified_slice", merge_slice),
+                  ("allgather_merged", ag_res))
         for name, fn in stages:
             fn()
             m_, _ = timed(fn, 3)

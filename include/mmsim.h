@@ -174,6 +174,13 @@ MMSIM_API int mmsim_evaluate_large_f32(const float* E, const int32_t* labels, co
                              int32_t* first, int32_t* depth, int32_t* hist, int32_t* rank, void* workspace,
                              size_t workspace_bytes, mmsim_stream_t stream);
 
+/* Embedding head: out[r] = l2_normalize(X[r] @ W + b) -- networks.CUBLayer.forward (src/networks.py:376-380, xw_plus_b)
+ * followed by tf.nn.l2_normalize(logits, axis=-1, epsilon) (src/base_model_CUB.py:197-201): y * rsqrt(max(sum(y^2), epsilon)).
+ * X [N, K], W [K, E], b [E] or NULL, out [N, E], all fp32 row-major; E <= 256; normalized == 0 skips the normalisation
+ * (cfg.normalized false). */
+MMSIM_API int mmsim_project_normalize_f32(const float* X, int64_t N, int64_t K, const float* W, const float* b, int64_t E,
+                                int normalized, float epsilon, float* out, mmsim_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,7 @@
 Function-level drop-ins for the reference's leaf functions (same names, argument meaning and return tuples):
 
     distance   all_diffs / cdist / all_diffs_tf / cdist_tf / pairwise_distance     src/utils.py:302-360
+               project_normalize (xw_plus_b + l2_normalize embedding head)         src/networks.py:376-380
     losses     batch_hard / lifted_loss (fused forward + backward)                 src/networks.py:797-870
     retrieval  retrieve / retrieve_one / evaluate / evaluate_simple /
                recall_at_K / precision_at_recall / late_fusion                     src/utils.py:55-266
@@ -12,7 +13,7 @@ Function-level drop-ins for the reference's leaf functions (same names, argument
 Everything runs through the C-ABI library libmmsim.so (include/mmsim.h); there is no CPU fallback.
 """
 from ._lib import MmsimError, load  # noqa: F401
-from .distance import all_diffs, all_diffs_tf, cdist, cdist_tf, pairwise_distance  # noqa: F401
+from .distance import all_diffs, all_diffs_tf, cdist, cdist_tf, pairwise_distance, project_normalize  # noqa: F401
 from .losses import batch_hard, lifted_loss  # noqa: F401
 from .retrieval import (  # noqa: F401
     average_precision, evaluate, evaluate_simple, full_ranking, late_fusion, precision_at_recall, recall_at_K, retrieve,

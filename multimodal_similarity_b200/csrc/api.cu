@@ -12,6 +12,7 @@
 #include "loss.h"
 #include "merge.h"
 #include "mining.h"
+#include "project.h"
 #include "sqdist.h"
 
 namespace mmsim {
@@ -152,6 +153,11 @@ MMSIM_API int mmsim_evaluate_large_f32(const float* E, const int32_t* labels, co
                              size_t workspace_bytes, mmsim_stream_t stream) {
   return eval::run_large(E, labels, cls, N, D, C, queries, nq, alpha, aligned, ap, npos, first, depth, hist, rank, workspace,
                          workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+MMSIM_API int mmsim_project_normalize_f32(const float* X, int64_t N, int64_t K, const float* W, const float* b, int64_t E,
+                                int normalized, float epsilon, float* out, mmsim_stream_t stream) {
+  return project::run(X, N, K, W, b, E, normalized, epsilon, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

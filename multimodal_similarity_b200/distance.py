@@ -85,3 +85,22 @@ def cdist_tf(diff, metric: str = "squaredeuclidean") -> LazyDists:
 def pairwise_distance(a, b, metric: str = "squaredeuclidean"):
     """cdist(all_diffs(a, b), metric) in one call."""
     return cdist(all_diffs(a, b), metric)
+
+
+def project_normalize(x, W, b=None, normalized=True, epsilon=1e-10):
+    """The reference's embedding head in one kernel: ``tf.nn.l2_normalize(tf.nn.xw_plus_b(x, W, b), axis=-1, epsilon)``
+    (src/networks.py:376-380 + src/base_model_CUB.py:197-201); ``normalized=False`` returns the logits
+    (``cfg.normalized`` off).  x [N, K], W [K, E <= 256], b [E] or None -> [N, E] float32 (NumPy in -> NumPy out)."""
+    as_numpy = is_numpy_like(x)
+    xd = to_cuda_f32(x)
+    Wd = to_cuda_f32(W, xd.device)
+    bd = None if b is None else to_cuda_f32(b, xd.device)
+    if xd.dim() != 2 or Wd.dim() != 2 or xd.shape[1] != Wd.shape[0] or (bd is not None and tuple(bd.shape) != (Wd.shape[1],)):
+        raise ValueError(f"project_normalize expects x [N,K], W [K,E], b [E]; got {tuple(xd.shape)}, {tuple(Wd.shape)}")
+    out = torch.empty((xd.shape[0], Wd.shape[1]), dtype=torch.float32, device=xd.device)
+    with torch.cuda.device(xd.device):
+        rc = _lib.load().mmsim_project_normalize_f32(xd.data_ptr(), xd.shape[0], xd.shape[1], Wd.data_ptr(), _lib.ptr(bd),
+                                                     Wd.shape[1], int(bool(normalized)), float(epsilon), out.data_ptr(),
+                                                     stream_handle(xd.device))
+    _lib.check(rc, "mmsim_project_normalize_f32")
+    return out_like_input(out, as_numpy)

@@ -9,9 +9,12 @@ single-GPU result:
 ``reduced``       (default with CUDA tensors) the per-rank work that does not shrink with the number of shards is removed:
                   (1) the pivot pre-pass lists are all-gathered and merged, so all shards filter every query with ONE
                   threshold (about 1000 gallery rows below it in total, not per shard); (2) each shard re-ranks exactly
-                  only ``kp`` << 128 candidates and reports a lower bound for everything it did not re-rank; (3) the merge
-                  certifies the global top-k against those bounds.  If any query is uncertified (adversarial row
-                  order, massive ties) the call falls back to ``exact-shards`` -- so the result is always exact.
+                  only ``kp`` << 128 candidates and reports a lower bound for everything it did not re-rank; (3) the
+                  candidate lists are exchanged BY QUERY SLICE (one all-to-all: rank r receives every shard's lists for
+                  queries [r S, (r+1) S)), each rank merges and certifies its slice only, and one all-gather hands every
+                  rank the merged top-k of all queries -- the merge no longer repeats on every rank.  If any query is
+                  uncertified (adversarial row order, massive ties) the call falls back to ``exact-shards`` -- so the
+                  result is always exact.
 
 The training-loss kernels are not sharded (replicas only).
 """
@@ -147,6 +150,55 @@ def merge_certified(gathered: torch.Tensor, bases: torch.Tensor, nq: int, kp: in
     return out_d, out_i, status
 
 
+def slice_rows(nq: int, world: int) -> int:
+    """Queries per merge slice: ceil(nq / world) (the last slices may be short or empty)."""
+    return -(-nq // world)
+
+
+def pack_slices(packed: torch.Tensor, nq: int, kp: int, world: int) -> torch.Tensor:
+    """Stage-2 buffer of one shard -> [world, S * (2 kp + 1)] int32: for every destination rank j the rows of its query
+    slice as | distance bits S x kp | shard-local indices S x kp | lower-bound bits S | (rows past nq are padding)."""
+    S = slice_rows(nq, world)
+    d_, i_, lb_, _ = ReducedShard._views(packed, nq, kp)
+    out = torch.empty((world, S * (2 * kp + 1)), dtype=torch.int32, device=packed.device)
+    pad = world * S - nq
+    def rows(t, width):
+        t = t.view(torch.int32).reshape(nq, width)
+        if pad:
+            t = torch.cat((t, t.new_zeros((pad, width))))
+        return t.view(world, S * width)
+    out[:, :S * kp] = rows(d_, kp)
+    out[:, S * kp:2 * S * kp] = rows(i_, kp)
+    out[:, 2 * S * kp:] = rows(lb_, 1)
+    return out
+
+
+def merge_certified_slice(recv: torch.Tensor, bases: torch.Tensor, n_rows: int, S: int, kp: int, k: int):
+    """[parts, S * (2 kp + 1)] lists of ONE query slice (what the all-to-all delivers) -> merged
+    | global indices S x k as int64 (2 x int32; first, so they are 8-byte aligned) | distance bits S x k | status 8 |
+    as one int32 buffer."""
+    lib = _lib.load()
+    dev = recv.device
+    parts, stride = recv.shape[0], recv.stride(0)
+    res = torch.zeros(S * k * 3 + 8, dtype=torch.int32, device=dev)
+    base = recv.data_ptr()
+    if n_rows > 0:
+        with torch.cuda.device(dev):
+            rc = lib.mmsim_knn_merge_certified(base, base + S * kp * 4, stride, bases.data_ptr(), parts, n_rows, kp, k,
+                                               base + 2 * S * kp * 4, stride, res.data_ptr() + S * k * 8, res.data_ptr(),
+                                               res.data_ptr() + S * k * 12, stream_handle(dev))
+        _lib.check(rc, "mmsim_knn_merge_certified")
+    return res
+
+
+def unpack_merged(allres: torch.Tensor, nq: int, S: int, k: int):
+    """[world, S * 3 k + 8] merged slices -> (dist [nq, k] f32, idx [nq, k] i64, uncertified count tensor)."""
+    world = allres.shape[0]
+    i = allres[:, :S * k * 2].reshape(world * S, 2 * k)[:nq].contiguous().view(torch.int64)
+    d = allres[:, S * k * 2:S * k * 3].reshape(world * S, k)[:nq].contiguous().view(torch.float32)
+    return d, i, allres[:, S * k * 3].sum()
+
+
 class ShardedGallery:
     """``ShardedGallery(gallery, group).retrieve(queries, k)`` -> identical (dist, idx) on every rank.
 
@@ -229,10 +281,17 @@ class ShardedGallery:
         if piv is not None:
             merge_pivots_into(allpiv.view(self.world, rows, 16), piv)
         rs.stage2(q, k, kp, exclude_self, self_offset, packed)
-        gathered = torch.empty((self.world, packed.numel()), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(gathered.view(-1), packed, group=self.group)
-        out_d, out_i, status = merge_certified(gathered, self._bases(dev), nq, kp, k)
-        if int(status[0]) != 0:          # identical on every rank (same inputs, same kernel): no extra collective needed
+        # merge by query slice: all-to-all of the candidate lists, merge + certify my slice, all-gather of the results
+        S = slice_rows(nq, self.world)
+        send = pack_slices(packed, nq, kp, self.world)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
+        mine = max(0, min(S, nq - self.rank * S))
+        res = merge_certified_slice(recv, self._bases(dev), mine, S, kp, k)
+        allres = torch.empty((self.world, res.numel()), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allres.view(-1), res, group=self.group)
+        out_d, out_i, uncertified = unpack_merged(allres, nq, S, k)
+        if int(uncertified) != 0:        # identical on every rank (it is part of the gathered buffer)
             return None
         return out_d, out_i
 

@@ -42,3 +42,29 @@ def test_torch_in_torch_out_and_self_distance(rs):
     assert torch.equal(d, d.T)
     with pytest.raises(NotImplementedError):
         mm.pairwise_distance(a, a, "cosine")
+
+
+@pytest.mark.parametrize("n,k,e,bias,normalized", [(5924, 1024, 128, True, True), (37, 100, 7, False, True), (300, 1024, 256, True, False),
+                                                   (65, 33, 160, True, True), (1, 1, 1, True, True)])
+def test_project_normalize(n, k, e, bias, normalized, rs):
+    """Embedding head (xw_plus_b + l2_normalize, src/networks.py:376-380, src/base_model_CUB.py:197-201) against a float64
+    restatement; the TF graph computes in fp32, so the bar is fp32 round-off: 1e-5 of the row scale."""
+    import multimodal_similarity_b200 as mm
+    x = rs.randn(n, k).astype(np.float32)
+    W = (rs.randn(k, e) / np.sqrt(k)).astype(np.float32)
+    b = rs.randn(e).astype(np.float32) if bias else None
+    y = x.astype(np.float64) @ W.astype(np.float64) + (0 if b is None else b.astype(np.float64))
+    ref = y / np.sqrt(np.maximum((y * y).sum(1, keepdims=True), 1e-10)) if normalized else y
+    got = mm.project_normalize(x, W, b, normalized=normalized)
+    assert got.shape == (n, e) and got.dtype == np.float32
+    assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+    if normalized and n > 1:
+        assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+
+
+def test_project_normalize_zero_row_uses_epsilon():
+    import multimodal_similarity_b200 as mm
+    x = np.zeros((3, 8), np.float32)
+    W = np.ones((8, 4), np.float32)
+    got = mm.project_normalize(x, W)                      # y = 0 -> 0 * rsqrt(1e-10) = 0, no NaN (tf.nn.l2_normalize)
+    assert np.array_equal(got, np.zeros((3, 4), np.float32))

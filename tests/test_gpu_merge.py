@@ -64,7 +64,21 @@ def _simulate_reduced(g, q, k, R, exclude_self):
     for r in range(R):
         shards[r].stage2(q, k, kp, exclude_self, 0, packed[r])
     gathered = torch.stack(packed)                   # the second all-gather
-    return merge_certified(gathered, torch.tensor(bases, device="cuda"), nq, kp, k), kp
+    whole = merge_certified(gathered, torch.tensor(bases, device="cuda"), nq, kp, k)
+    # the production path merges by query slice (all-to-all + all-gather): simulate it and require identical results
+    from multimodal_similarity_b200.sharded import merge_certified_slice, pack_slices, slice_rows, unpack_merged
+    S = slice_rows(nq, R)
+    sends = [pack_slices(packed[r], nq, kp, R) for r in range(R)]
+    bases_t = torch.tensor(bases, device="cuda")
+    res = []
+    for r in range(R):                               # rank r receives slice r of every shard
+        recv = torch.stack([sends[src][r] for src in range(R)])
+        res.append(merge_certified_slice(recv, bases_t, max(0, min(S, nq - r * S)), S, kp, k))
+    sd, si, unc = unpack_merged(torch.stack(res), nq, S, k)
+    assert int(unc) == int(whole[2][0])
+    if int(unc) == 0:
+        assert torch.equal(sd, whole[0]) and torch.equal(si, whole[1])
+    return whole, kp
 
 
 @pytest.mark.parametrize("R", [2, 4, 8])
