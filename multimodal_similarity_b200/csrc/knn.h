@@ -16,7 +16,7 @@ struct Plan {
   int n_splits, tiles_per_split, grid;
   int unc_cap;                // max uncertified queries handled by the exact fallback
   int logcap, use_pivots, n_sample_tiles, sample_cols, pivot_grid;   // candidate log / pivot pre-pass geometry
-  int n_anchor, group_blocks; // query grouping: anchors (0: queries keep the caller's order), blocks of the counting sort
+  int n_anchor, group_blocks, group_default; // query grouping: anchors (0: never), blocks of the counting sort, on outside shard mode
   size_t off_ah, off_apack, off_aidx, off_assign, off_perm, off_ghist;
   size_t off_qh, off_gh, off_gpack, off_qnorm, off_qerr, off_stats, off_piv16, off_ladder, off_log, off_log_cnt, off_log_tau, off_split_done;
   size_t off_unc_query, off_unc_bound, off_fb_count, off_fb_dist, off_fb_idx;

@@ -1176,10 +1176,11 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
     p.pivot_grid = std::min(num_sms, p.n_qblocks);
   }
 
-  // query grouping (see "query grouping" above): worth it when the sweep is long and there are enough queries to form
-  // groups of a warp's size around each anchor
-  p.n_anchor = 0;
-  if (p.use_pivots && p.n_tiles >= 256) p.n_anchor = nq >= 65536 ? 4096 : nq >= 16384 ? 2048 : nq >= 4096 ? 1024 : 0;
+  // query grouping (see "query grouping" above): anchors for enough queries to form groups of a warp's size; on by
+  // default when the sweep is long enough to repay the 0.3 ms, and ALWAYS in gallery-shard mode (every shard must derive
+  // the same sweep order from the queries alone: the pivot lists they exchange are indexed by sweep position)
+  p.n_anchor = nq >= 65536 ? 4096 : nq >= 16384 ? 2048 : nq >= 4096 ? 1024 : 0;
+  p.group_default = p.use_pivots && p.n_tiles >= 256;
   if (const char* e = getenv("MMSIM_KNN_GROUP")) {     // experiment switch: 0 = off
     if (atoi(e) == 0) p.n_anchor = 0;
   }
@@ -1287,7 +1288,8 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   float* apack = reinterpret_cast<float*>(w + p.off_apack);
   int* aidx = reinterpret_cast<int*>(w + p.off_aidx);
   int* assign = reinterpret_cast<int*>(w + p.off_assign);
-  int* perm = p.n_anchor ? reinterpret_cast<int*>(w + p.off_perm) : nullptr;
+  const bool group = p.n_anchor != 0 && (shard_kp != 0 || p.group_default);
+  int* perm = group ? reinterpret_cast<int*>(w + p.off_perm) : nullptr;
   int* ghist = reinterpret_cast<int*>(w + p.off_ghist);
 
   if (phases & kPhaseRerank) {
@@ -1312,7 +1314,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     const unsigned qb = unsigned(std::min<int64_t>((nq + warps_per_block - 1) / warps_per_block, cap));
     prep<<<qb, PREP_THREADS, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, 0, nullptr, nullptr);
     MMSIM_CUDA_CHECK(cudaGetLastError());
-    if (p.n_anchor) {
+    if (group) {
       // query grouping: anchors = evenly spaced query rows -> nearest anchor of every query (tensor cores) -> stable
       // counting sort -> operand copies of the queries again, in the sweep's order
       const int a_tiles = p.n_anchor / BN;
