@@ -176,7 +176,7 @@ struct Smem {
   static constexpr int CNT_OFF = TAU_OFF + BM * 4;            // u32   [BM]   packed log cursor + ladder counters
   static constexpr int PV_OFF = CNT_OFF + BM * 4;             // float [4][NPSUB][BM] pivot pre-pass: per-warp sorted sub-lists
   static constexpr int BAR_OFF = PV_OFF + 4 * NPSUB * BM * 4;
-  static constexpr int NUM_BARS = 2 * NS + 2 + 2 + 2 + NT;
+  static constexpr int NUM_BARS = 2 * NS + 2 + 2 + 2 + NT + NT;
   static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
   static constexpr int TOTAL = TMEM_PTR_OFF + 8;
   static constexpr int DYN_BYTES = TOTAL;
@@ -264,7 +264,12 @@ __device__ __forceinline__ int tile_of(const SweepArgs& a, int t0, int i) {
 
 // ABL: ablation variants for scripts/sweep_ablate.py (wrong results by construction): 0 = product, 2 = never log a
 // candidate (first-level test only), 4 = drain the accumulator without scanning it.
-template <int KATOMS, int NEPI, int MODE, int ABL>
+// PAIR: two CTAs of a cluster (adjacent SMs) work as one tcgen05 cta_group::2 unit: each has its own 128 queries and its
+// own accumulators, but a 256-row gallery tile is loaded ONCE per pair -- each CTA's TMA brings half of it into its own
+// shared memory and the pair's MMAs (issued by the leader CTA, M = 256) read both halves.  Per CTA and tile that halves
+// the TMA writes into shared memory and the L2 -> SM traffic; the 1-CTA kernel moves 160 KB through a 128 B/cycle shared
+// memory per 1,024-cycle tile (64 KB TMA writes + 96 KB operand reads), the pair 96 KB.
+template <int KATOMS, int NEPI, int MODE, int ABL, bool PAIR>
 __global__ void __launch_bounds__(128 + NEPI * 32, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_g, const SweepArgs a) {
   using S = Smem<KATOMS>;
@@ -290,10 +295,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   uint64_t* afull = bars + 2 * NS + 4;   //       query tile landed
   uint64_t* aempty = bars + 2 * NS + 5;  //       all MMAs of the item done, query tile may be overwritten
   uint64_t* nempty = bars + 2 * NS + 6;  // [NT]  epilogue finished a tile: its norm-pack slot may be refilled
+  uint64_t* nfull = bars + 2 * NS + 6 + NT;  // [NT]  PAIR: this CTA's copy of a tile's norm pack landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + S::TMEM_PTR_OFF);
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
+  const uint32_t crank = PAIR ? ptx::cluster_ctarank() : 0u;   // rank in the CTA pair; 0 = leader (issues the MMAs)
+  constexpr int BROWS = PAIR ? BN / 2 : BN;                    // gallery rows of a tile in THIS CTA's shared memory
+  constexpr int B_BYTES = BROWS * 128;                         // ... per K atom
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_q);
@@ -304,24 +313,35 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull[i], 1);
-      ptx::mbar_init(&tempty[i], EPI_THREADS);
+      // PAIR: one elected arrival per epilogue warp of BOTH CTAs (they arrive on the leader's barrier)
+      ptx::mbar_init(&tempty[i], PAIR ? 2 * NEPI : EPI_THREADS);
     }
     ptx::mbar_init(afull, 1);
     ptx::mbar_init(aempty, 1);
-    for (int i = 0; i < NT; ++i) ptx::mbar_init(&nempty[i], EPI_THREADS);
+    for (int i = 0; i < NT; ++i) {
+      ptx::mbar_init(&nempty[i], EPI_THREADS);
+      ptx::mbar_init(&nfull[i], 1);
+    }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_ptr, 2 * BN);  // 512 columns: two 128x256 fp32 accumulators
+  if (warp == 1) {                                     // 512 columns: two 128x256 fp32 accumulators
+    if (PAIR) ptx::tmem_alloc_pair(tmem_ptr, 2 * BN); else ptx::tmem_alloc(tmem_ptr, 2 * BN);
+  }
   ptx::tc_fence_before();
   __syncthreads();
+  if (PAIR) ptx::cluster_sync();                       // the peer's barriers are initialised before anyone signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int n_items = MODE == MODE_SWEEP ? a.n_qblocks * a.n_splits : a.n_qblocks;
+  // items: (split, query block) -- PAIR: (split, PAIR of query blocks), this CTA takes block 2 * pair + rank
+  const int n_qb_items = PAIR ? (a.n_qblocks + 1) / 2 : a.n_qblocks;
+  const int n_items = MODE == MODE_SWEEP ? n_qb_items * a.n_splits : a.n_qblocks;
+  const int item0 = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x), item_step = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
   auto item_range = [&](int item, int& qb, int& split, int& t0, int& nt) {
     if (MODE == MODE_SWEEP) {
-      split = item / a.n_qblocks;
-      qb = item - split * a.n_qblocks;
+      split = item / n_qb_items;
+      qb = item - split * n_qb_items;
+      if (PAIR) qb = 2 * qb + int(crank);              // may be == n_qblocks (odd count): all rows invalid, loads zero-filled
       t0 = split * a.tiles_per_split;
       nt = min(a.n_tiles, t0 + a.tiles_per_split) - t0;
     } else {
@@ -336,24 +356,41 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     // =============================================================== TMA producer (one thread)
     if (lane == 0) {
       uint32_t it = 0, tc = 0, ic = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
+      for (int item = item0; item < n_items; item += item_step, ++ic) {
         int qb, split, t0, nt;
         item_range(item, qb, split, t0, nt);
         ptx::mbar_wait(aempty, (ic & 1) ^ 1);
-        ptx::mbar_expect_tx(afull, KATOMS * A_ATOM_BYTES);
-        for (int ka = 0; ka < KATOMS; ++ka)
-          ptx::tma_load_2d(smem_a + ka * A_ATOM_BYTES, &tm_q, ka * KATOM, qb * BM, afull);
+        if (!PAIR) {
+          ptx::mbar_expect_tx(afull, KATOMS * A_ATOM_BYTES);
+          for (int ka = 0; ka < KATOMS; ++ka)
+            ptx::tma_load_2d(smem_a + ka * A_ATOM_BYTES, &tm_q, ka * KATOM, qb * BM, afull);
+        } else {
+          // both CTAs' query tiles are counted on the leader's barrier, which expects the bytes of the pair
+          if (crank == 0) ptx::mbar_expect_tx(afull, 2 * KATOMS * A_ATOM_BYTES);
+          for (int ka = 0; ka < KATOMS; ++ka)
+            ptx::tma_load_2d_pair(smem_a + ka * A_ATOM_BYTES, &tm_q, ka * KATOM, qb * BM, afull);
+        }
         for (int i = 0; i < nt; ++i, ++tc) {
           const int t = tile_of<MODE>(a, t0, i);
           for (int ka = 0; ka < KATOMS; ++ka, ++it) {
             const uint32_t stage = it % NS, phase = (it / NS) & 1;
             ptx::mbar_wait(&empty[stage], phase ^ 1);
-            ptx::mbar_expect_tx(&full[stage], B_STAGE_BYTES + (ka == 0 ? NPACK * 4 : 0));
-            ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tm_g, ka * KATOM, t * BN, &full[stage]);
+            if (!PAIR) {
+              ptx::mbar_expect_tx(&full[stage], B_STAGE_BYTES + (ka == 0 ? NPACK * 4 : 0));
+              ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tm_g, ka * KATOM, t * BN, &full[stage]);
+            } else {
+              if (crank == 0) ptx::mbar_expect_tx(&full[stage], 2 * B_BYTES);
+              ptx::tma_load_2d_pair(smem_b + stage * B_BYTES, &tm_g, ka * KATOM, t * BN + int(crank) * BROWS, &full[stage]);
+            }
             if (ka == 0) {
               // the epilogue reads this tile's norms long after it released the accumulator: separate hand-back
               ptx::mbar_wait(&nempty[tc % NT], ((tc / NT) & 1) ^ 1);
-              ptx::bulk_load_1d(norm_ring + (tc % NT) * NPACK, a.gpack + size_t(t) * NPACK, NPACK * 4, &full[stage]);
+              if (!PAIR) {
+                ptx::bulk_load_1d(norm_ring + (tc % NT) * NPACK, a.gpack + size_t(t) * NPACK, NPACK * 4, &full[stage]);
+              } else {   // every CTA needs the whole tile's pack: its own copy, its own barrier
+                ptx::mbar_expect_tx(&nfull[tc % NT], NPACK * 4);
+                ptx::bulk_load_1d(norm_ring + (tc % NT) * NPACK, a.gpack + size_t(t) * NPACK, NPACK * 4, &nfull[tc % NT]);
+              }
             }
           }
         }
@@ -361,18 +398,20 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // =============================================================== MMA issuer (one thread issues, warp waits)
-    const uint32_t idesc = ptx::umma_idesc_f16(BM, BN);
+    // PAIR: only the leader CTA issues (M = 256 over both CTAs' query tiles); the peer's warp 1 just owns its TMEM
+    const uint32_t idesc = ptx::umma_idesc_f16(PAIR ? 2 * BM : BM, BN);
     const uint64_t adesc0 = ptx::umma_desc_k128(ptx::smem_u32(smem_a));
     const uint64_t bdesc0 = ptx::umma_desc_k128(ptx::smem_u32(smem_b));
     uint32_t it = 0, tc = 0, ic = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ic) {
+    if (!PAIR || crank == 0) {
+    for (int item = item0; item < n_items; item += item_step, ++ic) {
       int qb, split, t0, nt;
       item_range(item, qb, split, t0, nt);
       ptx::mbar_wait(afull, ic & 1);
       ptx::tc_fence_after();
       for (int i = 0; i < nt; ++i, ++tc) {
         const uint32_t as = tc & 1;
-        ptx::mbar_wait(&tempty[as], ((tc >> 1) & 1) ^ 1);
+        ptx::mbar_wait(&tempty[as], ((tc >> 1) & 1) ^ 1);   // (a spinning wait here is slower: 22.3 vs 21.2 ms)
         ptx::tc_fence_after();
         for (int ka = 0; ka < KATOMS; ++ka, ++it) {
           const uint32_t stage = it % NS, phase = (it / NS) & 1;
@@ -382,17 +421,26 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < KATOM / 16; ++k) {
               const uint64_t ad = adesc0 + uint64_t(ka * (A_ATOM_BYTES >> 4) + k * 2);
-              const uint64_t bd = bdesc0 + uint64_t(stage * (B_STAGE_BYTES >> 4) + k * 2);
-              ptx::umma_f16(tmem_base + as * BN, ad, bd, idesc, (ka | k) != 0);
+              const uint64_t bd = bdesc0 + uint64_t(stage * (B_BYTES >> 4) + k * 2);
+              if (PAIR) ptx::umma_f16_pair(tmem_base + as * BN, ad, bd, idesc, (ka | k) != 0);
+              else ptx::umma_f16(tmem_base + as * BN, ad, bd, idesc, (ka | k) != 0);
             }
-            ptx::umma_commit(&empty[stage]);                      // smem stage reusable once these MMAs retire
-            if (ka == KATOMS - 1) ptx::umma_commit(&tfull[as]);   // accumulator complete
+            if (PAIR) {
+              ptx::umma_commit_pair(&empty[stage]);                      // both CTAs' producers
+              if (ka == KATOMS - 1) ptx::umma_commit_pair(&tfull[as]);   // both CTAs' epilogue warps
+            } else {
+              ptx::umma_commit(&empty[stage]);                      // smem stage reusable once these MMAs retire
+              if (ka == KATOMS - 1) ptx::umma_commit(&tfull[as]);   // accumulator complete
+            }
           }
           __syncwarp();
         }
       }
-      if (lane == 0) ptx::umma_commit(aempty);
+      if (lane == 0) {
+        if (PAIR) ptx::umma_commit_pair(aempty); else ptx::umma_commit(aempty);
+      }
       __syncwarp();
+    }
     }
   }
   } else {
@@ -407,11 +455,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 #endif
     uint32_t tc = 0;
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = item0; item < n_items; item += item_step) {
       int qb, split, t0, nt;
       item_range(item, qb, split, t0, nt);
-      const int grow = qb * BM + row;          // global query row (may be >= nq in the last block)
-      const bool valid = grow < a.nq;
+      const bool qb_ok = !PAIR || qb < a.n_qblocks;      // PAIR: the second CTA of the last pair may have no block
+      const int grow = (qb_ok ? qb : 0) * BM + row;      // global query row (may be >= nq in the last block)
+      const bool valid = qb_ok && grow < a.nq;
 
       float piv0 = -kInf, piv1 = -kInf;                 // MODE_SWEEP: ladder below the initial threshold
       uint32_t carry = 0;                               // MODE_SWEEP: rows finished splits logged below piv1 | piv0 << 15
@@ -561,7 +610,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
           ptx::tmem_ld_wait(vb);
           if (last) {
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&tempty[as]);
+            if (PAIR) {
+              __syncwarp();                                   // every lane's loads have landed
+              if (lane == 0) ptx::mbar_arrive_leader(&tempty[as]);
+              ptx::mbar_wait(&nfull[tc % NT], (tc / NT) & 1); // this CTA's copy of the tile's norm pack
+            } else {
+              ptx::mbar_arrive(&tempty[as]);
+            }
           }
           const float tau = MODE == MODE_SWEEP ? lds_f32(tau_addr) : pv_thr;
           if (sampled(c0)) scan_chunk(va, c0, nrm, col0, tau);
@@ -584,7 +639,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
       if (MODE == MODE_SWEEP) {
         epi_bar_sync(EPI_THREADS);             // all appends of this item are done
-        if (h == 0) {
+        if (h == 0 && qb_ok) {
           const size_t o = size_t(grow) * a.n_splits + split;
           const uint32_t cn = s_cnt[row];
           a.log_cnt[o] = int(cn & CUR_MASK);
@@ -643,7 +698,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 2 * BN);
+  if (PAIR) ptx::cluster_sync();       // the peer may still be reading accumulators the pair's allocation covers
+  if (warp == 1) {
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, 2 * BN); else ptx::tmem_dealloc(tmem_base, 2 * BN);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ query grouping
@@ -1220,6 +1278,17 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
 // profiles/r1_b_log_epilogue_nepi8.txt, r1_c_nepi16.txt).
 constexpr int NEPI_SWEEP = 16;
 
+// MMSIM_KNN_PAIR=1: run the sweep as CTA pairs (tcgen05 cta_group::2), see the PAIR template parameter.  Opt-in: results
+// are identical (tests/test_gpu_knn.py::test_cta_pair_sweep_matches), but on B200 it is not faster -- 28.1 vs 21.2 ms at
+// 128-d, 43.0 vs 42.8 ms at 256-d (gpurun_out/pair_ab.log): the MMA warp and the epilogue warps hand each 256-column
+// accumulator back and forth once per tile, the pair adds a cross-SM hop to that loop (remote mbarrier arrive, multicast
+// commit), and at K = 128 the loop, not shared-memory bandwidth, sets the tile rate.  Read on every call so that a test
+// can switch it.
+static bool sweep_pairs() {
+  const char* e = getenv("MMSIM_KNN_PAIR");
+  return e && atoi(e) == 1;
+}
+
 // MMSIM_SWEEP_FLAGS (scripts/sweep_ablate.py): 2 = never log a candidate, 4 = TMEM drain only.  Ablations, wrong results.
 static int sweep_ablation() {
   const char* e = getenv("MMSIM_SWEEP_FLAGS");
@@ -1229,10 +1298,30 @@ static int sweep_ablation() {
 template <int KATOMS, int NEPI, int MODE, int ABL>
 static int launch_tc(int grid, const CUtensorMap& tq, const CUtensorMap& tg, const SweepArgs& args, cudaStream_t stream) {
   using S = Smem<KATOMS>;
-  auto kern = knn_tc_kernel<KATOMS, NEPI, MODE, ABL>;
+  auto kern = knn_tc_kernel<KATOMS, NEPI, MODE, ABL, false>;
   MMSIM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
   kern<<<grid, 128 + NEPI * 32, S::DYN_BYTES, stream>>>(tq, tg, args);
   MMSIM_CUDA_CHECK(cudaGetLastError());
+  return MMSIM_OK;
+}
+
+// the sweep as CTA pairs (clusters of 2): grid = an even number of CTAs, tg = tensor map with 128-row boxes
+template <int KATOMS>
+static int launch_pair(int grid, const CUtensorMap& tq, const CUtensorMap& tg, const SweepArgs& args, cudaStream_t stream) {
+  using S = Smem<KATOMS>;
+  auto kern = knn_tc_kernel<KATOMS, NEPI_SWEEP, MODE_SWEEP, 0, true>;
+  MMSIM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(grid));
+  cfg.blockDim = dim3(128 + NEPI_SWEEP * 32);
+  cfg.dynamicSmemBytes = S::DYN_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MMSIM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tq, tg, args));
   return MMSIM_OK;
 }
 
@@ -1386,6 +1475,19 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
         MMSIM_CUDA_CHECK(cudaMemsetAsync(split_done, 0, size_t(p.n_qblocks) * BM * p.n_splits * 4, stream));
       const int abl = sweep_ablation();
       args.close_rows = abl == 8;
+      if (sweep_pairs() && (abl == 0 || abl == 8)) {
+        CUtensorMap tgh;
+        rc = make_tmap(&tgh, gh, ng, p.Dp, BN / 2);
+        if (rc) return rc;
+        const int grid = std::min(num_sms & ~1, 2 * ((p.n_qblocks + 1) / 2) * p.n_splits);
+        switch (p.katoms) {
+          case 1: rc = launch_pair<1>(grid, tq, tgh, args, stream); break;
+          case 2: rc = launch_pair<2>(grid, tq, tgh, args, stream); break;
+          case 3: rc = launch_pair<3>(grid, tq, tgh, args, stream); break;
+          default: rc = launch_pair<4>(grid, tq, tgh, args, stream); break;
+        }
+        if (rc) return rc;
+      } else
       rc = abl == 2   ? launch_mode<MODE_SWEEP, 2>(p.katoms, p.grid, tq, tg, args, stream)
            : abl == 4 ? launch_mode<MODE_SWEEP, 4>(p.katoms, p.grid, tq, tg, args, stream)
                       : launch_mode<MODE_SWEEP, 0>(p.katoms, p.grid, tq, tg, args, stream);

@@ -170,3 +170,19 @@ def test_unclustered_data_certifies(normalize):
     rows = [0, 1, 77, 4095]
     ref_d, ref_i = O.knn(q[rows].cpu().numpy(), g.cpu().numpy(), 100)
     assert_knn_equal(d[rows].cpu().numpy(), i[rows].cpu().numpy().astype(np.int64), ref_d, ref_i)
+
+
+def test_cta_pair_sweep_matches(rs, monkeypatch):
+    """The sweep as CTA pairs (MMSIM_KNN_PAIR=1: clusters of two CTAs, tcgen05 cta_group::2, each CTA's TMA loading half of
+    every gallery tile) returns exactly what the single-CTA sweep returns -- odd and even numbers of query blocks."""
+    import multimodal_similarity_b200 as mm
+    x, _ = clustered(rs, 70000, 128, 40)
+    g = torch.from_numpy(x).cuda()
+    for nq in (300, 1000):                                   # 3 and 8 query blocks
+        q = torch.from_numpy(clustered(rs, nq, 128, 40)[0]).cuda()
+        monkeypatch.delenv("MMSIM_KNN_PAIR", raising=False)
+        d0, i0 = mm.retrieve(q, g, 50)
+        monkeypatch.setenv("MMSIM_KNN_PAIR", "1")
+        d1, i1 = mm.retrieve(q, g, 50)
+        assert torch.equal(d0, d1) and torch.equal(i0, i1)
+    monkeypatch.delenv("MMSIM_KNN_PAIR", raising=False)
