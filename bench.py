@@ -417,7 +417,10 @@ def main():
         "metric": "knn_queries_per_s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f16 tensor-core filter + f32 exact re-rank", "data": "synthetic", "config": config_of(a, world),
-        "clocks": clocks, "e2e": e2e, "gpu_launches": 17 * a.steps,   # per step: 4 operand-copy + 1 norm-pack kernels, 6 query-grouping kernels (anchor index, tcgen05 assign pass, 4 counting-sort), tcgen05 pivot pre-pass, ladder, tcgen05 sweep, re-rank, then 2 fallback kernels (N=1) or pivot merge + certified merge (N>1); profiles/r1_g_launches.csv "roofline": roofline,
+        # our kernels per step: 4 operand-copy + 1 norm-pack, 6 query-grouping (anchor index, tcgen05 assign pass, 4 counting
+        # sort), tcgen05 pivot pre-pass, ladder, tcgen05 sweep, re-rank, then 2 fallback kernels (N=1) or pivot merge +
+        # certified merge (N>1); profiles/r1_g_launches.csv
+        "clocks": clocks, "e2e": e2e, "gpu_launches": 17 * a.steps, "roofline": roofline,
         "exact_fallback_queries": fell_back, "protocol": sg.last_protocol if world > 1 else "single",
     }
 
