@@ -98,7 +98,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -297,7 +297,21 @@ def main():
         step()
     with ClockSampler(local) as clk:
         ms, (out_d, out_i) = timed(step, a.steps)
+        # the timed region can be shorter than nvidia-smi's sampling period (K steps of a few ms at N = 8): keep the SAME
+        # load running, untimed, until the sampler has a few rows (every rank takes the same number of extra steps)
+        extra = 0
+        while extra < 200:
+            n_rows = torch.tensor([len(clk.rows)], device=dev)
+            if world > 1:
+                dist.all_reduce(n_rows, op=dist.ReduceOp.MIN)
+            if int(n_rows) >= 4:
+                break
+            for _ in range(5):
+                step()
+            torch.cuda.synchronize()
+            extra += 5
     clocks = clk.summary()
+    clocks["untimed_extra_steps_for_sampling"] = extra
     fell_back = check_status(statuses[-1]) if statuses else 0
     value = Q * a.steps / (ms / 1e3)
 
