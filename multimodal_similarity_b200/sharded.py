@@ -194,8 +194,14 @@ def merge_certified_slice(recv: torch.Tensor, bases: torch.Tensor, n_rows: int, 
 def unpack_merged(allres: torch.Tensor, nq: int, S: int, k: int):
     """[world, S * 3 k + 8] merged slices -> (dist [nq, k] f32, idx [nq, k] i64, uncertified count tensor)."""
     world = allres.shape[0]
-    i = allres[:, :S * k * 2].reshape(world * S, 2 * k)[:nq].contiguous().view(torch.int64)
-    d = allres[:, S * k * 2:S * k * 3].reshape(world * S, k)[:nq].contiguous().view(torch.float32)
+    # explicit copies into fresh buffers: the int64 view needs 8-byte aligned rows, and a slice that happens to be a view
+    # of `allres` (odd row pitch) would not have them
+    i = torch.empty((nq, 2 * k), dtype=torch.int32, device=allres.device)
+    i.copy_(allres[:, :S * k * 2].reshape(world * S, 2 * k)[:nq])
+    i = i.view(torch.int64)
+    d = torch.empty((nq, k), dtype=torch.int32, device=allres.device)
+    d.copy_(allres[:, S * k * 2:S * k * 3].reshape(world * S, k)[:nq])
+    d = d.view(torch.float32)
     return d, i, allres[:, S * k * 3].sum()
 
 

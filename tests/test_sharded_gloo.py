@@ -94,3 +94,37 @@ def test_shard_bounds_cover_and_partition():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[r][1] == b[r + 1][0] for r in range(w - 1))
             assert all(lo <= hi for lo, hi in b)
+
+
+def test_slice_packing_roundtrip():
+    """Host-side layout of the reduced protocol's exchange (pure tensor ops, runs on CPU): pack_slices lays every
+    destination rank's query slice out contiguously, unpack_merged reassembles the all-gathered merged slices."""
+    from multimodal_similarity_b200.sharded import ReducedShard, pack_slices, slice_rows, unpack_merged
+    for nq, kp, k, world in ((10, 3, 2, 4), (7, 5, 5, 2), (1, 2, 1, 3), (64, 47, 10, 8)):
+        S = slice_rows(nq, world)
+        packed = torch.zeros(ReducedShard.packed_elems(nq, kp), dtype=torch.int32)
+        d_, i_, lb_, st_ = ReducedShard._views(packed, nq, kp)
+        d_.copy_(torch.arange(nq * kp, dtype=torch.float32).view(nq, kp) + 0.5)
+        i_.copy_(torch.arange(nq * kp, dtype=torch.int32).view(nq, kp) * 3)
+        lb_.copy_(torch.arange(nq, dtype=torch.float32) + 0.25)
+        send = pack_slices(packed, nq, kp, world)
+        assert send.shape == (world, S * (2 * kp + 1))
+        for r in range(world):
+            rows = range(r * S, min(nq, (r + 1) * S))
+            dd = send[r, :S * kp].view(torch.float32).view(S, kp)
+            ii = send[r, S * kp:2 * S * kp].view(S, kp)
+            ll = send[r, 2 * S * kp:].view(torch.float32)
+            for n_, q in enumerate(rows):
+                assert torch.equal(dd[n_], d_[q]) and torch.equal(ii[n_], i_[q]) and ll[n_] == lb_[q]
+        # merged slices as merge_certified_slice lays them out: | idx int64 S x k | dist S x k | status 8 |
+        allres = torch.zeros((world, S * k * 3 + 8), dtype=torch.int32)
+        want_d = torch.arange(nq * k, dtype=torch.float32).view(nq, k)
+        want_i = (torch.arange(nq * k, dtype=torch.int64).view(nq, k) << 33) + 5          # needs all 64 bits
+        for r in range(world):
+            lo, hi = r * S, min(nq, (r + 1) * S)
+            if hi > lo:
+                allres[r, :(hi - lo) * k * 2] = want_i[lo:hi].contiguous().view(torch.int32).reshape(-1)
+                allres[r, S * k * 2:S * k * 2 + (hi - lo) * k] = want_d[lo:hi].contiguous().view(torch.int32).reshape(-1)
+            allres[r, S * k * 3] = r                                                        # uncertified count of the slice
+        got_d, got_i, unc = unpack_merged(allres, nq, S, k)
+        assert torch.equal(got_d, want_d) and torch.equal(got_i, want_i) and int(unc) == sum(range(world))
