@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
   float* pid_i = Ej + TJ * DP;    // [TI]
   float* pid_j = pid_i + TI;      // [TJ]
   float* st = pid_j + TJ;         // lifted: per-row stats for TI + TJ rows: fp, cn, coef -> 3 * (TI + TJ)
-  float* Ss = st + 3 * (TI + TJ); // lifted: S tile [TI][TJ + 1]
+  float* Ss = st + 3 * (TI + TJ); // lifted: S tile, transposed [TJ][TI + 4] (16-byte aligned rows)
   __shared__ int s_red[THREADS / 32];
   __shared__ int s_W;
   __shared__ int s_last;
@@ -477,19 +477,31 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(const Params p) {
             if (cj != 0.f) s -= cj * expf(p.margin - dist - st[(TI + TJ) + TI + lj]);
           }
         }
-        Ss[li * (TJ + 1) + lj] = s;
+        Ss[lj * (TI + 4) + li] = s;                 // transposed: the gradient loop reads four rows of a column at once
       }
     }
     __syncthreads();
-    // dE[i][d] += 2 * sum_j S_ij (e_i[d] - e_j[d])
-    for (int x = t; x < TI * D; x += THREADS) {
-      const int li = x / D, d = x - li * D;
-      if (i0 + li >= N) continue;
-      const float eid = Ei[li * DP + d];
-      float o = 0.f;
-#pragma unroll 8
-      for (int lj = 0; lj < TJ; ++lj) o = fmaf(Ss[li * (TJ + 1) + lj], eid - Ej[lj * DP + d], o);
-      if (o != 0.f) atomicAdd(&p.dE[size_t(i0 + li) * D + d], 2.f * o);
+    // dE[i][d] += 2 * sum_j S_ij (e_i[d] - e_j[d]).  A thread owns one feature d and FOUR rows at a time, so every e_j[d]
+    // it loads from shared memory is used four times (the one-row form did two shared loads per FMA and the loop was
+    // shared-memory-issue bound).
+    static_assert(TI % 4 == 0, "rows are processed four at a time");
+    for (int x = t; x < (TI / 4) * D; x += THREADS) {
+      const int lq = x / D, d = x - lq * D, li0 = lq * 4;
+      float ei[4], o[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { ei[a] = Ei[(li0 + a) * DP + d]; o[a] = 0.f; }
+#pragma unroll 4
+      for (int lj = 0; lj < TJ; ++lj) {
+        const float ej = Ej[lj * DP + d];
+        const float4 s4 = *reinterpret_cast<const float4*>(Ss + lj * (TI + 4) + li0);   // one broadcast load
+        o[0] = fmaf(s4.x, ei[0] - ej, o[0]);
+        o[1] = fmaf(s4.y, ei[1] - ej, o[1]);
+        o[2] = fmaf(s4.z, ei[2] - ej, o[2]);
+        o[3] = fmaf(s4.w, ei[3] - ej, o[3]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if (i0 + li0 + a < N && o[a] != 0.f) atomicAdd(&p.dE[size_t(i0 + li0 + a) * D + d], 2.f * o[a]);
     }
   }
 
@@ -821,7 +833,7 @@ static const int kShapes[3][2] = {{2, 2}, {4, 4}, {8, 8}};
 
 static size_t smem_for(int TI, int TJ, int64_t D) {
   const int D4 = int((D + 3) & ~int64_t(3));
-  return size_t(TI + TJ) * (D4 + 4) * 4 + size_t(TI + TJ) * 4 + size_t(3) * (TI + TJ) * 4 + size_t(TI) * (TJ + 1) * 4;
+  return size_t(TI + TJ) * (D4 + 4) * 4 + size_t(TI + TJ) * 4 + size_t(3) * (TI + TJ) * 4 + size_t(TJ) * (TI + 4) * 4 + 16;
 }
 
 static const void* kernel_for(int shape, int kind) {
