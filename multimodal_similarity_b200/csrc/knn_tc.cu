@@ -176,7 +176,7 @@ struct Smem {
   static constexpr int CNT_OFF = TAU_OFF + BM * 4;            // u32   [BM]   packed log cursor + ladder counters
   static constexpr int PV_OFF = CNT_OFF + BM * 4;             // float [4][NPSUB][BM] pivot pre-pass: per-warp sorted sub-lists
   static constexpr int BAR_OFF = PV_OFF + 4 * NPSUB * BM * 4;
-  static constexpr int NUM_BARS = 2 * NS + 2 + 2 + 2 + NT + NT;
+  static constexpr int NUM_BARS = 4 * NS + 2 + 2 + 2 + NT + NT;   // PAIR runs twice the stages (half the bytes each)
   static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
   static constexpr int TOTAL = TMEM_PTR_OFF + 8;
   static constexpr int DYN_BYTES = TOTAL;
@@ -273,7 +273,7 @@ template <int KATOMS, int NEPI, int MODE, int ABL, bool PAIR>
 __global__ void __launch_bounds__(128 + NEPI * 32, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_g, const SweepArgs a) {
   using S = Smem<KATOMS>;
-  constexpr int NS = S::NS;
+  constexpr int NS = PAIR ? 2 * S::NS : S::NS;   // PAIR: a stage holds half a tile's K atom (16 KiB), so twice as many fit
   constexpr int NH = NEPI / 4;            // epilogue warps per TMEM lane quarter; each takes every NH-th 32-column chunk
   constexpr int EPI_THREADS = NEPI * 32;
   // No static shared memory in this kernel, so the dynamic window starts at the CTA's shared base and the declared
