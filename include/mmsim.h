@@ -181,6 +181,15 @@ MMSIM_API int mmsim_evaluate_large_f32(const float* E, const int32_t* labels, co
 MMSIM_API int mmsim_project_normalize_f32(const float* X, int64_t N, int64_t K, const float* W, const float* b, int64_t E,
                                 int normalized, float epsilon, float* out, mmsim_stream_t stream);
 
+/* tf.contrib's triplet_semihard_loss (metric_loss_ops.triplet_semihard_loss(labels, embeddings, margin),
+ * src/base_CUB.py:163-166), forward + backward: loss[0] = mean over (anchor, positive) pairs of
+ * max(margin + D_ap - n*, 0) with n* the smallest negative distance beyond D_ap, else the largest negative distance
+ * (squared distances); dE (nullable) = d loss / d E.  labels int32 [N], E [N, D] fp32; N <= 8192.  The TF function is a
+ * third-party dependency of the reference that is neither vendored nor installable here: parity unpinned. */
+MMSIM_API int mmsim_triplet_semihard_workspace_bytes(int64_t N, size_t* bytes);
+MMSIM_API int mmsim_triplet_semihard_f32(const float* E, const int32_t* labels, int64_t N, int64_t D, float margin, float* loss,
+                               float* dE, void* workspace, size_t workspace_bytes, mmsim_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@
 #include "merge.h"
 #include "mining.h"
 #include "project.h"
+#include "semihard_loss.h"
 #include "sqdist.h"
 
 namespace mmsim {
@@ -158,6 +159,13 @@ MMSIM_API int mmsim_evaluate_large_f32(const float* E, const int32_t* labels, co
 MMSIM_API int mmsim_project_normalize_f32(const float* X, int64_t N, int64_t K, const float* W, const float* b, int64_t E,
                                 int normalized, float epsilon, float* out, mmsim_stream_t stream) {
   return project::run(X, N, K, W, b, E, normalized, epsilon, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+MMSIM_API int mmsim_triplet_semihard_workspace_bytes(int64_t N, size_t* bytes) { return semihard_loss::workspace_bytes(N, bytes); }
+
+MMSIM_API int mmsim_triplet_semihard_f32(const float* E, const int32_t* labels, int64_t N, int64_t D, float margin, float* loss,
+                               float* dE, void* workspace, size_t workspace_bytes, mmsim_stream_t stream) {
+  return semihard_loss::run(E, labels, N, D, margin, loss, dE, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -119,3 +119,42 @@ def lifted_loss(dists_or_embeddings, pids, margin, weighted=True) -> LossOutput:
     """The reference's lifted-structured variant (src/networks.py:835-870); num_active is the constant 1.0."""
     emb, pids = _prepare(dists_or_embeddings, pids)
     return _wrap(_FusedLoss.apply(emb.contiguous(), pids, _lib.LOSS_LIFTED, False, float(margin), weighted))
+
+
+# --------------------------------------------------------------------------- tf.contrib triplet_semihard_loss (K8)
+class _SemihardLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, labels, margin):
+        lib = _lib.load()
+        n, d = emb.shape
+        dev = emb.device
+        c = ctypes.c_size_t()
+        _lib.check(lib.mmsim_triplet_semihard_workspace_bytes(n, ctypes.byref(c)), "mmsim_triplet_semihard_workspace_bytes")
+        ws = workspace("semihard_loss", c.value, dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(emb) if emb.requires_grad else None
+        with torch.cuda.device(dev):
+            rc = lib.mmsim_triplet_semihard_f32(emb.data_ptr(), labels.data_ptr(), n, d, float(margin), loss.data_ptr(),
+                                                _lib.ptr(grad), ws.data_ptr(), ws.numel(), stream_handle(dev))
+        _lib.check(rc, "mmsim_triplet_semihard_f32")
+        ctx.grad = grad
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None if ctx.grad is None else ctx.grad * g), None, None
+
+
+def triplet_semihard_loss(labels, embeddings, margin=1.0):
+    """``tf.contrib.losses.metric_learning.triplet_semihard_loss(labels, embeddings, margin)`` -- the loss the reference's
+    CUB trainers select with ``--loss triplet`` (src/base_CUB.py:163-166) -- forward and backward on the device
+    (csrc/semihard_loss.cu).  Same argument order as the TF function; returns a scalar CUDA tensor that supports
+    ``.backward()`` when ``embeddings`` requires grad.  Parity with TF is unpinned (see the kernel's header)."""
+    keep = torch.is_tensor(embeddings) and embeddings.is_cuda and embeddings.dtype == torch.float32
+    emb = embeddings if keep else to_cuda_f32(embeddings)
+    emb = emb if emb.is_contiguous() else emb.contiguous()
+    lab = labels if torch.is_tensor(labels) else torch.as_tensor(labels)
+    lab = lab.reshape(-1).to(device=emb.device).to(torch.int32).contiguous()     # class ids (the TF op compares for equality)
+    if emb.dim() != 2 or lab.numel() != emb.shape[0]:
+        raise ValueError(f"triplet_semihard_loss expects labels [N] and embeddings [N,D]; got {tuple(lab.shape)}, {tuple(emb.shape)}")
+    return _SemihardLoss.apply(emb, lab, float(margin))

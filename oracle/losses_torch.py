@@ -120,3 +120,50 @@ def loss_and_grad(kind: str, emb: torch.Tensor, pids: torch.Tensor, margin, weig
     out = fn(d, pids.to(e.dtype), margin, weighted)
     out[0].backward()
     return out, e.grad.detach(), d.detach()
+
+
+# --------------------------------------------------------------------------- tf.contrib metric_learning (third party)
+# The reference's CUB trainers call tensorflow.contrib.losses.python.metric_learning.triplet_semihard_loss
+# (src/base_CUB.py:8,163-166).  TensorFlow 1.x is neither vendored by the reference nor installable here, and the
+# reference holds no test or golden vector for it: PARITY UNPINNED.  What follows restates the published TF 1.x source
+# (tensorflow/contrib/losses/python/metric_learning/metric_loss_ops.py: pairwise_distance, masked_minimum,
+# masked_maximum, triplet_semihard_loss) op for op in torch, so autograd gives the TF gradient as well.
+def contrib_pairwise_distance(feature: torch.Tensor, squared: bool = False) -> torch.Tensor:
+    sq = (feature * feature).sum(1, keepdim=True)
+    d2 = sq + sq.t() - 2.0 * feature @ feature.t()
+    d2 = torch.clamp(d2, min=0.0)
+    err = (d2 <= 0.0).to(feature.dtype)
+    d = d2 if squared else torch.sqrt(d2 + err * 1e-16)
+    d = d * (1.0 - err)
+    n = feature.shape[0]
+    return d * (torch.ones_like(d) - torch.eye(n, dtype=d.dtype))
+
+
+def contrib_masked_maximum(data, mask, dim=1):
+    axis_min = data.amin(dim, keepdim=True)
+    return ((data - axis_min) * mask).amax(dim, keepdim=True) + axis_min
+
+
+def contrib_masked_minimum(data, mask, dim=1):
+    axis_max = data.amax(dim, keepdim=True)
+    return ((data - axis_max) * mask).amin(dim, keepdim=True) + axis_max
+
+
+def contrib_triplet_semihard_loss(labels: torch.Tensor, embeddings: torch.Tensor, margin: float = 1.0) -> torch.Tensor:
+    labels = labels.reshape(-1, 1)
+    pdist = contrib_pairwise_distance(embeddings, squared=True)
+    adjacency = labels == labels.t()
+    adjacency_not = ~adjacency
+    b = labels.numel()
+    pdist_tile = pdist.repeat(b, 1)
+    mask = adjacency_not.repeat(b, 1) & (pdist_tile > pdist.t().reshape(-1, 1))
+    mask_final = (mask.to(pdist.dtype).sum(1, keepdim=True) > 0.0).reshape(b, b).t()
+    adjacency_not_f = adjacency_not.to(pdist.dtype)
+    mask_f = mask.to(pdist.dtype)
+    negatives_outside = contrib_masked_minimum(pdist_tile, mask_f).reshape(b, b).t()
+    negatives_inside = contrib_masked_maximum(pdist, adjacency_not_f).repeat(1, b)
+    semi_hard_negatives = torch.where(mask_final, negatives_outside, negatives_inside)
+    loss_mat = margin + pdist - semi_hard_negatives
+    mask_positives = adjacency.to(pdist.dtype) - torch.eye(b, dtype=pdist.dtype)
+    num_positives = mask_positives.sum()
+    return torch.clamp(loss_mat * mask_positives, min=0.0).sum() / num_positives

@@ -50,3 +50,20 @@ def test_edge_semantics():
     out, g, _ = L.loss_and_grad("batch_hard", E2, torch.tensor([1., 1., 1., 2.], dtype=torch.float64), 0.2, weighted=False)
     # row 0 has two furthest positives at distance 1 -> each gets half
     assert g[0, 0] == pytest.approx(0.0)
+
+
+def test_contrib_triplet_semihard_known_answer():
+    """tf.contrib triplet_semihard_loss restatement on SURVEY App. B's four points, by hand:
+    E = [[0,0],[1,0],[0,2],[3,0]], labels [1,1,2,2], squared distances d01=1 d02=4 d03=9 d12=5 d13=4 d23=13, margin 0.5.
+    (a=0,p=1): d_ap=1, negatives {4, 9} beyond it -> n*=4 -> max(0.5+1-4, 0) = 0
+    (a=1,p=0): d_ap=1, negatives {5, 4} -> n*=4 -> 0
+    (a=2,p=3): d_ap=13, negatives {4, 5}, none beyond -> largest = 5 -> 0.5+13-5 = 8.5
+    (a=3,p=2): d_ap=13, negatives {9, 4}, none beyond -> largest = 9 -> 0.5+13-9 = 4.5
+    loss = (0 + 0 + 8.5 + 4.5) / 4 = 3.25"""
+    import torch
+    from oracle import losses_torch as L
+    e = torch.tensor([[0., 0.], [1., 0.], [0., 2.], [3., 0.]], dtype=torch.float64)
+    lab = torch.tensor([1, 1, 2, 2])
+    assert float(L.contrib_triplet_semihard_loss(lab, e, 0.5)) == pytest.approx(3.25, abs=1e-12)
+    # anchors without any negative: masked_maximum degenerates to the row minimum (0): l = margin + d_ap
+    assert float(L.contrib_triplet_semihard_loss(torch.tensor([7, 7]), e[:2], 0.5)) == pytest.approx(1.5, abs=1e-12)
