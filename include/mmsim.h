@@ -190,6 +190,14 @@ MMSIM_API int mmsim_triplet_semihard_workspace_bytes(int64_t N, size_t* bytes);
 MMSIM_API int mmsim_triplet_semihard_f32(const float* E, const int32_t* labels, int64_t N, int64_t D, float margin, float* loss,
                                float* dE, void* workspace, size_t workspace_bytes, mmsim_stream_t stream);
 
+/* tf.contrib's lifted_struct_loss (metric_loss_ops.lifted_struct_loss(labels, embeddings, margin), src/base_CUB.py:167-171),
+ * forward + backward: loss[0] = 0.25 * sum over ordered positive pairs of max(log(S_a + S_b) + D_ab, 0)^2 / (P / 2) with
+ * S_a = sum over a's negatives of exp(margin - D_aj), Euclidean (not squared) distances; dE (nullable) = d loss / d E.
+ * Same arguments as mmsim_triplet_semihard_f32; third-party function, parity unpinned. */
+MMSIM_API int mmsim_lifted_struct_workspace_bytes(int64_t N, size_t* bytes);
+MMSIM_API int mmsim_lifted_struct_f32(const float* E, const int32_t* labels, int64_t N, int64_t D, float margin, float* loss,
+                            float* dE, void* workspace, size_t workspace_bytes, mmsim_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

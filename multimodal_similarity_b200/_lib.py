@@ -46,6 +46,9 @@ SIGNATURES = {
     "mmsim_triplet_semihard_workspace_bytes": (c_int, [c_int64, POINTER(c_size_t)]),
     "mmsim_triplet_semihard_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
                                            c_void_p]),
+    "mmsim_lifted_struct_workspace_bytes": (c_int, [c_int64, POINTER(c_size_t)]),
+    "mmsim_lifted_struct_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
+                                        c_void_p]),
     "mmsim_knn_merge": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

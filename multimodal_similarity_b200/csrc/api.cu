@@ -13,6 +13,7 @@
 #include "merge.h"
 #include "mining.h"
 #include "project.h"
+#include "lifted_struct.h"
 #include "semihard_loss.h"
 #include "sqdist.h"
 
@@ -166,6 +167,13 @@ MMSIM_API int mmsim_triplet_semihard_workspace_bytes(int64_t N, size_t* bytes) {
 MMSIM_API int mmsim_triplet_semihard_f32(const float* E, const int32_t* labels, int64_t N, int64_t D, float margin, float* loss,
                                float* dE, void* workspace, size_t workspace_bytes, mmsim_stream_t stream) {
   return semihard_loss::run(E, labels, N, D, margin, loss, dE, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+MMSIM_API int mmsim_lifted_struct_workspace_bytes(int64_t N, size_t* bytes) { return lifted_struct::workspace_bytes(N, bytes); }
+
+MMSIM_API int mmsim_lifted_struct_f32(const float* E, const int32_t* labels, int64_t N, int64_t D, float margin, float* loss,
+                            float* dE, void* workspace, size_t workspace_bytes, mmsim_stream_t stream) {
+  return lifted_struct::run(E, labels, N, D, margin, loss, dE, workspace, workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -121,28 +121,39 @@ def lifted_loss(dists_or_embeddings, pids, margin, weighted=True) -> LossOutput:
     return _wrap(_FusedLoss.apply(emb.contiguous(), pids, _lib.LOSS_LIFTED, False, float(margin), weighted))
 
 
-# --------------------------------------------------------------------------- tf.contrib triplet_semihard_loss (K8)
-class _SemihardLoss(torch.autograd.Function):
+# --------------------------------------------------------------------------- tf.contrib metric losses (K8, K9)
+class _ContribLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, emb, labels, margin):
+    def forward(ctx, emb, labels, margin, name):
         lib = _lib.load()
         n, d = emb.shape
         dev = emb.device
         c = ctypes.c_size_t()
-        _lib.check(lib.mmsim_triplet_semihard_workspace_bytes(n, ctypes.byref(c)), "mmsim_triplet_semihard_workspace_bytes")
-        ws = workspace("semihard_loss", c.value, dev)
+        _lib.check(getattr(lib, f"mmsim_{name}_workspace_bytes")(n, ctypes.byref(c)), f"mmsim_{name}_workspace_bytes")
+        ws = workspace(name, c.value, dev)
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         grad = torch.empty_like(emb) if emb.requires_grad else None
         with torch.cuda.device(dev):
-            rc = lib.mmsim_triplet_semihard_f32(emb.data_ptr(), labels.data_ptr(), n, d, float(margin), loss.data_ptr(),
-                                                _lib.ptr(grad), ws.data_ptr(), ws.numel(), stream_handle(dev))
-        _lib.check(rc, "mmsim_triplet_semihard_f32")
+            rc = getattr(lib, f"mmsim_{name}_f32")(emb.data_ptr(), labels.data_ptr(), n, d, float(margin), loss.data_ptr(),
+                                                   _lib.ptr(grad), ws.data_ptr(), ws.numel(), stream_handle(dev))
+        _lib.check(rc, f"mmsim_{name}_f32")
         ctx.grad = grad
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
-        return (None if ctx.grad is None else ctx.grad * g), None, None
+        return (None if ctx.grad is None else ctx.grad * g), None, None, None
+
+
+def _contrib(name, labels, embeddings, margin):
+    keep = torch.is_tensor(embeddings) and embeddings.is_cuda and embeddings.dtype == torch.float32
+    emb = embeddings if keep else to_cuda_f32(embeddings)
+    emb = emb if emb.is_contiguous() else emb.contiguous()
+    lab = labels if torch.is_tensor(labels) else torch.as_tensor(labels)
+    lab = lab.reshape(-1).to(device=emb.device).to(torch.int32).contiguous()     # class ids (the TF ops compare for equality)
+    if emb.dim() != 2 or lab.numel() != emb.shape[0]:
+        raise ValueError(f"{name} expects labels [N] and embeddings [N,D]; got {tuple(lab.shape)}, {tuple(emb.shape)}")
+    return _ContribLoss.apply(emb, lab, float(margin), name)
 
 
 def triplet_semihard_loss(labels, embeddings, margin=1.0):
@@ -150,11 +161,10 @@ def triplet_semihard_loss(labels, embeddings, margin=1.0):
     CUB trainers select with ``--loss triplet`` (src/base_CUB.py:163-166) -- forward and backward on the device
     (csrc/semihard_loss.cu).  Same argument order as the TF function; returns a scalar CUDA tensor that supports
     ``.backward()`` when ``embeddings`` requires grad.  Parity with TF is unpinned (see the kernel's header)."""
-    keep = torch.is_tensor(embeddings) and embeddings.is_cuda and embeddings.dtype == torch.float32
-    emb = embeddings if keep else to_cuda_f32(embeddings)
-    emb = emb if emb.is_contiguous() else emb.contiguous()
-    lab = labels if torch.is_tensor(labels) else torch.as_tensor(labels)
-    lab = lab.reshape(-1).to(device=emb.device).to(torch.int32).contiguous()     # class ids (the TF op compares for equality)
-    if emb.dim() != 2 or lab.numel() != emb.shape[0]:
-        raise ValueError(f"triplet_semihard_loss expects labels [N] and embeddings [N,D]; got {tuple(lab.shape)}, {tuple(emb.shape)}")
-    return _SemihardLoss.apply(emb, lab, float(margin))
+    return _contrib("triplet_semihard", labels, embeddings, margin)
+
+
+def lifted_struct_loss(labels, embeddings, margin=1.0):
+    """``tf.contrib.losses.metric_learning.lifted_struct_loss(labels, embeddings, margin)`` (``--loss lifted`` of the CUB
+    trainers, src/base_CUB.py:167-171), forward and backward on the device (csrc/lifted_struct.cu).  Parity unpinned."""
+    return _contrib("lifted_struct", labels, embeddings, margin)

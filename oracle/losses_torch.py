@@ -167,3 +167,26 @@ def contrib_triplet_semihard_loss(labels: torch.Tensor, embeddings: torch.Tensor
     mask_positives = adjacency.to(pdist.dtype) - torch.eye(b, dtype=pdist.dtype)
     num_positives = mask_positives.sum()
     return torch.clamp(loss_mat * mask_positives, min=0.0).sum() / num_positives
+
+
+def contrib_lifted_struct_loss(labels: torch.Tensor, embeddings: torch.Tensor, margin: float = 1.0) -> torch.Tensor:
+    """metric_loss_ops.lifted_struct_loss (src/base_CUB.py:167-171), restated op for op from the TF 1.x source."""
+    labels = labels.reshape(-1, 1)
+    pairwise_distances = contrib_pairwise_distance(embeddings)
+    adjacency = labels == labels.t()
+    adjacency_not = ~adjacency
+    b = labels.numel()
+    diff = margin - pairwise_distances
+    mask = adjacency_not.to(diff.dtype)
+    row_minimums = diff.amin(1, keepdim=True)
+    row_negative_maximums = ((diff - row_minimums) * mask).amax(1, keepdim=True) + row_minimums
+    max_elements = torch.maximum(row_negative_maximums, row_negative_maximums.t())
+    diff_tiled = diff.repeat(b, 1)
+    mask_tiled = mask.repeat(b, 1)
+    max_elements_vect = max_elements.t().reshape(-1, 1)
+    loss_exp_left = (torch.exp(diff_tiled - max_elements_vect) * mask_tiled).sum(1, keepdim=True).reshape(b, b)
+    loss_mat = max_elements + torch.log(loss_exp_left + loss_exp_left.t())
+    loss_mat = loss_mat + pairwise_distances
+    mask_positives = adjacency.to(diff.dtype) - torch.eye(b, dtype=diff.dtype)
+    num_positives = mask_positives.sum() / 2.0
+    return 0.25 * (torch.clamp(loss_mat * mask_positives, min=0.0) ** 2).sum() / num_positives

@@ -187,3 +187,27 @@ def test_contrib_triplet_semihard_numpy_inputs_and_errors():
     assert float(mm.triplet_semihard_loss(np.array([7, 7]), x, 0.5)) == pytest.approx(1.5, rel=1e-6)   # no negatives at all
     with pytest.raises(ValueError):
         mm.triplet_semihard_loss(np.array([1, 2, 3]), x)
+
+
+@pytest.mark.parametrize("n,d,classes,margin", [(4, 2, 2, 1.0), (64, 16, 5, 1.0), (256, 128, 32, 0.2), (300, 64, 100, 1.0), (513, 128, 7, 1.0)])
+def test_contrib_lifted_struct_vs_oracle(n, d, classes, margin):
+    import multimodal_similarity_b200 as mm
+    from oracle import losses_torch as L
+    rs = np.random.RandomState(n + 1)
+    if n == 4:
+        x = np.array([[0., 0.], [1., 0.], [0., 2.], [3., 0.]], np.float32)
+        lab = np.array([1, 1, 2, 2], np.int32)
+    else:
+        cent = rs.randn(classes, d).astype(np.float32)
+        lab = rs.randint(0, classes, n).astype(np.int32)
+        x = cent[lab] + 0.7 * rs.randn(n, d).astype(np.float32)
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+    e = torch.from_numpy(x).cuda().requires_grad_(True)
+    loss = mm.lifted_struct_loss(torch.from_numpy(lab).cuda(), e, margin)
+    loss.backward()
+    e64 = torch.from_numpy(x).double().requires_grad_(True)
+    ref = L.contrib_lifted_struct_loss(torch.from_numpy(lab).long(), e64, margin)
+    ref.backward()
+    assert float(loss) == pytest.approx(float(ref), rel=1e-4, abs=1e-6)
+    g, gr = e.grad.cpu().numpy(), e64.grad.numpy()
+    assert np.abs(g - gr).max() <= 1e-3 * max(np.abs(gr).max(), 1e-6)

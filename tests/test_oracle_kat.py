@@ -67,3 +67,19 @@ def test_contrib_triplet_semihard_known_answer():
     assert float(L.contrib_triplet_semihard_loss(lab, e, 0.5)) == pytest.approx(3.25, abs=1e-12)
     # anchors without any negative: masked_maximum degenerates to the row minimum (0): l = margin + d_ap
     assert float(L.contrib_triplet_semihard_loss(torch.tensor([7, 7]), e[:2], 0.5)) == pytest.approx(1.5, abs=1e-12)
+
+
+def test_contrib_lifted_struct_known_answer():
+    """tf.contrib lifted_struct_loss restatement on the same four points, margin 1, Euclidean distances
+    d01=1 d02=2 d03=3 d12=sqrt5 d13=2 d23=sqrt13:  S_0 = e^(1-2)+e^(1-3), S_1 = e^(1-sqrt5)+e^(1-2),
+    S_2 = e^(1-2)+e^(1-sqrt5), S_3 = e^(1-3)+e^(1-2);  J_01 = log(S_0+S_1)+1, J_23 = log(S_2+S_3)+sqrt13;
+    4 ordered positive pairs: loss = 0.25 * 2 (J_01^2 + J_23^2) / 2."""
+    import math
+    import torch
+    from oracle import losses_torch as L
+    e = torch.tensor([[0., 0.], [1., 0.], [0., 2.], [3., 0.]], dtype=torch.float64)
+    s0 = math.exp(-1) + math.exp(-2); s1 = math.exp(1 - math.sqrt(5)) + math.exp(-1)
+    s2 = math.exp(-1) + math.exp(1 - math.sqrt(5)); s3 = math.exp(-2) + math.exp(-1)
+    j01 = max(math.log(s0 + s1) + 1, 0.0); j23 = max(math.log(s2 + s3) + math.sqrt(13), 0.0)
+    want = 0.25 * 2 * (j01 ** 2 + j23 ** 2) / 2
+    assert float(L.contrib_lifted_struct_loss(torch.tensor([1, 1, 2, 2]), e, 1.0)) == pytest.approx(want, rel=1e-12)
