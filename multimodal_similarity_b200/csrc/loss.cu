@@ -847,6 +847,18 @@ static const void* kernel_for(int shape, int kind) {
   }
 }
 
+// The dynamic shared-memory limit is an attribute of the KERNEL, while the amount a launch needs depends on (N, D): the
+// attribute is only ever raised (a later, smaller problem must not lower it under a layout that is already cached --
+// that made a cached 256 x 128 launch fail with "invalid argument" after a 64 x 16 one in the same process).
+static void raise_smem_attr(int shape, int kind, size_t bytes) {
+  static std::mutex mu;
+  static size_t have[3][2] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  if (bytes > have[shape][kind] &&
+      cudaFuncSetAttribute(kernel_for(shape, kind), cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)) == cudaSuccess)
+    have[shape][kind] = bytes;
+}
+
 // Pick the smallest tile whose grid fits co-resident on the device (a cooperative launch requires it).
 static int pick_shape(int64_t N, int64_t D) {
   if (const char* e = getenv("MMSIM_LOSS_SHAPE")) {   // experiment switch: force tile shape 0 / 1 / 2
@@ -868,7 +880,7 @@ static int pick_shape(int64_t N, int64_t D) {
     if (num_sms > 0) {
       int per_kind[2] = {0, 0};
       for (int kd = 0; kd < 2; ++kd) {
-        cudaFuncSetAttribute(kernel_for(s, kd), cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        raise_smem_attr(s, kd, smem);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_kind[kd], kernel_for(s, kd), THREADS, smem) != cudaSuccess) per_kind[kd] = 0;
       }
       per_sm = per_kind[0] < per_kind[1] ? per_kind[0] : per_kind[1];
@@ -917,7 +929,7 @@ Layout make_layout(int64_t N, int64_t D) {
   Layout L = compute_layout(N, D);
   if (L.shape >= 0)
     for (int kd = 0; kd < 2; ++kd)
-      cudaFuncSetAttribute(kernel_for(L.shape, kd), cudaFuncAttributeMaxDynamicSharedMemorySize, int(L.smem_bytes));
+      raise_smem_attr(L.shape, kd, L.smem_bytes);
   cache.emplace(key, L);
   return L;
 }

@@ -211,3 +211,20 @@ def test_contrib_lifted_struct_vs_oracle(n, d, classes, margin):
     assert float(loss) == pytest.approx(float(ref), rel=1e-4, abs=1e-6)
     g, gr = e.grad.cpu().numpy(), e64.grad.numpy()
     assert np.abs(g - gr).max() <= 1e-3 * max(np.abs(gr).max(), 1e-6)
+
+
+def test_layouts_of_different_sizes_interleave():
+    """The shared-memory limit is a per-kernel attribute while the need depends on (N, D): a small problem between two
+    large ones must not lower it (regression: the cached 256 x 128 launch failed with 'invalid argument')."""
+    import multimodal_similarity_b200 as mm
+    g = torch.Generator().manual_seed(0)
+    big = torch.randn(256, 128, generator=g).cuda()
+    small = torch.randn(64, 16, generator=g).cuda()
+    pb = (torch.arange(256) % 32 + 1).float().cuda()
+    ps = (torch.arange(64) % 4 + 1).float().cuda()
+    a = float(mm.batch_hard(big, pb, "soft")[0])
+    mm.batch_hard(small, ps, "soft"); mm.lifted_loss(small, ps, 1.0)
+    assert float(mm.batch_hard(big, pb, "soft")[0]) == a
+    b = float(mm.lifted_loss(big, pb, 1.0)[0])
+    mm.lifted_loss(small, ps, 1.0)
+    assert float(mm.lifted_loss(big, pb, 1.0)[0]) == b
