@@ -1,4 +1,6 @@
 """K4: fused tcgen05 kNN + exact re-rank against the oracle (the reference's per-query distance + argsort)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -186,3 +188,25 @@ def test_cta_pair_sweep_matches(rs, monkeypatch):
         d1, i1 = mm.retrieve(q, g, 50)
         assert torch.equal(d0, d1) and torch.equal(i0, i1)
     monkeypatch.delenv("MMSIM_KNN_PAIR", raising=False)
+
+
+def test_grouped_queries_exclude_self_vs_oracle(rs):
+    """Enough queries and gallery rows for query grouping (sweep order != caller's order): leave-one-out retrieval with
+    the queries being gallery rows, spot-checked against the oracle; and grouping on/off give identical results."""
+    import multimodal_similarity_b200 as mm
+    x, _ = clustered(rs, 70000, 64, 300)
+    g = torch.from_numpy(x).cuda()
+    nq, off, k = 4500, 1234, 30
+    q = g[off:off + nq].clone()
+    d, i = mm.retrieve(q, g, k, exclude_self=True, self_offset=off)
+    d, i = d.cpu().numpy(), i.cpu().numpy()
+    for qi in (0, 1, 777, 2048, nq - 1):
+        rd, ri = O.knn(x[off + qi:off + qi + 1], x, k, exclude_self=True, self_offset=off + qi)
+        assert np.array_equal(d[qi], rd[0]) and np.array_equal(i[qi], ri[0]), qi
+    assert not (i == (off + np.arange(nq))[:, None]).any()
+    os.environ["MMSIM_KNN_GROUP"] = "0"
+    try:
+        d0, i0 = mm.retrieve(q, g, k, exclude_self=True, self_offset=off)
+    finally:
+        del os.environ["MMSIM_KNN_GROUP"]
+    assert np.array_equal(d0.cpu().numpy(), d) and np.array_equal(i0.cpu().numpy(), i)

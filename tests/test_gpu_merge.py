@@ -96,6 +96,19 @@ def test_reduced_protocol_equals_unsharded(R, exclude_self, rs):
     assert torch.equal(md, full_d) and torch.equal(mi, full_i)
 
 
+def test_reduced_protocol_with_grouped_queries(rs):
+    """4,200 queries: every simulated shard sorts them by nearest anchor (shard mode always groups), the pivot lists they
+    exchange are indexed by sweep position, results come back in the caller's order."""
+    import multimodal_similarity_b200 as mm
+    x, _ = clustered(rs, 50000, 64, 200)
+    g = torch.from_numpy(x).cuda()
+    q = torch.from_numpy(clustered(rs, 4200, 64, 200)[0]).cuda()
+    (md, mi, status), kp = _simulate_reduced(g, q, 20, 4, False)
+    assert int(status[0]) == 0
+    full_d, full_i = mm.retrieve(q, g, 20)
+    assert torch.equal(md, full_d) and torch.equal(mi, full_i)
+
+
 def test_reduced_protocol_certificate_catches_adversarial_order(rs):
     """Gallery sorted by cluster: all neighbours of a query live in ONE shard, which re-ranks only kp < k of them.
     The global certificate must flag those queries (the caller then falls back to the exact-shards protocol)."""
