@@ -321,25 +321,32 @@ def main():
     res_d = torch.empty((Q, k), dtype=torch.float32).pin_memory()
     res_i = torch.empty((Q, k), dtype=out_i.dtype).pin_memory()
 
+    st_e2e = torch.empty(8, dtype=torch.int32, device=dev)
+
     def step_e2e():
         qd = q_host.to(dev, non_blocking=True)
         gd = g_host.to(dev, non_blocking=True)
         if world == 1:
-            d_, i_, st = knn_raw(qd, gd, k)
+            # the re-rank kernel writes the result rows straight into the pinned host buffers (they are device-accessible
+            # under UVA): the device->host transfer of the result overlaps the kernel instead of following it
+            d_, i_, st = knn_raw(qd, gd, k, out=(res_d, res_i, st_e2e))
         else:
             d_, i_ = ShardedGallery(gd, presharded=True, row_offset=lo, total_rows=G).retrieve(qd, k, check=False)
-        res_d.copy_(d_, non_blocking=True)
-        res_i.copy_(i_, non_blocking=True)
+            res_d.copy_(d_, non_blocking=True)
+            res_i.copy_(i_, non_blocking=True)
         return d_, i_
 
     for _ in range(2):
         step_e2e()
     e2e_steps = max(3, min(a.steps, 10))
     ms_e2e, _ = timed(step_e2e, e2e_steps)
+    if world == 1:   # the zero-copy result equals the device-resident one of the timed steps
+        assert torch.equal(res_d, out_d.cpu()) and torch.equal(res_i, out_i.cpu()), "e2e result differs from the device result"
     e2e = {"value": Q * e2e_steps / (ms_e2e / 1e3), "unit": "queries/s",
            "h2d_bytes_per_step": int((q_host.numel() + g_host.numel()) * 4),
            "d2h_bytes_per_step": int(res_d.numel() * 4 + res_i.numel() * res_i.element_size()),
-           "ms_per_step": ms_e2e / e2e_steps}
+           "ms_per_step": ms_e2e / e2e_steps,
+           "d2h": "re-rank kernel writes the result rows into pinned host memory (zero-copy)" if world == 1 else "copy after the merge"}
 
     # ---- roofline of the dominant kernel (knn_tc_kernel), timed alone on its stream via the phase mask
     tc_reps = max(3, min(a.steps, 10))
