@@ -1282,8 +1282,9 @@ constexpr int NEPI_SWEEP = 16;
 // are identical (tests/test_gpu_knn.py::test_cta_pair_sweep_matches), but on B200 it is not faster -- 28.1 vs 21.2 ms at
 // 128-d, 43.0 vs 42.8 ms at 256-d (gpurun_out/pair_ab.log): the MMA warp and the epilogue warps hand each 256-column
 // accumulator back and forth once per tile, the pair adds a cross-SM hop to that loop (remote mbarrier arrive, multicast
-// commit), and at K = 128 the loop, not shared-memory bandwidth, sets the tile rate.  Read on every call so that a test
-// can switch it.
+// commit), and at K = 128 the loop, not shared-memory bandwidth, sets the tile rate.  (Pairs with FOUR 128-column
+// accumulators -- M = 256, N = 128 MMAs, three half-tiles of slack for the hand-off -- were also built and verified
+// bit-identical, and were slower still: 39.9 ms.)  Read on every call so that a test can switch it.
 static bool sweep_pairs() {
   const char* e = getenv("MMSIM_KNN_PAIR");
   return e && atoi(e) == 1;
