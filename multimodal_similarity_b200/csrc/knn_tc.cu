@@ -1227,7 +1227,12 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   p.n_sample_tiles = 0;
   if (p.use_pivots) {
     // about 1/64 of the gallery, as few MMA tiles as possible while still spread over >= 8 places of the gallery
-    const int64_t target = std::max<int64_t>(ng / 64, 32);
+    int div = 64;
+    if (const char* e = getenv("MMSIM_PIVOT_DIV")) {   // experiment switch: sample 1/div of the gallery (with MMSIM_LADDER)
+      const int v = atoi(e);
+      if (v >= 8 && v <= 1024) div = v;
+    }
+    const int64_t target = std::max<int64_t>(ng / div, 32);
     p.sample_cols = 32;
     while (p.sample_cols < BN && target / (2 * p.sample_cols) >= 8) p.sample_cols *= 2;
     p.n_sample_tiles = int(std::min<int64_t>(p.n_tiles, std::max<int64_t>(1, (target + p.sample_cols / 2) / p.sample_cols)));
