@@ -20,7 +20,7 @@ from .retrieval import (  # noqa: F401
     average_precision, evaluate, evaluate_simple, full_ranking, late_fusion, precision_at_recall, recall_at_K, retrieve,
     retrieve_one,
 )
-from .mining import select_triplets_facenet, semihard_counts  # noqa: F401
+from .mining import select_triplets_facenet, select_triplets_facenet_cub, semihard_counts  # noqa: F401
 from .sharded import ShardedGallery  # noqa: F401
 
 __version__ = "0.1.0"

@@ -21,14 +21,16 @@ from . import _lib
 from ._util import stream_handle, to_cuda_f32
 
 
-def _pair_stream(lab):
-    """(anchor, positive) pairs in the reference's visiting order (src/utils.py:445-472)."""
+def _pair_stream(lab, background=0):
+    """(anchor, positive) pairs in the reference's visiting order (src/utils.py:445-472).  ``background`` is the label
+    that gets no anchors (0 in utils.py:455); None gives every class anchors (src/base_model_CUB.py:50)."""
     idx_dict: dict = {}
     for i, l in enumerate(lab):
         idx_dict.setdefault(int(l), []).append(i)
     for key in idx_dict:
         random.shuffle(idx_dict[key])
-    iters = {key: itertools.permutations(idx_dict[key], 2) for key in idx_dict if not key == 0}
+    iters = {key: itertools.permutations(idx_dict[key], 2) for key in idx_dict
+             if background is None or not key == background}
     while iters:
         for key in list(iters):
             try:
@@ -57,10 +59,14 @@ def semihard_counts(all_dist, lab, pairs, alpha=0.2, return_mask=False):
     return (count, mask) if return_mask else count
 
 
-def select_triplets_facenet(lab, all_dist, triplet_per_batch, alpha=0.2, num_negative=3):
+def select_triplets_facenet(lab, all_dist, triplet_per_batch, alpha=0.2, num_negative=3, *, background=0,
+                            empty=([], 0.)):
     """Reference signature and return value: ``(triplet_input_idx, mean semi-hard count)`` -- a flat list
     ``[anchor, positive, negative, ...]`` of at most ``3 * triplet_per_batch`` ints, ``([], 0.)`` when nothing is found.
-    Same triplets as the reference for the same ``random`` / ``np.random`` seeds."""
+    Same triplets as the reference for the same ``random`` / ``np.random`` seeds.
+
+    The keyword-only arguments select the reference's near-copies: ``background=None, empty=(None, None)`` is the
+    CUB trainers' version (``select_triplets_facenet_cub`` below)."""
     dist = to_cuda_f32(all_dist)
     dev = dist.device
     n = dist.shape[0]
@@ -69,7 +75,7 @@ def select_triplets_facenet(lab, all_dist, triplet_per_batch, alpha=0.2, num_neg
     lib = _lib.load()
     labels = torch.as_tensor(np.asarray([int(l) for l in lab], dtype=np.int32)).to(dev)
     want = int(triplet_per_batch) * 3
-    stream = _pair_stream(lab)          # shuffles now, like the reference, even if nothing is asked for
+    stream = _pair_stream(lab, background)          # shuffles now, like the reference, even if nothing is asked for
     picks: list = []                    # (anchor, positive, r)
     all_neg_count: list = []
     chunk = max(256, 2 * int(triplet_per_batch))
@@ -95,7 +101,7 @@ def select_triplets_facenet(lab, all_dist, triplet_per_batch, alpha=0.2, num_neg
             if done:
                 break
     if not picks:
-        return [], 0.
+        return tuple(list(e) if isinstance(e, list) else e for e in empty)
     picks_d = torch.as_tensor(np.asarray(picks, dtype=np.int32)).to(dev)
     neg_d = torch.empty(len(picks), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
@@ -109,3 +115,10 @@ def select_triplets_facenet(lab, all_dist, triplet_per_batch, alpha=0.2, num_neg
     for (an, pos, _), ng in zip(picks, neg):
         triplet_input_idx.extend([an, pos, ng])
     return triplet_input_idx, float(np.mean(all_neg_count))
+
+
+def select_triplets_facenet_cub(lab, all_dist, triplet_per_batch, alpha=0.2, num_negative=3):
+    """The CUB trainers' copy (src/base_model_CUB.py:25-91, debug_CUB.py:22-88, pddm_CUB.py:26-92): label 0 is an
+    ordinary class and an empty result is ``(None, None)``; otherwise identical to ``select_triplets_facenet``."""
+    return select_triplets_facenet(lab, all_dist, triplet_per_batch, alpha, num_negative, background=None,
+                                   empty=(None, None))

@@ -22,14 +22,17 @@ def semihard_set(all_dist, lab_int, an_idx, pos_idx, alpha):
         return np.where(np.logical_and(neg_dist - pos_dist < alpha, pos_dist < neg_dist))[0]
 
 
-def select_triplets_facenet(lab, all_dist, triplet_per_batch, alpha=0.2, num_negative=3):
+def select_triplets_facenet(lab, all_dist, triplet_per_batch, alpha=0.2, num_negative=3, cub=False):
+    """``cub=True`` restates the CUB trainers' copy (src/base_model_CUB.py:25-91): label 0 also gets anchors (:50) and
+    an empty result is (None, None) (:91); pinned by ``tests/golden/mining_cubcopy*.npz``."""
     lab_int = np.asarray([int(l) for l in lab])
     idx_dict = {}
     for i, l in enumerate(lab_int):                               # :444-450
         idx_dict.setdefault(int(l), []).append(i)
     for key in idx_dict:                                          # :451-452
         random.shuffle(idx_dict[key])
-    iters = {key: itertools.permutations(idx_dict[key], 2) for key in idx_dict if key != 0}   # :455-458
+    iters = {key: itertools.permutations(idx_dict[key], 2) for key in idx_dict
+             if cub or key != 0}                                  # :455-458
     out, counts = [], []
     while len(out) < triplet_per_batch * 3 and iters:             # :462-465
         for key in list(iters):
@@ -46,4 +49,4 @@ def select_triplets_facenet(lab, all_dist, triplet_per_batch, alpha=0.2, num_neg
                     return out, np.mean(counts)
     if len(out) > 0:
         return out, np.mean(counts)
-    return [], 0.
+    return (None, None) if cub else ([], 0.)

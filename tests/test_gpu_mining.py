@@ -29,8 +29,12 @@ def test_golden_triplets_bit_exact(mm, name, on_device):
     dist = mm.cdist(mm.all_diffs(x, x), metric=str(g["metric"]))      # the reference call site, src/base_model.py:271
     random.seed(int(g["seed"]))
     np.random.seed(int(g["seed"]))
-    trip, active = mm.select_triplets_facenet(g["labels"], dist, int(g["triplet_per_batch"]), alpha=float(g["alpha"]),
-                                              num_negative=int(g["num_negative"]))
+    miner = mm.select_triplets_facenet_cub if name.startswith("cubcopy") else mm.select_triplets_facenet
+    trip, active = miner(g["labels"], dist, int(g["triplet_per_batch"]), alpha=float(g["alpha"]),
+                         num_negative=int(g["num_negative"]))
+    if bool(g["empty_is_none"]):                                      # src/base_model_CUB.py:91
+        assert trip is None and active is None
+        return
     assert np.array_equal(np.asarray(trip, dtype=np.int64), g["triplets"])
     assert float(active) == float(g["active"])
     if len(trip) == 0:

@@ -20,7 +20,7 @@ def load_case(name):
 
 
 def test_fixtures_present():
-    assert set(CASES) >= {"hdd", "cub", "euclid", "starved", "none"}
+    assert set(CASES) >= {"hdd", "cub", "euclid", "starved", "none", "cubcopy", "cubcopy_none"}
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -29,9 +29,14 @@ def test_select_triplets_facenet_matches_reference(name):
     random.seed(int(g["seed"]))
     np.random.seed(int(g["seed"]))
     trip, active = M.select_triplets_facenet(g["labels"], dist, int(g["triplet_per_batch"]), alpha=float(g["alpha"]),
-                                             num_negative=int(g["num_negative"]))
+                                             num_negative=int(g["num_negative"]), cub=name.startswith("cubcopy"))
+    if bool(g["empty_is_none"]):                                  # src/base_model_CUB.py:91
+        assert trip is None and active is None
+        return
     assert np.array_equal(np.asarray(trip, dtype=np.int64), g["triplets"])
     assert float(active) == float(g["active"])
+    if name == "cubcopy":                                         # label 0 is mined too in this copy (:50)
+        assert (g["labels"][np.asarray(trip[0::3])] == 0).any()
 
 
 def test_live_reference_when_mounted():
