@@ -260,4 +260,4 @@ def full_ranking(embeddings, labels=None):
     the argsort of the reference's retrieve_one, on the GPU."""
     n = embeddings.shape[0]
     lab = np.ones(n, np.int32) if labels is None else labels
-    return _loo_records(embeddings, lab, False, False, 0.5, True, want_rank=True)["rank"]
+    return _loo_records(embeddings, lab, False, False, 0.5, True, want_rank=True, queries=np.arange(n))["rank"]

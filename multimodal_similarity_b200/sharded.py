@@ -209,7 +209,7 @@ class ShardedGallery:
     """``ShardedGallery(gallery, group).retrieve(queries, k)`` -> identical (dist, idx) on every rank.
 
     gallery      the FULL [G, D] gallery (each rank keeps only its slice) or, with ``presharded=True``, this rank's
-                 rows together with ``row_offset`` / ``total_rows``
+                 rows together with ``row_offset`` / ``total_rows`` (the rows ``shard_bounds`` assigns to it)
     group        a torch.distributed process group (default: the world); without an initialised process group the
                  object degenerates to a single shard
     """
@@ -223,6 +223,11 @@ class ShardedGallery:
                 raise ValueError("presharded=True needs row_offset and total_rows")
             self.lo, self.total = int(row_offset), int(total_rows)
             shard = gallery
+            want = shard_bounds(self.total, self.world, self.rank)
+            if (self.lo, self.lo + int(gallery.shape[0])) != want:
+                # every rank derives the other shards' row offsets from (total_rows, world) alone -- see _bases()
+                raise ValueError(f"presharded rows [{self.lo}, {self.lo + int(gallery.shape[0])}) of rank {self.rank} are not "
+                                 f"shard_bounds({self.total}, {self.world}, {self.rank}) = {want}")
         else:
             self.total = int(gallery.shape[0])
             self.lo, hi = shard_bounds(self.total, self.world, self.rank)

@@ -128,3 +128,20 @@ def test_slice_packing_roundtrip():
             allres[r, S * k * 3] = r                                                        # uncertified count of the slice
         got_d, got_i, unc = unpack_merged(allres, nq, S, k)
         assert torch.equal(got_d, want_d) and torch.equal(got_i, want_i) and int(unc) == sum(range(world))
+
+
+def test_presharded_rows_must_follow_shard_bounds():
+    """Every rank derives the other shards' row offsets from (total_rows, world): a different split is refused."""
+    from multimodal_similarity_b200.sharded import ShardedGallery
+
+    class CpuShardedGallery(ShardedGallery):
+        def _to_device(self, x, device):
+            return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32))
+
+    x = np.zeros((10, 4), np.float32)
+    sg = CpuShardedGallery(x, presharded=True, row_offset=0, total_rows=10)      # world 1: the whole gallery
+    assert (sg.lo, sg.hi, sg.total) == (0, 10, 10)
+    with pytest.raises(ValueError, match="shard_bounds"):
+        CpuShardedGallery(x[:7], presharded=True, row_offset=0, total_rows=10)
+    with pytest.raises(ValueError, match="row_offset"):
+        CpuShardedGallery(x, presharded=True)
