@@ -101,6 +101,20 @@ MMSIM_API int mmsim_knn_f32_phases(const float* Q, int64_t nq, const float* G, i
                          int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
                          mmsim_stream_t stream, int phases);
 
+/* The same retrieval with HOST buffers in: what a caller holding NumPy arrays (the reference's retrieve_one loop over
+ * embeddings in host memory, src/utils.py:55-81, src/evaluate_model.py) binds.  q_host[nq*D] and g_host[ng*D] are host
+ * arrays -- page-locked (cudaHostAlloc / cudaHostRegister) for the transfers to overlap the kernels; pageable memory works
+ * but serialises.  The call copies the queries, then a 1/64 sample of the gallery (the pivot pre-pass needs nothing
+ * else), then the gallery one split at a time on an internal copy stream; each split is converted and swept while the
+ * next one is in flight, so only the first split's transfer is exposed.  q_stage[nq*D] and g_stage[ng*D] are device
+ * buffers the caller provides for the float32 copies (the exact re-rank reads them; the library never allocates).
+ * out_dist / out_idx may be device memory or page-locked host memory (the re-rank kernel writes them directly);
+ * status is device memory.  Everything is ordered after earlier work on `stream` and complete, as far as `stream` is
+ * concerned, when work queued after the call starts.  Results are identical to mmsim_knn_f32 on the same arrays. */
+MMSIM_API int mmsim_knn_host_f32(const float* q_host, int64_t nq, const float* g_host, int64_t ng, int64_t D, int k,
+                       int exclude_self, int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status,
+                       float* q_stage, float* g_stage, void* ws, size_t ws_bytes, mmsim_stream_t stream);
+
 /* Merge `parts` shard-local results (as produced by mmsim_knn_f32 on each gallery shard and gathered with one
  * NCCL all-gather) into the global top-k ordered by (distance, global index).  Part p's [nq][k] block starts at
  * dist_parts + p * part_stride (same for idx_parts; part_stride in elements, >= nq*k, so a packed

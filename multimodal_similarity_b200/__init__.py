@@ -6,7 +6,7 @@ Function-level drop-ins for the reference's leaf functions (same names, argument
                project_normalize (xw_plus_b + l2_normalize embedding head)         src/networks.py:376-380
     losses     batch_hard / lifted_loss (fused forward + backward)                 src/networks.py:797-870
                triplet_semihard_loss / lifted_struct_loss (tf.contrib equivalents) src/base_CUB.py:163-171
-    retrieval  retrieve / retrieve_one / evaluate / evaluate_simple /
+    retrieval  retrieve / retrieve_host / retrieve_one / evaluate / evaluate_simple /
                recall_at_K / precision_at_recall / late_fusion                     src/utils.py:55-266
     mining     select_triplets_facenet (semi-hard negatives counted and picked on device)  src/utils.py:430-496
     sharded    ShardedGallery (gallery rows split over ranks, NCCL merge)          (new)
@@ -18,7 +18,7 @@ from .distance import all_diffs, all_diffs_tf, cdist, cdist_tf, pairwise_distanc
 from .losses import batch_hard, lifted_loss, lifted_struct_loss, triplet_semihard_loss  # noqa: F401
 from .retrieval import (  # noqa: F401
     average_precision, evaluate, evaluate_simple, full_ranking, late_fusion, precision_at_recall, recall_at_K, retrieve,
-    retrieve_one,
+    retrieve_host, retrieve_one,
 )
 from .mining import select_triplets_facenet, select_triplets_facenet_cub, semihard_counts  # noqa: F401
 from .sharded import ShardedGallery  # noqa: F401

@@ -27,6 +27,8 @@ SIGNATURES = {
                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mmsim_knn_f32_phases": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int64,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
+    "mmsim_knn_host_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int64,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mmsim_knn_shard_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int64,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
     "mmsim_knn_pivot_region": (c_int, [c_int64, c_int64, c_int64, c_int, POINTER(c_size_t), POINTER(c_size_t)]),

@@ -81,6 +81,15 @@ MMSIM_API int mmsim_knn_f32_phases(const float* Q, int64_t nq, const float* G, i
                   reinterpret_cast<cudaStream_t>(stream), phases);
 }
 
+MMSIM_API int mmsim_knn_host_f32(const float* q_host, int64_t nq, const float* g_host, int64_t ng, int64_t D, int k,
+                       int exclude_self, int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status,
+                       float* q_stage, float* g_stage, void* ws, size_t ws_bytes, mmsim_stream_t stream) {
+  MMSIM_REQUIRE(q_host && g_host && q_stage && g_stage, MMSIM_ERR_ARG, "knn_host: null host or staging pointer");
+  const knn::HostPipe hp{q_host, g_host};
+  return knn::run(q_stage, nq, g_stage, ng, D, k, exclude_self, self_offset, out_dist, out_idx, status, ws, ws_bytes,
+                  reinterpret_cast<cudaStream_t>(stream), knn::kPhaseAll, 0, nullptr, &hp);
+}
+
 MMSIM_API int mmsim_knn_merge(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride, const int64_t* idx_base,
                     int parts, int64_t nq, int k, float* out_dist, int64_t* out_idx, mmsim_stream_t stream) {
   return merge::run(dist_parts, idx_parts, part_stride, idx_base, parts, nq, k, k, nullptr, 0, out_dist, out_idx, nullptr,

@@ -20,6 +20,7 @@ struct Plan {
   size_t off_ah, off_apack, off_aidx, off_assign, off_perm, off_ghist;
   size_t off_qh, off_gh, off_gpack, off_qnorm, off_qerr, off_stats, off_piv16, off_ladder, off_log, off_log_cnt, off_log_tau, off_split_done;
   size_t off_unc_query, off_unc_bound, off_fb_count, off_fb_dist, off_fb_idx;
+  size_t off_s32, off_sh, off_spack;   // host-buffer mode: compact copy of the sampled gallery tiles (fp32, fp16, norm pack)
   size_t total_bytes;
 };
 
@@ -27,9 +28,16 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms);
 
 enum : int { kPhasePrep = 1, kPhaseTensor = 2, kPhaseRerank = 4, kPhaseFallback = 8, kPhasePivot = 16, kPhaseLadder = 32, kPhaseAll = 63 };
 
+// Host-buffer mode (mmsim_knn_host_f32): Q and G given to run() are device STAGING buffers; run() fills them from these
+// host arrays on a copy stream, one gallery split at a time, while the sweep of the previous split is running.
+struct HostPipe {
+  const float* q_host;
+  const float* g_host;
+};
+
 int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
         float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream, int phases = kPhaseAll,
-        int shard_kp = 0, float* out_lb = nullptr);
+        int shard_kp = 0, float* out_lb = nullptr, const HostPipe* host = nullptr);
 
 constexpr int kPivotsPerRow = 16;  // floats per query row in the pivot region of the workspace
 int merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t rows, float* out, cudaStream_t stream);

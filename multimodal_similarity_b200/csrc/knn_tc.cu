@@ -20,6 +20,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 #include "exact.cuh"
@@ -150,6 +151,8 @@ struct SweepArgs {
   int nq, n_qblocks, n_tiles;
   // MODE_SWEEP: item = (split, query block); contiguous tile range per split
   int n_splits, tiles_per_split;
+  int item_begin, item_end;  // MODE_SWEEP: this launch takes items [item_begin, item_end); item_end == 0: all of them
+                             // (host-buffer mode launches one split at a time, as its gallery rows arrive)
   int use_pivots;            // 0: threshold +inf (everything is logged; small galleries)
   int close_rows;            // experiment (MMSIM_SWEEP_FLAGS=8): every row starts closed (threshold -inf): the product
                              // kernel's fast path with no candidate ever found (wrong results)
@@ -335,8 +338,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
   // items: (split, query block) -- PAIR: (split, PAIR of query blocks), this CTA takes block 2 * pair + rank
   const int n_qb_items = PAIR ? (a.n_qblocks + 1) / 2 : a.n_qblocks;
-  const int n_items = MODE == MODE_SWEEP ? n_qb_items * a.n_splits : a.n_qblocks;
-  const int item0 = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x), item_step = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
+  const int n_items = MODE == MODE_SWEEP ? (a.item_end ? a.item_end : n_qb_items * a.n_splits) : a.n_qblocks;
+  const int item0 = (MODE == MODE_SWEEP ? a.item_begin : 0) + (PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x));
+  const int item_step = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
   auto item_range = [&](int item, int& qb, int& split, int& t0, int& nt) {
     if (MODE == MODE_SWEEP) {
       split = item / n_qb_items;
@@ -1275,6 +1279,11 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
   p.off_assign = take(p.n_anchor ? q_rows * 4 : 0);
   p.off_perm = take(p.n_anchor ? q_rows * 4 : 0);
   p.off_ghist = take(size_t(p.n_anchor) * (p.group_blocks + 1) * 4);   // per (anchor, block) counts + per anchor totals
+  // host-buffer mode: the sampled tiles of the pivot pre-pass, copied ahead of the gallery into a compact block
+  const size_t s_rows = size_t(p.n_sample_tiles) * BN;
+  p.off_s32 = take(s_rows * size_t(D) * 4);
+  p.off_sh = take(s_rows * p.Dp * 2);
+  p.off_spack = take(size_t(p.n_sample_tiles) * NPACK * 4);
   p.total_bytes = off;
   return p;
 }
@@ -1341,9 +1350,42 @@ static int launch_mode(int katoms, int grid, const CUtensorMap& tq, const CUtens
   }
 }
 
+// Host-buffer mode: three internal streams per device (copies, gallery prep, every second sweep) and the events that order
+// them against the caller's stream.  Created once, never destroyed; calls on one device enqueue one at a time.
+constexpr int kMaxSplits = 16;
+struct PipeStreams {
+  cudaStream_t copy = nullptr, prep = nullptr, sweep2 = nullptr;
+  cudaEvent_t start = nullptr, q_in = nullptr, sample_in = nullptr, ladder = nullptr, sweep2_done = nullptr;
+  cudaEvent_t chunk_in[kMaxSplits] = {}, chunk_ready[kMaxSplits] = {};
+  bool ready = false;
+};
+static std::mutex g_pipe_mutex;
+static PipeStreams g_pipe[64];
+
+static int pipe_streams(int dev, PipeStreams** out) {
+  MMSIM_REQUIRE(dev >= 0 && dev < 64, MMSIM_ERR_ARG, "knn_host: device ordinal %d out of range", dev);
+  PipeStreams& ps = g_pipe[dev];
+  if (!ps.ready) {
+    MMSIM_CUDA_CHECK(cudaStreamCreateWithFlags(&ps.copy, cudaStreamNonBlocking));
+    MMSIM_CUDA_CHECK(cudaStreamCreateWithFlags(&ps.prep, cudaStreamNonBlocking));
+    MMSIM_CUDA_CHECK(cudaStreamCreateWithFlags(&ps.sweep2, cudaStreamNonBlocking));
+    cudaEvent_t* single[] = {&ps.start, &ps.q_in, &ps.sample_in, &ps.ladder, &ps.sweep2_done};
+    for (cudaEvent_t* e : single) MMSIM_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxSplits; ++i) {
+      MMSIM_CUDA_CHECK(cudaEventCreateWithFlags(&ps.chunk_in[i], cudaEventDisableTiming));
+      MMSIM_CUDA_CHECK(cudaEventCreateWithFlags(&ps.chunk_ready[i], cudaEventDisableTiming));
+    }
+    ps.ready = true;
+  }
+  *out = &ps;
+  return MMSIM_OK;
+}
+
 int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
         float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream, int phases, int shard_kp,
-        float* out_lb) {
+        float* out_lb, const HostPipe* host) {
+  MMSIM_REQUIRE(!host || (phases == kPhaseAll && shard_kp == 0 && host->q_host && host->g_host), MMSIM_ERR_ARG,
+                "knn_host: host-buffer mode runs all phases of an unsharded call");
   MMSIM_REQUIRE(shard_kp == 0 || (out_lb && shard_kp >= 1 && shard_kp <= KP), MMSIM_ERR_ARG,
                 "knn: shard mode needs out_lb and 1 <= kp <= %d", KP);
   MMSIM_REQUIRE(Q && G && out_dist && out_idx && status && ws, MMSIM_ERR_ARG, "knn: null pointer argument");
@@ -1386,6 +1428,21 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   const bool group = p.n_anchor != 0 && (shard_kp != 0 || p.group_default);
   int* perm = group ? reinterpret_cast<int*>(w + p.off_perm) : nullptr;
   int* ghist = reinterpret_cast<int*>(w + p.off_ghist);
+  float* s32 = reinterpret_cast<float*>(w + p.off_s32);
+  __half* sh = reinterpret_cast<__half*>(w + p.off_sh);
+  float* spack = reinterpret_cast<float*>(w + p.off_spack);
+
+  PipeStreams* ps = nullptr;
+  std::unique_lock<std::mutex> pipe_lock;
+  if (host) {
+    MMSIM_REQUIRE(p.n_splits <= kMaxSplits, MMSIM_ERR_UNSUPPORTED, "knn_host: more than %d gallery splits", kMaxSplits);
+    pipe_lock = std::unique_lock<std::mutex>(g_pipe_mutex);
+    if (int rc0 = pipe_streams(dev, &ps)) return rc0;
+  }
+  const bool vec = D % 4 == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0;
+  auto prep = vec ? prep_rows_kernel<true> : prep_rows_kernel<false>;
+  const int warps_per_block = PREP_THREADS / 32;
+  const int64_t cap = int64_t(num_sms) * 16;     // grid-stride: a few resident waves, one atomic pair per block
 
   if (phases & kPhaseRerank) {
     MMSIM_CUDA_CHECK(cudaMemsetAsync(status, 0, 8 * sizeof(int), stream));
@@ -1395,17 +1452,24 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   // 1. operand copies: fp16 rows, norm pack (+ per-8 / per-32 column minima), rounding-error norms
   if (phases & kPhasePrep) {
     MMSIM_CUDA_CHECK(cudaMemsetAsync(gstats, 0, 64, stream));
-    const int64_t g_pad = int64_t(p.n_tiles) * BN;
-    const bool vec = D % 4 == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0;
-    auto prep = vec ? prep_rows_kernel<true> : prep_rows_kernel<false>;
-    const int warps_per_block = PREP_THREADS / 32;
-    const int64_t cap = int64_t(num_sms) * 16;     // grid-stride: a few resident waves, one atomic pair per block
-    const unsigned gb = unsigned(std::min<int64_t>((g_pad + warps_per_block - 1) / warps_per_block, cap));
-    prep<<<gb, PREP_THREADS, 0, stream>>>(G, ng, g_pad, int(D), p.Dp, 1.0f, gh, gpack, nullptr, 1,
-                                          reinterpret_cast<unsigned int*>(gstats), nullptr);
-    MMSIM_CUDA_CHECK(cudaGetLastError());
-    pack_min_kernel<<<unsigned(p.n_tiles), BN, 0, stream>>>(gpack);
-    MMSIM_CUDA_CHECK(cudaGetLastError());
+    if (host) {
+      // host-buffer mode: the gallery is copied and prepared split by split next to the sweeps (below); only the queries
+      // are needed now.  Everything queued earlier on the caller's stream -- a previous call still reading the staging
+      // buffers or this workspace -- precedes the copies.
+      MMSIM_CUDA_CHECK(cudaEventRecord(ps->start, stream));
+      MMSIM_CUDA_CHECK(cudaStreamWaitEvent(ps->copy, ps->start, 0));
+      MMSIM_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(Q), host->q_host, size_t(nq) * D * 4, cudaMemcpyHostToDevice, ps->copy));
+      MMSIM_CUDA_CHECK(cudaEventRecord(ps->q_in, ps->copy));
+      MMSIM_CUDA_CHECK(cudaStreamWaitEvent(stream, ps->q_in, 0));
+    } else {
+      const int64_t g_pad = int64_t(p.n_tiles) * BN;
+      const unsigned gb = unsigned(std::min<int64_t>((g_pad + warps_per_block - 1) / warps_per_block, cap));
+      prep<<<gb, PREP_THREADS, 0, stream>>>(G, ng, g_pad, int(D), p.Dp, 1.0f, gh, gpack, nullptr, 1,
+                                            reinterpret_cast<unsigned int*>(gstats), nullptr);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
+      pack_min_kernel<<<unsigned(p.n_tiles), BN, 0, stream>>>(gpack);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
+    }
     const unsigned qb = unsigned(std::min<int64_t>((nq + warps_per_block - 1) / warps_per_block, cap));
     prep<<<qb, PREP_THREADS, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, 0, nullptr, nullptr);
     MMSIM_CUDA_CHECK(cudaGetLastError());
@@ -1467,8 +1531,36 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
       fill_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(piv16, n, kInf);
       MMSIM_CUDA_CHECK(cudaGetLastError());
     }
-    if ((phases & kPhasePivot) && p.use_pivots) {
+    if ((phases & kPhasePivot) && p.use_pivots && !host) {
       rc = launch_mode<MODE_PIVOT, 0>(p.katoms, p.pivot_grid, tq, tg, args, stream);
+      if (rc) return rc;
+    }
+    if ((phases & kPhasePivot) && p.use_pivots && host) {
+      // host-buffer mode: the sampled tiles come over first, as one compact block of n_sample_tiles tiles, so the pre-pass
+      // (and with it the first sweep) does not wait for the gallery.  Same rows, same windows, same pivot lists.
+      int64_t s_valid = 0;
+      for (int i = 0; i < p.n_sample_tiles; ++i) {
+        const int64_t t = (int64_t(2 * i + 1) * p.n_tiles) / (2 * p.n_sample_tiles);      // tile_of<MODE_PIVOT>
+        const int64_t rows = std::min<int64_t>(BN, ng - t * BN);                         // only the last one can be short
+        MMSIM_CUDA_CHECK(cudaMemcpyAsync(s32 + size_t(i) * BN * D, host->g_host + size_t(t) * BN * D, size_t(rows) * D * 4,
+                                         cudaMemcpyHostToDevice, ps->copy));
+        s_valid = int64_t(i) * BN + rows;
+      }
+      MMSIM_CUDA_CHECK(cudaEventRecord(ps->sample_in, ps->copy));
+      MMSIM_CUDA_CHECK(cudaStreamWaitEvent(stream, ps->sample_in, 0));
+      const int64_t s_pad = int64_t(p.n_sample_tiles) * BN;
+      const unsigned sb = unsigned(std::min<int64_t>((s_pad + warps_per_block - 1) / warps_per_block, cap));
+      prep<<<sb, PREP_THREADS, 0, stream>>>(s32, s_valid, s_pad, int(D), p.Dp, 1.0f, sh, spack, nullptr, 1, nullptr, nullptr);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
+      pack_min_kernel<<<unsigned(p.n_sample_tiles), BN, 0, stream>>>(spack);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
+      CUtensorMap ts;
+      rc = make_tmap(&ts, sh, s_valid, p.Dp, BN);
+      if (rc) return rc;
+      SweepArgs sa = args;
+      sa.gpack = spack;
+      sa.n_tiles = p.n_sample_tiles;           // every tile of the compact block is a sampled one
+      rc = launch_mode<MODE_PIVOT, 0>(p.katoms, p.pivot_grid, tq, ts, sa, stream);
       if (rc) return rc;
     }
     if ((phases & kPhaseLadder) && p.use_pivots) {
@@ -1481,7 +1573,44 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
         MMSIM_CUDA_CHECK(cudaMemsetAsync(split_done, 0, size_t(p.n_qblocks) * BM * p.n_splits * 4, stream));
       const int abl = sweep_ablation();
       args.close_rows = abl == 8;
-      if (sweep_pairs() && (abl == 0 || abl == 8)) {
+      if (host) {
+        // host-buffer mode: one launch per gallery split.  Split c's rows are copied (copy stream), converted (prep
+        // stream) and swept while the copy of split c + 1 is in flight; the sweeps alternate between the caller's stream
+        // and a second one so that the CTAs of the next sweep fill the SMs the last wave of the previous one leaves idle.
+        MMSIM_CUDA_CHECK(cudaEventRecord(ps->ladder, stream));
+        bool used2 = false;
+        for (int c = 0; c < p.n_splits; ++c) {
+          const int64_t t0 = int64_t(c) * p.tiles_per_split, t1 = std::min<int64_t>(p.n_tiles, t0 + p.tiles_per_split);
+          const int64_t r0 = t0 * BN, r1 = std::min<int64_t>(ng, t1 * BN), r_pad = t1 * BN - r0;
+          MMSIM_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(G) + size_t(r0) * D, host->g_host + size_t(r0) * D,
+                                           size_t(r1 - r0) * D * 4, cudaMemcpyHostToDevice, ps->copy));
+          MMSIM_CUDA_CHECK(cudaEventRecord(ps->chunk_in[c], ps->copy));
+          MMSIM_CUDA_CHECK(cudaStreamWaitEvent(ps->prep, ps->chunk_in[c], 0));
+          const unsigned gb = unsigned(std::min<int64_t>((r_pad + warps_per_block - 1) / warps_per_block, cap));
+          prep<<<gb, PREP_THREADS, 0, ps->prep>>>(G + size_t(r0) * D, r1 - r0, r_pad, int(D), p.Dp, 1.0f, gh + size_t(r0) * p.Dp,
+                                                  gpack + size_t(t0) * NPACK, nullptr, 1,
+                                                  reinterpret_cast<unsigned int*>(gstats), nullptr);
+          MMSIM_CUDA_CHECK(cudaGetLastError());
+          pack_min_kernel<<<unsigned(t1 - t0), BN, 0, ps->prep>>>(gpack + size_t(t0) * NPACK);
+          MMSIM_CUDA_CHECK(cudaGetLastError());
+          MMSIM_CUDA_CHECK(cudaEventRecord(ps->chunk_ready[c], ps->prep));
+          cudaStream_t x = (c & 1) ? ps->sweep2 : stream;
+          if ((c & 1) && !used2) {
+            MMSIM_CUDA_CHECK(cudaStreamWaitEvent(x, ps->ladder, 0));
+            used2 = true;
+          }
+          MMSIM_CUDA_CHECK(cudaStreamWaitEvent(x, ps->chunk_ready[c], 0));
+          SweepArgs sa = args;
+          sa.item_begin = c * p.n_qblocks;
+          sa.item_end = (c + 1) * p.n_qblocks;
+          rc = launch_mode<MODE_SWEEP, 0>(p.katoms, std::min(num_sms, p.n_qblocks), tq, tg, sa, x);
+          if (rc) return rc;
+        }
+        if (used2) {
+          MMSIM_CUDA_CHECK(cudaEventRecord(ps->sweep2_done, ps->sweep2));
+          MMSIM_CUDA_CHECK(cudaStreamWaitEvent(stream, ps->sweep2_done, 0));
+        }
+      } else if (sweep_pairs() && (abl == 0 || abl == 8)) {
         CUtensorMap tgh;
         rc = make_tmap(&tgh, gh, ng, p.Dp, BN / 2);
         if (rc) return rc;

@@ -56,6 +56,48 @@ def knn_raw(q: torch.Tensor, g: torch.Tensor, k: int, exclude_self: bool = False
     return dist, idx, status
 
 
+def knn_host(q_host: torch.Tensor, g_host: torch.Tensor, k: int, exclude_self: bool = False, self_offset: int = 0, *,
+             device=None, stage=None, out=None):
+    """``knn_raw`` for arrays in HOST memory (``mmsim_knn_host_f32``): CPU float32 tensors in -- page-locked
+    (``.pin_memory()``) for the transfers to overlap the kernels -- and the same (dist, idx, status) out.  The gallery
+    goes over one split at a time while the previous split is being swept, so only the first split's copy is exposed.
+    ``stage`` = (q_stage [Q,D], g_stage [G,D]) CUDA float32 buffers for the device copies (allocated when omitted; keep
+    them between calls); ``out`` = (dist, idx, status) with dist / idx in device or page-locked host memory."""
+    lib = _lib.load()
+    _lib.require_cuda(torch)
+    for name, t in (("q_host", q_host), ("g_host", g_host)):
+        if not (torch.is_tensor(t) and t.device.type == "cpu" and t.dtype == torch.float32 and t.dim() == 2 and t.is_contiguous()):
+            raise ValueError(f"{name} must be a contiguous 2-d float32 CPU tensor")
+    nq, d = q_host.shape
+    ng = g_host.shape[0]
+    if g_host.shape[1] != d:
+        raise ValueError(f"queries are {d}-d but the gallery is {g_host.shape[1]}-d")
+    if not 1 <= k <= _lib.KNN_MAX_K - (1 if exclude_self else 0):
+        raise ValueError(f"k={k} unsupported: 1 <= k <= {_lib.KNN_MAX_K - (1 if exclude_self else 0)}")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if stage is None:
+        stage = (torch.empty((nq, d), dtype=torch.float32, device=dev), torch.empty((ng, d), dtype=torch.float32, device=dev))
+    q_stage, g_stage = stage
+    if tuple(q_stage.shape) != (nq, d) or tuple(g_stage.shape) != (ng, d) or not (q_stage.is_contiguous() and g_stage.is_contiguous()) \
+            or q_stage.dtype != torch.float32 or g_stage.dtype != torch.float32 or q_stage.device != dev or g_stage.device != dev:
+        raise ValueError("stage must be contiguous float32 CUDA tensors shaped like q_host and g_host")
+    nbytes = ctypes.c_size_t()
+    _lib.check(lib.mmsim_knn_workspace_bytes(nq, ng, d, k, ctypes.byref(nbytes)), "mmsim_knn_workspace_bytes")
+    ws = workspace("knn", nbytes.value, dev)
+    if out is None:
+        dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        status = torch.empty(8, dtype=torch.int32, device=dev)
+    else:
+        dist, idx, status = out
+    with torch.cuda.device(dev):
+        rc = lib.mmsim_knn_host_f32(q_host.data_ptr(), nq, g_host.data_ptr(), ng, d, k, int(bool(exclude_self)), int(self_offset),
+                                    dist.data_ptr(), idx.data_ptr(), status.data_ptr(), q_stage.data_ptr(), g_stage.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), stream_handle(dev))
+    _lib.check(rc, "mmsim_knn_host_f32")
+    return dist, idx, status
+
+
 def check_status(status: torch.Tensor) -> int:
     """Synchronising check of a knn status word; returns the number of queries that took the exact fallback."""
     s = status.tolist()
@@ -89,6 +131,34 @@ def retrieve(queries, gallery, k, *, exclude_self=False, self_offset=0, queries2
     if as_numpy:
         return dist.cpu().numpy(), idx.cpu().numpy()
     return dist, idx
+
+
+def _as_host_f32(x) -> torch.Tensor:
+    if torch.is_tensor(x):
+        return x.detach().to(device="cpu", dtype=torch.float32).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+
+
+def retrieve_host(queries, gallery, k, *, exclude_self=False, self_offset=0, check=True, device=None):
+    """``retrieve`` for embeddings that live in host memory (NumPy arrays or CPU tensors), as they do in the reference's
+    evaluation scripts: (dist [Q,k] float32, idx [Q,k] int64) NumPy arrays out.  The transfers are part of the call and
+    overlap it (``knn_host``): the gallery is swept split by split as it arrives and the re-rank kernel writes the result
+    rows straight into page-locked host memory.  Page-locked inputs (``torch.Tensor.pin_memory``) overlap fully."""
+    q, g = _as_host_f32(queries), _as_host_f32(gallery)
+    if q.dim() != 2 or g.dim() != 2:
+        raise ValueError(f"queries and gallery must be [rows, D], got {tuple(q.shape)} and {tuple(g.shape)}")
+    k = int(k)
+    _lib.require_cuda(torch)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    dist = torch.empty((q.shape[0], k), dtype=torch.float32).pin_memory()
+    idx = torch.empty((q.shape[0], k), dtype=torch.int32).pin_memory()
+    status = torch.empty(8, dtype=torch.int32, device=dev)
+    knn_host(q, g, k, exclude_self, self_offset, device=dev, out=(dist, idx, status))
+    if check:
+        check_status(status)            # reads the status word back on the same stream: the host buffers are complete
+    else:
+        torch.cuda.current_stream(dev).synchronize()
+    return dist.numpy().copy(), idx.numpy().astype(np.int64)
 
 
 def retrieve_one(query, database, query_label=None, labels=None, normalize=False, k=None):

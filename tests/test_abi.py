@@ -40,6 +40,8 @@ def test_argument_errors_are_reported_without_a_device():
     assert lib.mmsim_knn_workspace_bytes(1000, 100000, 128, 100, ctypes.byref(n)) == 0 and n.value > 0
     assert lib.mmsim_sqdist_f32(None, 1, None, 1, 1, 0, None, 1, None) == -1
     assert lib.mmsim_knn_merge(None, None, 0, None, 1, 1, 1, None, None, None) == -1
+    assert lib.mmsim_knn_host_f32(None, 8, None, 8, 4, 1, 0, 0, None, None, None, None, None, None, 0, None) == -1
+    assert b"knn_host" in lib.mmsim_last_error()
 
 
 def test_no_cpu_fallback():
