@@ -62,6 +62,7 @@ MMSIM_API int mmsim_knn_workspace_bytes(int64_t nq, int64_t ng, int64_t D, int k
   // the layout is sized for the largest grid any device could use, so the answer does not depend on the device
   size_t worst = 0;
   for (int sms = 1; sms <= 192; ++sms) worst = std::max(worst, knn::make_plan(nq, ng, D, k, sms).total_bytes);
+  worst = std::max(worst, knn::make_plan(nq, ng, D, k, 148, true).total_bytes);   // mmsim_knn_host_f32 (any SM count)
   *bytes = worst;
   return MMSIM_OK;
 }

@@ -24,7 +24,8 @@ struct Plan {
   size_t total_bytes;
 };
 
-Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms);
+// host_mode: the plan of mmsim_knn_host_f32 (more gallery splits: the unit of its copy / sweep pipeline)
+Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, bool host_mode = false);
 
 enum : int { kPhasePrep = 1, kPhaseTensor = 2, kPhaseRerank = 4, kPhaseFallback = 8, kPhasePivot = 16, kPhaseLadder = 32, kPhaseAll = 63 };
 

@@ -1190,7 +1190,7 @@ static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int Dp, in
   return MMSIM_OK;
 }
 
-Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
+Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, bool host_mode) {
   Plan p{};
   p.Dp = int(align_up(size_t(D), KATOM));
   p.katoms = p.Dp / KATOM;
@@ -1211,6 +1211,12 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms) {
       best_eff = eff;
       best_s = s_eff;
     }
+  }
+  if (host_mode) {
+    // Host-buffer mode launches one sweep per split as its rows arrive, two in flight (no wave quantisation to balance):
+    // splits are the unit of the copy / sweep pipeline.  8 exposes only the queries' transfer -- 29.4 / 28.2 / 28.0 / 27.1 /
+    // 27.1 / 27.9 ms end to end with 3 / 4 / 6 / 8 / 12 / 16 splits against 26.1 ms device-resident (gpurun_out/host_splits*.log).
+    best_s = int(std::max<int64_t>(1, std::min<int64_t>(8, p.n_tiles / 64)));
   }
   if (const char* e = getenv("MMSIM_KNN_SPLITS")) {   // experiment switch
     const int v = atoi(e);
@@ -1400,7 +1406,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   int dev = 0, num_sms = 0;
   MMSIM_CUDA_CHECK(cudaGetDevice(&dev));
   MMSIM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  const Plan p = make_plan(nq, ng, D, k, num_sms);
+  const Plan p = make_plan(nq, ng, D, k, num_sms, host != nullptr);
   MMSIM_REQUIRE(ws_bytes >= p.total_bytes, MMSIM_ERR_WORKSPACE, "knn: workspace too small (%zu < %zu)", ws_bytes, p.total_bytes);
 
   uint8_t* w = static_cast<uint8_t*>(ws);
@@ -1579,6 +1585,8 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
         // and a second one so that the CTAs of the next sweep fill the SMs the last wave of the previous one leaves idle.
         MMSIM_CUDA_CHECK(cudaEventRecord(ps->ladder, stream));
         bool used2 = false;
+        const char* e1 = getenv("MMSIM_HOST_ONE_STREAM");   // experiment switch: every sweep on the caller's stream
+        const bool one_stream = e1 && atoi(e1) == 1;
         for (int c = 0; c < p.n_splits; ++c) {
           const int64_t t0 = int64_t(c) * p.tiles_per_split, t1 = std::min<int64_t>(p.n_tiles, t0 + p.tiles_per_split);
           const int64_t r0 = t0 * BN, r1 = std::min<int64_t>(ng, t1 * BN), r_pad = t1 * BN - r0;
@@ -1594,8 +1602,8 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
           pack_min_kernel<<<unsigned(t1 - t0), BN, 0, ps->prep>>>(gpack + size_t(t0) * NPACK);
           MMSIM_CUDA_CHECK(cudaGetLastError());
           MMSIM_CUDA_CHECK(cudaEventRecord(ps->chunk_ready[c], ps->prep));
-          cudaStream_t x = (c & 1) ? ps->sweep2 : stream;
-          if ((c & 1) && !used2) {
+          cudaStream_t x = (c & 1) && !one_stream ? ps->sweep2 : stream;
+          if (x != stream && !used2) {
             MMSIM_CUDA_CHECK(cudaStreamWaitEvent(x, ps->ladder, 0));
             used2 = true;
           }
