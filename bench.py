@@ -323,15 +323,25 @@ def main():
 
     st_e2e = torch.empty(8, dtype=torch.int32, device=dev)
 
+    if world > 1:
+        # Device staging buffers that persist across steps, like the workspace: the inputs are copied INTO them every
+        # step.  (A fresh ShardedGallery per step re-allocates its multi-GB workspace from torch's caching allocator,
+        # which fragments and falls back to cudaMalloc / cudaFree erratically: 22 vs 31 ms per step at N = 2,
+        # profiles/r1_i_e2e_sharded_n2.txt.)
+        q_stage = torch.empty_like(queries)
+        sg_e2e = ShardedGallery(torch.empty_like(sg.shard), presharded=True, row_offset=lo, total_rows=G)
+
     def step_e2e():
-        qd = q_host.to(dev, non_blocking=True)
-        gd = g_host.to(dev, non_blocking=True)
         if world == 1:
+            qd = q_host.to(dev, non_blocking=True)
+            gd = g_host.to(dev, non_blocking=True)
             # the re-rank kernel writes the result rows straight into the pinned host buffers (they are device-accessible
             # under UVA): the device->host transfer of the result overlaps the kernel instead of following it
             d_, i_, st = knn_raw(qd, gd, k, out=(res_d, res_i, st_e2e))
         else:
-            d_, i_ = ShardedGallery(gd, presharded=True, row_offset=lo, total_rows=G).retrieve(qd, k, check=False)
+            q_stage.copy_(q_host, non_blocking=True)
+            sg_e2e.shard.copy_(g_host, non_blocking=True)
+            d_, i_ = sg_e2e.retrieve(q_stage, k, check=False)
             res_d.copy_(d_, non_blocking=True)
             res_i.copy_(i_, non_blocking=True)
         return d_, i_
