@@ -56,7 +56,17 @@ def test_no_cpu_fallback():
     with pytest.raises(mm.MmsimError):
         mm.retrieve(x, x, 2)
     with pytest.raises(mm.MmsimError):
+        mm.retrieve_host(x, x, 2)
+    with pytest.raises(mm.MmsimError):
         mm.batch_hard(x, np.array([1, 1, 2, 2], np.float32))
+    with pytest.raises(mm.MmsimError):
+        mm.evaluate(x, np.array([1, 1, 2, 2], np.int32))
+    with pytest.raises(mm.MmsimError):
+        mm.select_triplets_facenet(np.array([1, 1, 2, 2]), np.zeros((4, 4), np.float32), 4)
+    with pytest.raises(mm.MmsimError):
+        mm.project_normalize(x, np.zeros((8, 3), np.float32))
+    with pytest.raises(mm.MmsimError):
+        mm.triplet_semihard_loss(np.array([1, 1, 2, 2]), x)
 
 
 def test_product_never_imports_oracle():
