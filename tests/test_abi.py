@@ -44,6 +44,20 @@ def test_argument_errors_are_reported_without_a_device():
     assert b"knn_host" in lib.mmsim_last_error()
 
 
+def test_every_entry_point_rejects_null_arguments():
+    """All-zero / NULL arguments: each compute entry point returns MMSIM_ERR_ARG with a message naming itself, before
+    touching the device (this box has none) or any pointer."""
+    from multimodal_similarity_b200 import _lib
+    lib = _lib.load()
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        if name in ("mmsim_version", "mmsim_last_error"):
+            continue
+        args = [0.0 if t in (ctypes.c_float, ctypes.c_double) else 0 if t in (ctypes.c_int, ctypes.c_int32, ctypes.c_int64,
+                                                                               ctypes.c_size_t) else None for t in argtypes]
+        assert getattr(lib, name)(*args) == -1, name
+        assert lib.mmsim_last_error(), name
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
