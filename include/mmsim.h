@@ -80,9 +80,18 @@ MMSIM_API int mmsim_loss_f32(int kind, const float* E, const float* pids, int64_
  * (a shard holds < 2^31 rows), ordered by (distance, index); -1 / +inf pad when G has fewer than k rows.
  * exclude_self != 0 drops gallery row (self_offset + i) for query i: the leave-one-out of utils.evaluate
  * (src/utils.py:115,172) without the np.delete copy; indices stay in G's numbering.
- * status[8] (device int32): [0] queries that needed the exact fallback, [1] fallback overflow (result invalid),
- * [2] more uncertified queries than the fallback handles (result invalid).  D <= 256. */
+ * The tcgen05 kernel only filters: every returned distance is recomputed in the reference's arithmetic and the result is
+ * either certified or recomputed by the exact fallback (a second tensor-core sweep of the uncertified queries with a
+ * threshold derived from their k-th candidate distance; queries without such a bound, or with more ties than a log
+ * holds, take a streaming exact scan of the gallery) -- exact for ANY row order and any number of ties.
+ * status[8] (device int32): [0] queries that took the exact fallback, [1] queries queued for the streaming scan,
+ * [2] how many of those are done.  The call itself runs the first wave of 128; while status[2] < status[1] the caller
+ * repeats mmsim_knn_finish_f32 with the same arguments (the Python wrappers do) -- the result is complete when they are
+ * equal, which on data without thousands of exact duplicates they are when the call returns.  D <= 256. */
 MMSIM_API int mmsim_knn_workspace_bytes(int64_t nq, int64_t ng, int64_t D, int k, size_t* bytes);
+MMSIM_API int mmsim_knn_finish_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
+                         int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
+                         mmsim_stream_t stream);
 MMSIM_API int mmsim_knn_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
                   int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
                   mmsim_stream_t stream);
@@ -104,13 +113,15 @@ MMSIM_API int mmsim_knn_f32_phases(const float* Q, int64_t nq, const float* G, i
 /* The same retrieval with HOST buffers in: what a caller holding NumPy arrays (the reference's retrieve_one loop over
  * embeddings in host memory, src/utils.py:55-81, src/evaluate_model.py) binds.  q_host[nq*D] and g_host[ng*D] are host
  * arrays -- page-locked (cudaHostAlloc / cudaHostRegister) for the transfers to overlap the kernels; pageable memory works
- * but serialises.  The call copies the queries, then a 1/64 sample of the gallery (the pivot pre-pass needs nothing
+ * but serialises.  The call copies the queries, then a 1/61 sample of the gallery (the pivot pre-pass needs nothing
  * else), then the gallery one split at a time on an internal copy stream; each split is converted and swept while the
  * next one is in flight, so only the first split's transfer is exposed.  q_stage[nq*D] and g_stage[ng*D] are device
- * buffers the caller provides for the float32 copies (the exact re-rank reads them; the library never allocates).
+ * buffers the caller provides for the float32 copies (the exact re-rank reads them; the library never allocates); the
+ * workspace of this call is sized by mmsim_knn_host_workspace_bytes (more gallery splits than the device-resident call).
  * out_dist / out_idx may be device memory or page-locked host memory (the re-rank kernel writes them directly);
  * status is device memory.  Everything is ordered after earlier work on `stream` and complete, as far as `stream` is
  * concerned, when work queued after the call starts.  Results are identical to mmsim_knn_f32 on the same arrays. */
+MMSIM_API int mmsim_knn_host_workspace_bytes(int64_t nq, int64_t ng, int64_t D, int k, size_t* bytes);
 MMSIM_API int mmsim_knn_host_f32(const float* q_host, int64_t nq, const float* g_host, int64_t ng, int64_t D, int k,
                        int exclude_self, int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status,
                        float* q_stage, float* g_stage, void* ws, size_t ws_bytes, mmsim_stream_t stream);
@@ -133,9 +144,15 @@ MMSIM_API int mmsim_knn_merge(const float* dist_parts, const int32_t* idx_parts,
  *   3. every rank: mmsim_knn_shard_f32(phases = LADDER | TENSOR | RERANK) with kp << 128: its kp best candidates re-ranked
  *      exactly (out_dist/out_idx [nq*kp], shard-local indices) and out_lb[nq], a lower bound on the true distance of
  *      every row of the shard that was NOT re-ranked
- *   4. all-gather, mmsim_knn_merge_certified: global top-k by (distance, global index); status[0] counts queries whose
- *      k-th distance is not below every shard's bound.  If it is non-zero the caller repeats with the plain per-shard
- *      mmsim_knn_f32 + mmsim_knn_merge path (always exact; multimodal_similarity_b200/sharded.py does this).
+ *   4. exchange, mmsim_knn_merge_certified: global top-k by (distance, global index); status[0] counts queries whose
+ *      k-th distance is not below every shard's bound, out_flag[q] (nullable) = that k-th distance for such a query, -1
+ *      for a certified one.
+ *   5. per-QUERY exact fallback: every rank runs mmsim_knn_shard_fallback_f32 with the flags -- the exact top-k inside its
+ *      shard of the flagged queries only (same two tiers as mmsim_knn_f32's fallback; compact [cap, k] blocks, slots in
+ *      ascending query order, identical on every rank) -- the blocks are all-gathered and mmsim_knn_merge_patch rewrites
+ *      those rows of the merged result.  Only if more than `cap` queries are flagged, or its streaming scan has queries
+ *      left (status[1] > status[2]), does the caller repeat the whole call with the plain per-shard mmsim_knn_f32 +
+ *      mmsim_knn_merge path (multimodal_similarity_b200/sharded.py).
  * kp is the caller's choice (sharded.py: twice the expected share of the 128 best keys per shard plus a margin). */
 MMSIM_API int mmsim_knn_shard_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int kp, int exclude_self,
                         int64_t self_offset, float* out_dist, int32_t* out_idx, float* out_lb, int32_t* status, void* ws,
@@ -143,14 +160,23 @@ MMSIM_API int mmsim_knn_shard_f32(const float* Q, int64_t nq, const float* G, in
 MMSIM_API int mmsim_knn_pivot_region(int64_t nq, int64_t ng, int64_t D, int k, size_t* offset, size_t* bytes);
 /* Introspection (tests): the launch geometry chosen for a problem on a device with num_sms SMs.
  * out[0..12) = padded width, K atoms, 128-query blocks, 256-row gallery tiles, gallery splits, tiles per split, grid,
- * log capacity per (query, split), pivot pre-pass used, sampled tiles, sampled columns per tile, workspace bytes,
+ * log capacity per (query, split), pivot pre-pass used, tiles of the compact gallery sample, sampled rows, workspace bytes,
  * [12], [13] (if n_out >= 14): workspace offsets of the per-(query, split) candidate counts (int32) and final thresholds. */
 MMSIM_API int mmsim_knn_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, int64_t* out, int n_out);
 MMSIM_API int mmsim_knn_merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t rows, float* out,
                            mmsim_stream_t stream);
 MMSIM_API int mmsim_knn_merge_certified(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride,
                               const int64_t* idx_base, int parts, int64_t nq, int k_in, int k, const float* lb_parts,
-                              int64_t lb_stride, float* out_dist, int64_t* out_idx, int32_t* status, mmsim_stream_t stream);
+                              int64_t lb_stride, float* out_dist, int64_t* out_idx, int32_t* status, float* out_flag,
+                              mmsim_stream_t stream);
+MMSIM_API int mmsim_knn_shard_fallback_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
+                                 int64_t self_offset, const float* flag, int cap, float* out_dist, int32_t* out_idx,
+                                 int32_t* out_query, int32_t* status, void* ws, size_t ws_bytes, mmsim_stream_t stream);
+/* rows row_map[s] (s < min(*count, cap); count and row_map on the device) of out_dist / out_idx [*, k] = merge of the
+ * `parts` compact lists of slot s (layout as mmsim_knn_merge with nq = cap) */
+MMSIM_API int mmsim_knn_merge_patch(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride, const int64_t* idx_base,
+                          int parts, int cap, int k, const int32_t* count, const int32_t* row_map, float* out_dist,
+                          int64_t* out_idx, mmsim_stream_t stream);
 
 /* Semi-hard (FaceNet) negative mining -- the inner test of utils.select_triplets_facenet (src/utils.py:474-480) for m
  * (anchor, positive) pairs at once.  dist is the [n, n] distance matrix (row pitch ld, e.g. from mmsim_sqdist_f32),

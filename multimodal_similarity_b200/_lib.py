@@ -25,6 +25,13 @@ SIGNATURES = {
     "mmsim_knn_workspace_bytes": (c_int, [c_int64, c_int64, c_int64, c_int, POINTER(c_size_t)]),
     "mmsim_knn_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int64,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mmsim_knn_finish_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int64,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mmsim_knn_host_workspace_bytes": (c_int, [c_int64, c_int64, c_int64, c_int, POINTER(c_size_t)]),
+    "mmsim_knn_shard_fallback_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int64, c_void_p, c_int,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "mmsim_knn_merge_patch": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
     "mmsim_knn_f32_phases": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int64,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
     "mmsim_knn_host_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int64,
@@ -35,7 +42,7 @@ SIGNATURES = {
     "mmsim_knn_plan": (c_int, [c_int64, c_int64, c_int64, c_int, c_int, POINTER(c_int64), c_int]),
     "mmsim_knn_merge_pivots": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
     "mmsim_knn_merge_certified": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_int, c_void_p,
-                                          c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                          c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmsim_semihard_mask_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p,
                                         c_void_p]),
     "mmsim_semihard_pick_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p]),
@@ -63,10 +70,24 @@ _lib = None
 
 
 def load() -> ctypes.CDLL:
-    """Load libmmsim.so (building it first if the sources are newer and nvcc is available)."""
+    """Load libmmsim.so, building it first when it is missing.  A library older than its sources is loaded with a warning
+    (set MMSIM_AUTO_REBUILD=1 to rebuild instead: never on by default, N ranks of one job would race on the same file)."""
     global _lib
     if _lib is not None:
         return _lib
+    if os.path.exists(LIB_PATH) and not os.environ.get("MMSIM_LIB"):
+        try:
+            from .build import needs_build
+            stale = needs_build()
+        except Exception:  # noqa: BLE001 -- sources not shipped with the library: nothing to compare against
+            stale = False
+        if stale and os.environ.get("MMSIM_AUTO_REBUILD") == "1":
+            from .build import build
+            build()
+        elif stale:
+            import warnings
+            warnings.warn("libmmsim.so is older than csrc/ or include/mmsim.h; run `python -m multimodal_similarity_b200.build` "
+                          "(or set MMSIM_AUTO_REBUILD=1) -- loading the existing library")
     if not os.path.exists(LIB_PATH):
         try:
             from .build import build

@@ -56,15 +56,22 @@ MMSIM_API int mmsim_loss_f32(int kind, const float* E, const float* pids, int64_
                    closest_negative, pos_idx, neg_idx, dE, ws, ws_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
-MMSIM_API int mmsim_knn_workspace_bytes(int64_t nq, int64_t ng, int64_t D, int k, size_t* bytes) {
-  MMSIM_REQUIRE(bytes, MMSIM_ERR_ARG, "knn_workspace_bytes: null output");
-  MMSIM_REQUIRE(nq > 0 && ng > 0 && D > 0 && D <= 256 && k >= 1, MMSIM_ERR_ARG, "knn_workspace_bytes: bad sizes");
+static int knn_ws_bytes(const char* what, int64_t nq, int64_t ng, int64_t D, int k, bool host_mode, size_t* bytes) {
+  MMSIM_REQUIRE(bytes, MMSIM_ERR_ARG, "%s: null output", what);
+  MMSIM_REQUIRE(nq > 0 && ng > 0 && D > 0 && D <= 256 && k >= 1, MMSIM_ERR_ARG, "%s: bad sizes", what);
   // the layout is sized for the largest grid any device could use, so the answer does not depend on the device
   size_t worst = 0;
-  for (int sms = 1; sms <= 192; ++sms) worst = std::max(worst, knn::make_plan(nq, ng, D, k, sms).total_bytes);
-  worst = std::max(worst, knn::make_plan(nq, ng, D, k, 148, true).total_bytes);   // mmsim_knn_host_f32 (any SM count)
+  for (int sms = 1; sms <= 192; ++sms) worst = std::max(worst, knn::make_plan(nq, ng, D, k, sms, host_mode).total_bytes);
   *bytes = worst;
   return MMSIM_OK;
+}
+
+MMSIM_API int mmsim_knn_workspace_bytes(int64_t nq, int64_t ng, int64_t D, int k, size_t* bytes) {
+  return knn_ws_bytes("knn_workspace_bytes", nq, ng, D, k, false, bytes);
+}
+
+MMSIM_API int mmsim_knn_host_workspace_bytes(int64_t nq, int64_t ng, int64_t D, int k, size_t* bytes) {
+  return knn_ws_bytes("knn_host_workspace_bytes", nq, ng, D, k, true, bytes);
 }
 
 MMSIM_API int mmsim_knn_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
@@ -89,6 +96,28 @@ MMSIM_API int mmsim_knn_host_f32(const float* q_host, int64_t nq, const float* g
   const knn::HostPipe hp{q_host, g_host};
   return knn::run(q_stage, nq, g_stage, ng, D, k, exclude_self, self_offset, out_dist, out_idx, status, ws, ws_bytes,
                   reinterpret_cast<cudaStream_t>(stream), knn::kPhaseAll, 0, nullptr, &hp);
+}
+
+MMSIM_API int mmsim_knn_finish_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
+                         int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
+                         mmsim_stream_t stream) {
+  return knn::run(Q, nq, G, ng, D, k, exclude_self, self_offset, out_dist, out_idx, status, ws, ws_bytes,
+                  reinterpret_cast<cudaStream_t>(stream), knn::kPhaseFinish);
+}
+
+MMSIM_API int mmsim_knn_shard_fallback_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
+                                 int64_t self_offset, const float* flag, int cap, float* out_dist, int32_t* out_idx,
+                                 int32_t* out_query, int32_t* status, void* ws, size_t ws_bytes, mmsim_stream_t stream) {
+  return knn::shard_fallback(Q, nq, G, ng, D, k, exclude_self, self_offset, flag, cap, out_dist, out_idx, out_query, status, ws,
+                             ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+MMSIM_API int mmsim_knn_merge_patch(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride, const int64_t* idx_base,
+                          int parts, int cap, int k, const int32_t* count, const int32_t* row_map, float* out_dist,
+                          int64_t* out_idx, mmsim_stream_t stream) {
+  MMSIM_REQUIRE(count && row_map, MMSIM_ERR_ARG, "knn_merge_patch: null pointer argument");
+  return merge::run(dist_parts, idx_parts, part_stride, idx_base, parts, cap, k, k, nullptr, 0, out_dist, out_idx, nullptr,
+                    reinterpret_cast<cudaStream_t>(stream), nullptr, count, row_map);
 }
 
 MMSIM_API int mmsim_knn_merge(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride, const int64_t* idx_base,
@@ -127,7 +156,7 @@ MMSIM_API int mmsim_knn_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_s
   MMSIM_REQUIRE(nq > 0 && ng > 0 && D > 0 && D <= 256 && k >= 1 && num_sms >= 1, MMSIM_ERR_ARG, "knn_plan: bad sizes");
   const knn::Plan p = knn::make_plan(nq, ng, D, k, num_sms);
   const int64_t v[14] = {p.Dp, p.katoms, p.n_qblocks, p.n_tiles, p.n_splits, p.tiles_per_split, p.grid, p.logcap,
-                         p.use_pivots, p.n_sample_tiles, p.sample_cols, int64_t(p.total_bytes),
+                         p.use_pivots, p.n_sample_tiles, p.n_sample, int64_t(p.total_bytes),
                          int64_t(p.off_log_cnt), int64_t(p.off_log_tau)};
   for (int i = 0; i < 14 && i < n_out; ++i) out[i] = v[i];
   return MMSIM_OK;
@@ -140,9 +169,10 @@ MMSIM_API int mmsim_knn_merge_pivots(const float* parts, int nparts, int64_t par
 
 MMSIM_API int mmsim_knn_merge_certified(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride,
                               const int64_t* idx_base, int parts, int64_t nq, int k_in, int k, const float* lb_parts,
-                              int64_t lb_stride, float* out_dist, int64_t* out_idx, int32_t* status, mmsim_stream_t stream) {
+                              int64_t lb_stride, float* out_dist, int64_t* out_idx, int32_t* status, float* out_flag,
+                              mmsim_stream_t stream) {
   return merge::run(dist_parts, idx_parts, part_stride, idx_base, parts, nq, k_in, k, lb_parts, lb_stride, out_dist, out_idx,
-                    status, reinterpret_cast<cudaStream_t>(stream));
+                    status, reinterpret_cast<cudaStream_t>(stream), out_flag);
 }
 
 MMSIM_API int mmsim_semihard_mask_f32(const float* dist, int64_t n, int64_t ld, const int32_t* labels, const int32_t* pairs,

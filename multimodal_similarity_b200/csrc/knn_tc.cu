@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "exact.cuh"
 #include "knn.h"
+#include "knn_fallback.cuh"
 #include "ptx.cuh"
 
 // the ablation instantiations of the sweep (ABL != 0) return early from the scan on purpose
@@ -135,7 +136,9 @@ constexpr int NPIV = 16;                   // pivot pre-pass: the 16 smallest sa
 constexpr int NPSUB = 8;                   // ... gathered from per-warp sub-lists of 8 (each warp scans a quarter of the columns)
 constexpr int KPT = KP;                    // candidates that must lie below a pivot before it becomes the threshold
 
-enum { MODE_PIVOT = 0, MODE_SWEEP = 1, MODE_ASSIGN = 2 };
+// MODE_RESWEEP: the sweep of the exact fallback (knn_fallback.cuh) -- same epilogue as MODE_SWEEP with a fixed threshold per
+// row, but the number of queries is only known on the device: the geometry is derived in the kernel from *dyn_count.
+enum { MODE_PIVOT = 0, MODE_SWEEP = 1, MODE_ASSIGN = 2, MODE_RESWEEP = 3 };
 
 // Experiment counters (MMSIM_DEBUG_BUILD=1 builds only; scripts/sweep_debug.py): [5] 8-column groups handed to the
 // candidate path, [6] epilogue warp cycles (sum over warps), [7] 32-column warp chunks with a hit
@@ -162,11 +165,15 @@ struct SweepArgs {
   float* log_tau;            // [row * n_splits + split] final threshold of the sweep
   int* split_done;           // [row * n_splits + split] bit 0: log_tau is published (later splits start from it);
                              // bits [1,16) / [16,31): rows this split logged below ladder rung piv1 / piv0
-  // MODE_PIVOT: item = query block; n_sample_tiles evenly spaced tiles, first sample_cols columns of each
-  int n_sample_tiles, sample_cols;
+  // MODE_PIVOT: item = query block; the "gallery" is the compact sample block of n_sample_tiles tiles, swept whole
+  int n_sample_tiles;
   float* piv16;              // MODE_PIVOT out: [row][16] the smallest sampled keys, ascending (+inf where missing)
   int* assign;               // MODE_ASSIGN out: [row] nearest row of the (small) "gallery" given -- the query's anchor
   const float* ladder;       // MODE_SWEEP in:  [row][4] = ladder pivots (ascending) and the initial threshold
+  // MODE_RESWEEP: number of queries (device), its cap, and the inputs of resweep_geometry()
+  const int* dyn_count;
+  int dyn_cap, dyn_ctas;
+  long long dyn_budget;
 };
 
 template <int KATOMS>
@@ -261,8 +268,7 @@ __device__ __noinline__ float pivot_insert(float x, uint32_t pv_addr) {
 
 template <int MODE>
 __device__ __forceinline__ int tile_of(const SweepArgs& a, int t0, int i) {
-  if (MODE != MODE_PIVOT) return t0 + i;
-  return int((int64_t(2 * i + 1) * a.n_tiles) / (2 * a.n_sample_tiles));
+  return t0 + i;
 }
 
 // ABL: ablation variants for scripts/sweep_ablate.py (wrong results by construction): 0 = product, 2 = never log a
@@ -336,18 +342,25 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  constexpr bool SWEEP = MODE == MODE_SWEEP || MODE == MODE_RESWEEP;
+  int nq = a.nq, n_qblocks = a.n_qblocks, n_splits = a.n_splits, tiles_per_split = a.tiles_per_split;
+  if (MODE == MODE_RESWEEP) {   // geometry from the device-side count of uncertified queries (uniform over the grid)
+    const DynGeom dg = resweep_geometry(min(*a.dyn_count, a.dyn_cap), a.n_tiles, a.dyn_ctas, a.dyn_budget);
+    nq = dg.nq; n_qblocks = dg.n_qblocks; n_splits = dg.n_splits; tiles_per_split = dg.tiles_per_split;
+  }
+
   // items: (split, query block) -- PAIR: (split, PAIR of query blocks), this CTA takes block 2 * pair + rank
-  const int n_qb_items = PAIR ? (a.n_qblocks + 1) / 2 : a.n_qblocks;
-  const int n_items = MODE == MODE_SWEEP ? (a.item_end ? a.item_end : n_qb_items * a.n_splits) : a.n_qblocks;
+  const int n_qb_items = PAIR ? (n_qblocks + 1) / 2 : n_qblocks;
+  const int n_items = SWEEP ? (a.item_end ? a.item_end : n_qb_items * n_splits) : n_qblocks;
   const int item0 = (MODE == MODE_SWEEP ? a.item_begin : 0) + (PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x));
   const int item_step = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
   auto item_range = [&](int item, int& qb, int& split, int& t0, int& nt) {
-    if (MODE == MODE_SWEEP) {
+    if (SWEEP) {
       split = item / n_qb_items;
       qb = item - split * n_qb_items;
       if (PAIR) qb = 2 * qb + int(crank);              // may be == n_qblocks (odd count): all rows invalid, loads zero-filled
-      t0 = split * a.tiles_per_split;
-      nt = min(a.n_tiles, t0 + a.tiles_per_split) - t0;
+      t0 = split * tiles_per_split;
+      nt = min(a.n_tiles, t0 + tiles_per_split) - t0;
     } else {
       split = 0; qb = item; t0 = 0; nt = a.n_sample_tiles;
     }
@@ -462,9 +475,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     for (int item = item0; item < n_items; item += item_step) {
       int qb, split, t0, nt;
       item_range(item, qb, split, t0, nt);
-      const bool qb_ok = !PAIR || qb < a.n_qblocks;      // PAIR: the second CTA of the last pair may have no block
+      const bool qb_ok = !PAIR || qb < n_qblocks;      // PAIR: the second CTA of the last pair may have no block
       const int grow = (qb_ok ? qb : 0) * BM + row;      // global query row (may be >= nq in the last block)
-      const bool valid = qb_ok && grow < a.nq;
+      const bool valid = qb_ok && grow < nq;
 
       float piv0 = -kInf, piv1 = -kInf;                 // MODE_SWEEP: ladder below the initial threshold
       uint32_t carry = 0;                               // MODE_SWEEP: rows finished splits logged below piv1 | piv0 << 15
@@ -472,9 +485,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       float as_best = kInf;                             // MODE_ASSIGN: smallest key of the row so far in this thread's chunks,
       int as_col = 0x7fffffff;                          //              and its column
       const uint32_t tau_addr = ptx::smem_u32(s_tau + row), cnt_addr = ptx::smem_u32(s_cnt + row);
-      uint2* const mylog = a.log + (size_t(grow) * a.n_splits + split) * a.logcap;
+      uint2* const mylog = a.log + (size_t(grow) * n_splits + split) * a.logcap;
       const uint32_t pv_addr = ptx::smem_u32(s_pv + (h * NPSUB) * BM + row);
-      if (MODE == MODE_SWEEP) {
+      if (SWEEP) {
         float tau0 = kInf;
         if (a.use_pivots) {
           const float4 pp = *reinterpret_cast<const float4*>(a.ladder + size_t(grow) * 4);
@@ -486,9 +499,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         // kept; the certificate in the rerank kernel bounds every unlogged row by the smallest threshold in force.)
         // It also publishes how many rows it logged below each rung: the ladder counters continue across splits instead
         // of restarting (a split on its own rarely sees KPT rows below the lower rung).
-        for (int s2 = 0; s2 < a.n_splits; ++s2) {
+        for (int s2 = 0; MODE == MODE_SWEEP && s2 < n_splits; ++s2) {   // (the re-sweep's thresholds are fixed)
           if (s2 == split) continue;
-          const size_t o = size_t(grow) * a.n_splits + s2;
+          const size_t o = size_t(grow) * n_splits + s2;
           uint32_t done;
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(a.split_done + o) : "memory");
           if (done) {
@@ -546,7 +559,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         const float nm32 = lds_f32(nrm + (BN + 32 + c) * 4);
         const float bound = tau - nm32;
         if (!__any_sync(0xffffffffu, m < bound) || ABL == 2) return;
-        if (MODE == MODE_SWEEP) {
+        if (SWEEP) {
           // Level 2 (warp has a hit): the same test per 8-column group; level 3 (out of line): the 8 keys of a group.
           // (The query operand was pre-scaled by -2: acc = -2 q.g, key = |g|^2 - 2 q.g.)
           const float4 nm8 = lds_f32x4(nrm + (BN + c * 4) * 4);
@@ -591,10 +604,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         const uint32_t nrm = ring_u32 + (tc % NT) * NPACK * 4;
         const uint32_t taddr = taddr0 + as * BN;
         const int col0 = tile_of<MODE>(a, t0, i) * BN;
-        // MODE_PIVOT samples whole tiles or a window of sample_cols/32 chunks per sampled tile (the window rotates over the
-        // tile's 8 chunks from one sampled tile to the next, so the epilogue warps share the work)
-        const int win = MODE == MODE_PIVOT ? a.sample_cols / 32 : 8, rot = i & 7;
-        auto sampled = [&](int c) { return MODE != MODE_PIVOT || ((c - rot) & 7) < win; };
         // Two register buffers.  Both loads of a pair are issued before either chunk is scanned, and the TMEM stage is
         // handed back to the MMA warp as soon as this warp's LAST load has landed -- before anything is scanned: the
         // MMA warp and the epilogue warps wait on each other once per tile, and whatever sits between the accumulator
@@ -622,10 +631,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
               ptx::mbar_arrive(&tempty[as]);
             }
           }
-          const float tau = MODE == MODE_SWEEP ? lds_f32(tau_addr) : pv_thr;
-          if (sampled(c0)) scan_chunk(va, c0, nrm, col0, tau);
+          const float tau = SWEEP ? lds_f32(tau_addr) : pv_thr;
+          scan_chunk(va, c0, nrm, col0, tau);
           if (!last) ptx::tmem_ld32(taddr + (cp + 2) * NH * 32, va);
-          if (sampled(c1)) scan_chunk(vb, c1, nrm, col0, MODE == MODE_SWEEP ? tau : pv_thr);
+          scan_chunk(vb, c1, nrm, col0, SWEEP ? tau : pv_thr);
           if (!last) ptx::tmem_ld32(taddr + (cp + 3) * NH * 32, vb);
         }
         if (MODE == MODE_SWEEP && h == (tc & (NH - 1))) {
@@ -641,14 +650,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         ptx::mbar_arrive(&nempty[tc % NT]);
       }
 
-      if (MODE == MODE_SWEEP) {
+      if (SWEEP) {
         epi_bar_sync(EPI_THREADS);             // all appends of this item are done
         if (h == 0 && qb_ok) {
-          const size_t o = size_t(grow) * a.n_splits + split;
+          const size_t o = size_t(grow) * n_splits + split;
           const uint32_t cn = s_cnt[row];
           a.log_cnt[o] = int(cn & CUR_MASK);
           a.log_tau[o] = s_tau[row];
-          if (a.n_splits > 1) {
+          if (MODE == MODE_SWEEP && n_splits > 1) {
             // Thresholds only steer how many candidates are kept: the final certificate (rerank kernel) bounds every
             // unlogged row by the smallest threshold in force, so a shared threshold can cost a fallback, never exactness.
             const uint32_t own1 = ((cn >> CN1_SHIFT) & 511u) - (carry & 0x7fffu), own0 = ((cn >> CN0_SHIFT) & 511u) - (carry >> 15);
@@ -879,7 +888,8 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
                   const float* __restrict__ gstats, float delta_coeff, int k, int kp, int exclude_self, int64_t self_offset,
                   float* __restrict__ out_dist, int* __restrict__ out_idx, float* __restrict__ out_lb,
                   int* __restrict__ status, int* __restrict__ unc_query, float* __restrict__ unc_bound, int unc_cap,
-                  const int* __restrict__ perm /* sweep position -> query (query grouping), or null: identity */) {
+                  const int* __restrict__ perm /* sweep position -> query (query grouping), or null: identity */,
+                  int force_mod /* test hook (MMSIM_KNN_FORCE_FALLBACK=m): every m-th query counts as uncertified */) {
   // kp <= KP candidates are re-ranked.  out_lb == nullptr: emit the top-k and certify locally (k <= kp).
   // out_lb != nullptr (gallery-shard mode): emit all kp re-ranked candidates (k == kp) plus the lower bound on the
   // true distance of every row of this shard that is NOT among them; the certificate is evaluated after the merge.
@@ -1063,97 +1073,18 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
       lb = sqrtf(fmaxf(lb2, 0.f)) * 0.999999f - (qerr[qi] + gstats[0]);
       if (!(lb == lb)) lb = -kInf;    // NaN inputs certify nothing
     }
+    if (force_mod > 0 && qo % force_mod == 0) lb = -kInf;
     if (out_lb) {
       out_lb[qo] = lb;
     } else {
       const float dk = sk[k - 1];
       if (!(dk < lb)) {
-        const int slot = atomicAdd(&status[0], 1);
+        const int slot = atomicAdd(&status[0], 1);     // unc_cap == nq: every query has a slot
         if (slot < unc_cap) {
           unc_query[slot] = qo;
           unc_bound[slot] = dk;
-        } else {
-          status[2] = 1;
         }
       }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ fallback
-// Exact recomputation for the (rare) uncertified queries.  Pass 1 collects every gallery row whose exact distance
-// is <= the query's upper bound (the k-th exact candidate distance); pass 2 sorts the collected rows.
-constexpr int FB_CAP = 2048;  // collected rows per uncertified query
-
-__global__ void knn_fallback_collect_kernel(const float* __restrict__ Q, const float* __restrict__ G, int64_t ng, int D,
-                                            int exclude_self, int64_t self_offset, const int* __restrict__ status,
-                                            const int* __restrict__ unc_query, const float* __restrict__ unc_bound,
-                                            int unc_cap, int* __restrict__ fb_count, float* __restrict__ fb_dist,
-                                            int* __restrict__ fb_idx, int* __restrict__ status_w) {
-  extern __shared__ float fb_q[];
-  const int n_unc = min(status[0], unc_cap);
-  const int chunks = gridDim.x;
-  for (int slot = blockIdx.y; slot < n_unc; slot += gridDim.y) {
-    const int qi = unc_query[slot];
-    const float bound = unc_bound[slot];
-    __syncthreads();
-    for (int c = threadIdx.x; c < D; c += blockDim.x) fb_q[c] = Q[size_t(qi) * D + c];
-    __syncthreads();
-    const int self = exclude_self ? int(self_offset + qi) : -1;
-    const int64_t per = (ng + chunks - 1) / chunks;
-    const int64_t g0 = int64_t(blockIdx.x) * per, g1 = min(ng, g0 + per);
-    for (int64_t g = g0 + threadIdx.x; g < g1; g += blockDim.x) {
-      if (int(g) == self) continue;
-      const float d = exact_l2(fb_q, G + g * D, D);
-      if (d <= bound) {
-        const int pos = atomicAdd(&fb_count[slot], 1);
-        if (pos < FB_CAP) {
-          fb_dist[size_t(slot) * FB_CAP + pos] = d;
-          fb_idx[size_t(slot) * FB_CAP + pos] = int(g);
-        } else {
-          status_w[1] = 1;  // overflow: more than FB_CAP rows within the bound (massive ties)
-        }
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-knn_fallback_select_kernel(const int* __restrict__ status, const int* __restrict__ unc_query, int unc_cap,
-                           const int* __restrict__ fb_count, const float* __restrict__ fb_dist,
-                           const int* __restrict__ fb_idx, int k, float* __restrict__ out_dist, int* __restrict__ out_idx) {
-  __shared__ float sk[FB_CAP];
-  __shared__ int sv[FB_CAP];
-  const int n_unc = min(status[0], unc_cap);
-  for (int slot = blockIdx.x; slot < n_unc; slot += gridDim.x) {
-    const int n = min(fb_count[slot], FB_CAP);
-    __syncthreads();
-    for (int i = threadIdx.x; i < FB_CAP; i += blockDim.x) {
-      sk[i] = i < n ? fb_dist[size_t(slot) * FB_CAP + i] : kInf;
-      sv[i] = i < n ? fb_idx[size_t(slot) * FB_CAP + i] : 0x7fffffff;
-    }
-    __syncthreads();
-    for (int size = 2; size <= FB_CAP; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int t = threadIdx.x; t < FB_CAP / 2; t += blockDim.x) {
-          const int lo = 2 * t - (t & (stride - 1));
-          const int hi = lo + stride;
-          const bool asc = (lo & size) == 0;
-          const float a = sk[lo], b = sk[hi];
-          const int ia = sv[lo], ib = sv[hi];
-          const bool gt = (a > b) || (a == b && ia > ib);
-          if (gt == asc) {
-            sk[lo] = b; sk[hi] = a;
-            sv[lo] = ib; sv[hi] = ia;
-          }
-        }
-        __syncthreads();
-      }
-    }
-    const int qi = unc_query[slot];
-    for (int r = threadIdx.x; r < k; r += blockDim.x) {
-      out_dist[size_t(qi) * k + r] = sk[r];
-      out_idx[size_t(qi) * k + r] = sk[r] < kInf ? sv[r] : -1;
     }
   }
 }
@@ -1226,26 +1157,25 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, bool host_
   p.tiles_per_split = (p.n_tiles + p.n_splits - 1) / p.n_splits;
   p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.grid = int(std::min<int64_t>(num_sms, int64_t(p.n_qblocks) * p.n_splits));
-  p.unc_cap = int(std::min<int64_t>(nq, 1024));
+  p.unc_cap = int(nq);
 
-  // candidate log + pivot pre-pass.  Small galleries are logged whole (threshold +inf); otherwise a sample of
-  // about 1/64 of the gallery gives each query the 16 smallest sampled keys: the 16th is the initial threshold
-  // (about 1000 gallery rows below it), the 8th / 4th / 2nd are the ladder the sweep tightens along.
+  // candidate log + pivot pre-pass.  Small galleries are logged whole (threshold +inf); otherwise a systematic sample of
+  // about 1/61 of the gallery rows gives each query its 16 smallest sampled keys: the 12th is the initial threshold, the
+  // 6th / 3rd are the ladder the sweep tightens along (make_ladder_kernel).  The sample takes every 61st row (a prime
+  // stride; the offset inside the stride changes from segment to segment), NOT contiguous tiles: with a class-sorted
+  // gallery a contiguous sample holds whole classes or nothing of them, and a query whose class was sampled got a threshold
+  // near its 12th neighbour (round-1 advisor finding).  The rows are gathered into a compact block the pre-pass sweeps whole.
   p.logcap = p.n_splits == 1 ? 2048 : 1024;
   p.use_pivots = ng > p.logcap ? 1 : 0;
-  p.sample_cols = BN;
-  p.n_sample_tiles = 0;
+  p.n_sample = 0; p.n_sample_tiles = 0; p.sample_div = 61; p.sample_seg = 1;
   if (p.use_pivots) {
-    // about 1/64 of the gallery, as few MMA tiles as possible while still spread over >= 8 places of the gallery
-    int div = 64;
     if (const char* e = getenv("MMSIM_PIVOT_DIV")) {   // experiment switch: sample 1/div of the gallery (with MMSIM_LADDER)
       const int v = atoi(e);
-      if (v >= 8 && v <= 1024) div = v;
+      if (v >= 8 && v <= 1024) p.sample_div = v;
     }
-    const int64_t target = std::max<int64_t>(ng / div, 32);
-    p.sample_cols = 32;
-    while (p.sample_cols < BN && target / (2 * p.sample_cols) >= 8) p.sample_cols *= 2;
-    p.n_sample_tiles = int(std::min<int64_t>(p.n_tiles, std::max<int64_t>(1, (target + p.sample_cols / 2) / p.sample_cols)));
+    p.n_sample = int(ng / p.sample_div);               // >= 33 rows (ng > 2048)
+    p.sample_seg = (p.n_sample + 15) / 16;             // 16 segments, each with its own offset inside the stride
+    p.n_sample_tiles = (p.n_sample + BN - 1) / BN;
     p.pivot_grid = std::min(num_sms, p.n_qblocks);
   }
 
@@ -1276,18 +1206,22 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, bool host_
   p.off_split_done = take(q_rows * p.n_splits * 4);
   p.off_unc_query = take(size_t(p.unc_cap) * 4);
   p.off_unc_bound = take(size_t(p.unc_cap) * 4);
-  p.off_fb_count = take(size_t(p.unc_cap) * 4);
-  p.off_fb_dist = take(size_t(p.unc_cap) * FB_CAP * 4);
-  p.off_fb_idx = take(size_t(p.unc_cap) * FB_CAP * 4);
+  p.off_fb2_list = take(size_t(p.unc_cap) * 4);
+  p.off_fb_qh = take(q_rows * p.Dp * 2);
+  p.off_fb_ladder = take(q_rows * 16);
+  p.off_fb2_dist = take(size_t(FB2_WAVE) * FB2_CHUNKS * KP * 4);
+  p.off_fb2_idx = take(size_t(FB2_WAVE) * FB2_CHUNKS * KP * 4);
   p.off_ah = take(size_t(p.n_anchor) * p.Dp * 2);
   p.off_apack = take(size_t(p.n_anchor / BN + 1) * NPACK * 4);
   p.off_aidx = take(size_t(p.n_anchor) * 4);
   p.off_assign = take(p.n_anchor ? q_rows * 4 : 0);
   p.off_perm = take(p.n_anchor ? q_rows * 4 : 0);
   p.off_ghist = take(size_t(p.n_anchor) * (p.group_blocks + 1) * 4);   // per (anchor, block) counts + per anchor totals
-  // host-buffer mode: the sampled tiles of the pivot pre-pass, copied ahead of the gallery into a compact block
+  // the gallery sample of the pivot pre-pass: row indices, fp16 rows + norm pack; host-buffer mode copies the fp32 rows
+  // ahead of the gallery into s32
   const size_t s_rows = size_t(p.n_sample_tiles) * BN;
-  p.off_s32 = take(s_rows * size_t(D) * 4);
+  p.off_sidx = take(s_rows * 4);
+  p.off_s32 = take(host_mode ? s_rows * size_t(D) * 4 : 0);
   p.off_sh = take(s_rows * p.Dp * 2);
   p.off_spack = take(size_t(p.n_sample_tiles) * NPACK * 4);
   p.total_bytes = off;
@@ -1387,6 +1321,90 @@ static int pipe_streams(int dev, PipeStreams** out) {
   return MMSIM_OK;
 }
 
+__global__ void sample_index_kernel(int* __restrict__ idx, int n_sample, int div, int seg) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_sample) idx[j] = int(sample_row(j, div, seg));
+}
+
+// delta bounds the fp32 accumulation error of key = |g|^2 - 2 q.g: (Dp + 8) roundings of relative size 2^-24, on terms
+// bounded by (|q|^2 + |g|^2), 4x safety (which also covers the one-ulp slack of the sweep's reordered chunk test
+// m < tau - min|g|^2; tests/test_gpu_certificate.py measures the real key error against it).
+static int env_int(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+}
+
+static float delta_coeff_of(int Dp) { return 4.0f * float(Dp + 8) * 5.9604645e-8f; }
+
+// Exact fallback (knn_fallback.cuh) for the queries listed in L (count on the device).  first_wave: tier 1 + the first
+// tier-2 wave (part of every call); otherwise one further tier-2 wave (mmsim_knn_finish_f32).
+static int run_fallback(const Plan& p, uint8_t* w, const float* Q, const float* G, int64_t ng, int D, int k, int exclude_self,
+                        int64_t self_offset, const FbLists& L, const FbOut& out, int num_sms, bool first_wave, cudaStream_t stream) {
+  const __half* gh = reinterpret_cast<const __half*>(w + p.off_gh);
+  const float* gpack = reinterpret_cast<const float*>(w + p.off_gpack);
+  const float* gstats = reinterpret_cast<const float*>(w + p.off_stats);
+  __half* fb_qh = reinterpret_cast<__half*>(w + p.off_fb_qh);
+  float* fb_ladder = reinterpret_cast<float*>(w + p.off_fb_ladder);
+  uint2* log = reinterpret_cast<uint2*>(w + p.off_log);
+  int* log_cnt = reinterpret_cast<int*>(w + p.off_log_cnt);
+  float* log_tau = reinterpret_cast<float*>(w + p.off_log_tau);
+  float* part_dist = reinterpret_cast<float*>(w + p.off_fb2_dist);
+  int* part_idx = reinterpret_cast<int*>(w + p.off_fb2_idx);
+  const size_t q_rows = size_t(p.n_qblocks) * BM;
+  const long long budget = (long long)(q_rows) * p.n_splits;     // (query row, split) slots of the main plan's log
+  if (first_wave) {
+    fb_prepare_kernel<<<2 * num_sms, FB_THREADS, 0, stream>>>(Q, D, p.Dp, L, gstats, delta_coeff_of(p.Dp), fb_qh, fb_ladder,
+                                                              env_int("MMSIM_KNN_FORCE_TIER2"));
+    MMSIM_CUDA_CHECK(cudaGetLastError());
+    CUtensorMap tq, tg;
+    int rc = make_tmap(&tq, fb_qh, int64_t(q_rows), p.Dp, BM);
+    if (rc) return rc;
+    rc = make_tmap(&tg, gh, ng, p.Dp, BN);
+    if (rc) return rc;
+    SweepArgs a{};
+    a.gpack = gpack;
+    a.n_tiles = p.n_tiles;
+    a.use_pivots = 1;
+    a.log = log; a.logcap = p.logcap; a.log_cnt = log_cnt; a.log_tau = log_tau;
+    a.ladder = fb_ladder;
+    a.dyn_count = L.count; a.dyn_cap = L.cap; a.dyn_ctas = num_sms; a.dyn_budget = budget;
+    rc = launch_mode<MODE_RESWEEP, 0>(p.katoms, num_sms, tq, tg, a, stream);
+    if (rc) return rc;
+    fb_select_kernel<<<4 * num_sms, FB_THREADS, size_t(D) * 4, stream>>>(Q, G, D, log, p.logcap, log_cnt, p.n_tiles, num_sms, budget, L,
+                                                                         k, exclude_self, self_offset, out);
+    MMSIM_CUDA_CHECK(cudaGetLastError());
+  }
+  fb2_scan_kernel<<<dim3(FB2_CHUNKS, FB2_WAVE), FB_THREADS, size_t(D) * 4, stream>>>(Q, G, ng, D, L, k, exclude_self, self_offset,
+                                                                                      part_dist, part_idx);
+  MMSIM_CUDA_CHECK(cudaGetLastError());
+  fb2_merge_kernel<<<FB2_WAVE, FB_THREADS, 0, stream>>>(L, k, part_dist, part_idx, out);
+  MMSIM_CUDA_CHECK(cudaGetLastError());
+  fb2_advance_kernel<<<1, 1, 0, stream>>>(L.status, L.cap);
+  MMSIM_CUDA_CHECK(cudaGetLastError());
+  return MMSIM_OK;
+}
+
+int shard_fallback(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
+                   const float* flag, int cap, float* out_dist, int* out_idx, int* out_query, int* status, void* ws,
+                   size_t ws_bytes, cudaStream_t stream) {
+  MMSIM_REQUIRE(Q && G && flag && out_dist && out_idx && out_query && status && ws, MMSIM_ERR_ARG, "knn_shard_fallback: null pointer argument");
+  MMSIM_REQUIRE(nq > 0 && ng > 0 && D > 0 && D <= 4 * KATOM && k >= 1 && k <= KP && cap >= 1 && cap <= nq, MMSIM_ERR_ARG,
+                "knn_shard_fallback: bad sizes");
+  int dev = 0, num_sms = 0;
+  MMSIM_CUDA_CHECK(cudaGetDevice(&dev));
+  MMSIM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  const Plan p = make_plan(nq, ng, D, k, num_sms, false);
+  MMSIM_REQUIRE(ws_bytes >= p.total_bytes, MMSIM_ERR_WORKSPACE, "knn_shard_fallback: workspace too small (%zu < %zu)", ws_bytes,
+                p.total_bytes);
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  float* bound = reinterpret_cast<float*>(w + p.off_unc_bound);
+  fb_list_from_flags_kernel<<<1, 1024, 0, stream>>>(flag, int(nq), cap, out_query, bound, status);
+  MMSIM_CUDA_CHECK(cudaGetLastError());
+  FbLists L{status, out_query, bound, reinterpret_cast<int*>(w + p.off_fb2_list), status, cap};
+  const FbOut out{out_dist, out_idx, 1};
+  return run_fallback(p, w, Q, G, ng, int(D), k, exclude_self, self_offset, L, out, num_sms, true, stream);
+}
+
 int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
         float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream, int phases, int shard_kp,
         float* out_lb, const HostPipe* host) {
@@ -1424,9 +1442,6 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   int* split_done = reinterpret_cast<int*>(w + p.off_split_done);
   int* unc_query = reinterpret_cast<int*>(w + p.off_unc_query);
   float* unc_bound = reinterpret_cast<float*>(w + p.off_unc_bound);
-  int* fb_count = reinterpret_cast<int*>(w + p.off_fb_count);
-  float* fb_dist = reinterpret_cast<float*>(w + p.off_fb_dist);
-  int* fb_idx = reinterpret_cast<int*>(w + p.off_fb_idx);
   __half* ah = reinterpret_cast<__half*>(w + p.off_ah);
   float* apack = reinterpret_cast<float*>(w + p.off_apack);
   int* aidx = reinterpret_cast<int*>(w + p.off_aidx);
@@ -1434,6 +1449,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   const bool group = p.n_anchor != 0 && (shard_kp != 0 || p.group_default);
   int* perm = group ? reinterpret_cast<int*>(w + p.off_perm) : nullptr;
   int* ghist = reinterpret_cast<int*>(w + p.off_ghist);
+  int* sidx = reinterpret_cast<int*>(w + p.off_sidx);
   float* s32 = reinterpret_cast<float*>(w + p.off_s32);
   __half* sh = reinterpret_cast<__half*>(w + p.off_sh);
   float* spack = reinterpret_cast<float*>(w + p.off_spack);
@@ -1452,7 +1468,6 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
 
   if (phases & kPhaseRerank) {
     MMSIM_CUDA_CHECK(cudaMemsetAsync(status, 0, 8 * sizeof(int), stream));
-    MMSIM_CUDA_CHECK(cudaMemsetAsync(fb_count, 0, size_t(p.unc_cap) * 4, stream));
   }
 
   // 1. operand copies: fp16 rows, norm pack (+ per-8 / per-32 column minima), rounding-error norms
@@ -1488,6 +1503,12 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
       prep<<<unsigned((p.n_anchor + warps_per_block - 1) / warps_per_block), PREP_THREADS, 0, stream>>>(
           Q, p.n_anchor, p.n_anchor, int(D), p.Dp, 1.0f, ah, apack, nullptr, 1, nullptr, aidx);
       MMSIM_CUDA_CHECK(cudaGetLastError());
+      // the assign pass reads the per-32-column minima of the pack for its chunk-level early out.  (Round 1 left them
+      // uninitialised: the assignment then depended on whatever the workspace held, so two shards with their own
+      // workspaces could derive DIFFERENT sweep orders from the same queries and exchange misaligned pivot lists --
+      // the uncertified query of tests/test_gpu_merge.py::test_reduced_protocol_with_grouped_queries on a fresh box.)
+      pack_min_kernel<<<unsigned(a_tiles), BN, 0, stream>>>(apack);
+      MMSIM_CUDA_CHECK(cudaGetLastError());
       CUtensorMap tq0, ta;
       int rc0 = make_tmap(&tq0, qh, nq, p.Dp, BM);
       if (rc0) return rc0;
@@ -1497,7 +1518,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
       aa.gpack = apack;
       aa.nq = int(nq); aa.n_qblocks = p.n_qblocks; aa.n_tiles = a_tiles;
       aa.n_splits = 1; aa.tiles_per_split = a_tiles;
-      aa.n_sample_tiles = a_tiles; aa.sample_cols = BN;
+      aa.n_sample_tiles = a_tiles;
       aa.assign = assign;
       rc0 = launch_mode<MODE_ASSIGN, 0>(p.katoms, std::min(num_sms, p.n_qblocks), tq0, ta, aa, stream);
       if (rc0) return rc0;
@@ -1530,42 +1551,44 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     args.n_splits = p.n_splits; args.tiles_per_split = p.tiles_per_split;
     args.use_pivots = p.use_pivots;
     args.log = log; args.logcap = p.logcap; args.log_cnt = log_cnt; args.log_tau = log_tau; args.split_done = split_done;
-    args.n_sample_tiles = p.n_sample_tiles; args.sample_cols = p.sample_cols;
+    args.n_sample_tiles = p.n_sample_tiles;
     args.piv16 = piv16; args.ladder = ladder;
     if ((phases & kPhasePivot) && !p.use_pivots) {   // shard small enough to be logged whole: an empty (+inf) pivot list
       const int64_t n = int64_t(p.n_qblocks) * BM * NPIV;
       fill_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(piv16, n, kInf);
       MMSIM_CUDA_CHECK(cudaGetLastError());
     }
-    if ((phases & kPhasePivot) && p.use_pivots && !host) {
-      rc = launch_mode<MODE_PIVOT, 0>(p.katoms, p.pivot_grid, tq, tg, args, stream);
-      if (rc) return rc;
-    }
-    if ((phases & kPhasePivot) && p.use_pivots && host) {
-      // host-buffer mode: the sampled tiles come over first, as one compact block of n_sample_tiles tiles, so the pre-pass
-      // (and with it the first sweep) does not wait for the gallery.  Same rows, same windows, same pivot lists.
-      int64_t s_valid = 0;
-      for (int i = 0; i < p.n_sample_tiles; ++i) {
-        const int64_t t = (int64_t(2 * i + 1) * p.n_tiles) / (2 * p.n_sample_tiles);      // tile_of<MODE_PIVOT>
-        const int64_t rows = std::min<int64_t>(BN, ng - t * BN);                         // only the last one can be short
-        MMSIM_CUDA_CHECK(cudaMemcpyAsync(s32 + size_t(i) * BN * D, host->g_host + size_t(t) * BN * D, size_t(rows) * D * 4,
-                                         cudaMemcpyHostToDevice, ps->copy));
-        s_valid = int64_t(i) * BN + rows;
-      }
-      MMSIM_CUDA_CHECK(cudaEventRecord(ps->sample_in, ps->copy));
-      MMSIM_CUDA_CHECK(cudaStreamWaitEvent(stream, ps->sample_in, 0));
+    if ((phases & kPhasePivot) && p.use_pivots) {
+      // The pre-pass sweeps a compact block holding the sampled gallery rows (sample_row(): every sample_div-th row).
+      // Device-resident call: the operand-copy kernel gathers them from G.  Host-buffer call: they come over first, as
+      // one strided 2-D copy per segment, so the pre-pass (and with it the first sweep) does not wait for the gallery.
+      // Same rows either way, so both calls derive the same pivot lists.
       const int64_t s_pad = int64_t(p.n_sample_tiles) * BN;
       const unsigned sb = unsigned(std::min<int64_t>((s_pad + warps_per_block - 1) / warps_per_block, cap));
-      prep<<<sb, PREP_THREADS, 0, stream>>>(s32, s_valid, s_pad, int(D), p.Dp, 1.0f, sh, spack, nullptr, 1, nullptr, nullptr);
+      if (host) {
+        for (int64_t j0 = 0; j0 < p.n_sample; j0 += p.sample_seg) {
+          const int64_t j1 = std::min<int64_t>(p.n_sample, j0 + p.sample_seg);
+          MMSIM_CUDA_CHECK(cudaMemcpy2DAsync(s32 + size_t(j0) * D, size_t(D) * 4, host->g_host + size_t(sample_row(j0, p.sample_div, p.sample_seg)) * D,
+                                             size_t(p.sample_div) * D * 4, size_t(D) * 4, size_t(j1 - j0), cudaMemcpyHostToDevice,
+                                             ps->copy));
+        }
+        MMSIM_CUDA_CHECK(cudaEventRecord(ps->sample_in, ps->copy));
+        MMSIM_CUDA_CHECK(cudaStreamWaitEvent(stream, ps->sample_in, 0));
+        prep<<<sb, PREP_THREADS, 0, stream>>>(s32, p.n_sample, s_pad, int(D), p.Dp, 1.0f, sh, spack, nullptr, 1, nullptr, nullptr);
+      } else {
+        sample_index_kernel<<<unsigned((p.n_sample + 255) / 256), 256, 0, stream>>>(sidx, p.n_sample, p.sample_div, p.sample_seg);
+        MMSIM_CUDA_CHECK(cudaGetLastError());
+        prep<<<sb, PREP_THREADS, 0, stream>>>(G, p.n_sample, s_pad, int(D), p.Dp, 1.0f, sh, spack, nullptr, 1, nullptr, sidx);
+      }
       MMSIM_CUDA_CHECK(cudaGetLastError());
       pack_min_kernel<<<unsigned(p.n_sample_tiles), BN, 0, stream>>>(spack);
       MMSIM_CUDA_CHECK(cudaGetLastError());
       CUtensorMap ts;
-      rc = make_tmap(&ts, sh, s_valid, p.Dp, BN);
+      rc = make_tmap(&ts, sh, p.n_sample, p.Dp, BN);
       if (rc) return rc;
       SweepArgs sa = args;
       sa.gpack = spack;
-      sa.n_tiles = p.n_sample_tiles;           // every tile of the compact block is a sampled one
+      sa.n_tiles = p.n_sample_tiles;           // every tile of the compact block is swept whole
       rc = launch_mode<MODE_PIVOT, 0>(p.katoms, p.pivot_grid, tq, ts, sa, stream);
       if (rc) return rc;
     }
@@ -1641,27 +1664,26 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   // 3. candidate selection + exact re-rank + certificate.  delta bounds the fp32 accumulation error of
   //    key = |g|^2 - 2 q.g: (Dp + 8) roundings of relative size 2^-24, on terms bounded by (|q|^2 + |g|^2), 4x safety.
   if (phases & kPhaseRerank) {
-    const float delta_coeff = 4.0f * float(p.Dp + 8) * 5.9604645e-8f;
+    const float delta_coeff = delta_coeff_of(p.Dp);
     const int blocks = int((nq + RR_WARPS - 1) / RR_WARPS);
     const size_t smem = size_t(RR_WARPS) * (size_t(D) + 2 * KP + RR_STAGE) * 4;
     knn_rerank_kernel<<<blocks, RR_WARPS * 32, smem, stream>>>(Q, G, int(nq), ng, int(D), log, p.logcap, log_cnt, log_tau,
                                                                p.n_splits, qnorm, qerr, gstats, delta_coeff, shard_kp ? shard_kp : k,
                                                                shard_kp ? shard_kp : KP, exclude_self, self_offset, out_dist,
                                                                out_idx, shard_kp ? out_lb : nullptr, status, unc_query,
-                                                               unc_bound, p.unc_cap, perm);
+                                                               unc_bound, p.unc_cap, perm, env_int("MMSIM_KNN_FORCE_FALLBACK"));
     MMSIM_CUDA_CHECK(cudaGetLastError());
   }
 
-  // 4. exact fallback for uncertified queries (no-op when status[0] == 0; the count lives on the device)
-  if ((phases & kPhaseFallback) && !shard_kp) {
-    dim3 grid(64, 16);
-    knn_fallback_collect_kernel<<<grid, 256, size_t(D) * 4, stream>>>(Q, G, ng, int(D), exclude_self, self_offset, status,
-                                                                      unc_query, unc_bound, p.unc_cap, fb_count, fb_dist,
-                                                                      fb_idx, status);
-    MMSIM_CUDA_CHECK(cudaGetLastError());
-    knn_fallback_select_kernel<<<32, 256, 0, stream>>>(status, unc_query, p.unc_cap, fb_count, fb_dist, fb_idx, k, out_dist,
-                                                       out_idx);
-    MMSIM_CUDA_CHECK(cudaGetLastError());
+  // 4. exact fallback for the uncertified queries (knn_fallback.cuh; the count lives on the device: when it is zero the
+  //    kernels below find nothing to do)
+  if (((phases & kPhaseFallback) && !shard_kp) || (phases & kPhaseFinish)) {
+    if ((phases & kPhaseFallback) && !(phases & kPhaseRerank))      // phase-by-phase timing: restart the tier-2 queue
+      MMSIM_CUDA_CHECK(cudaMemsetAsync(status + 1, 0, 2 * sizeof(int), stream));
+    FbLists L{status, unc_query, unc_bound, reinterpret_cast<int*>(w + p.off_fb2_list), status, p.unc_cap};
+    const FbOut out{out_dist, out_idx, 0};
+    rc = run_fallback(p, w, Q, G, ng, int(D), k, exclude_self, self_offset, L, out, num_sms, (phases & kPhaseFallback) != 0, stream);
+    if (rc) return rc;
   }
   return MMSIM_OK;
 }

@@ -850,13 +850,29 @@ static const void* kernel_for(int shape, int kind) {
 // The dynamic shared-memory limit is an attribute of the KERNEL, while the amount a launch needs depends on (N, D): the
 // attribute is only ever raised (a later, smaller problem must not lower it under a layout that is already cached --
 // that made a cached 256 x 128 launch fail with "invalid argument" after a 64 x 16 one in the same process).
+// It is also an attribute PER DEVICE (the current one when it is set), and a process may drive several GPUs: everything
+// cached here -- the raised limits, the occupancy-derived tile shape, the SM count -- is keyed by the device ordinal
+// (round-1 advisor finding: the second GPU of a process never had its limit raised).  Slot kMaxDev = "no device"
+// (workspace-size queries on a CPU box).
+constexpr int kMaxDev = 64;
+static int current_dev_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return kMaxDev;
+  }
+  return dev >= 0 && dev < kMaxDev ? dev : kMaxDev;
+}
+
 static void raise_smem_attr(int shape, int kind, size_t bytes) {
   static std::mutex mu;
-  static size_t have[3][2] = {};
+  static size_t have[kMaxDev + 1][3][2] = {};
+  const int slot = current_dev_slot();
   std::lock_guard<std::mutex> lock(mu);
-  if (bytes > have[shape][kind] &&
+  if (slot == kMaxDev) return;
+  if (bytes > have[slot][shape][kind] &&
       cudaFuncSetAttribute(kernel_for(shape, kind), cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)) == cudaSuccess)
-    have[shape][kind] = bytes;
+    have[slot][shape][kind] = bytes;
 }
 
 // Pick the smallest tile whose grid fits co-resident on the device (a cooperative launch requires it).
@@ -865,11 +881,13 @@ static int pick_shape(int64_t N, int64_t D) {
     const int s = atoi(e);
     if (s >= 0 && s <= 2) return s;
   }
-  static int num_sms = 0;
-  if (!num_sms) {
+  int num_sms = 0;
+  {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      cudaGetLastError();
       num_sms = 0;
+    }
   }
   for (int s = 0; s < 3; ++s) {
     const int TI = 8 * kShapes[s][0], TJ = 16 * kShapes[s][1];
@@ -922,7 +940,7 @@ static Layout compute_layout(int64_t N, int64_t D) {
 Layout make_layout(int64_t N, int64_t D) {
   static std::mutex mu;
   static std::unordered_map<int64_t, Layout> cache;
-  const int64_t key = (N << 20) | D;
+  const int64_t key = (int64_t(current_dev_slot()) << 40) | (N << 20) | D;
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
@@ -965,10 +983,11 @@ int run(int kind, const float* E, const float* pids, int64_t N, int64_t D, int s
   p.NBI = L.NBI; p.NBJ = L.NBJ; p.Npad = L.Npad;
 
   if (kind == 0 && bh_rows_ok(N, D)) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDev + 1] = {};
+    const int slot = current_dev_slot();
+    if (!attr_set[slot]) {
       MMSIM_CUDA_CHECK(cudaFuncSetAttribute(bh_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
+      attr_set[slot] = true;
     }
     if (dE) MMSIM_CUDA_CHECK(cudaMemsetAsync(dE, 0, size_t(N) * D * sizeof(float), stream));
     bh_rows_kernel<<<unsigned((N + BR_R - 1) / BR_R), BR_THREADS, bh_rows_smem(N, D), stream>>>(p);

@@ -21,11 +21,13 @@ __global__ void __launch_bounds__(WARPS * 32)
 knn_merge_kernel(const float* __restrict__ dist_parts, const int* __restrict__ idx_parts,
                  int64_t part_stride, const int64_t* __restrict__ idx_base, int parts, int64_t nq, int k_in, int k, int P,
                  const float* __restrict__ lb_parts, int64_t lb_stride, float* __restrict__ out_dist,
-                 int64_t* __restrict__ out_idx, int* __restrict__ status) {
+                 int64_t* __restrict__ out_idx, int* __restrict__ status, float* __restrict__ out_flag,
+                 const int* __restrict__ count_ptr, const int* __restrict__ row_map) {
   extern __shared__ __align__(8) unsigned char msm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t qi = int64_t(blockIdx.x) * WARPS + warp;
-  if (qi >= nq) return;
+  if (qi >= nq || (count_ptr && qi >= *count_ptr)) return;
+  const int64_t qo = row_map ? row_map[qi] : qi;      // output row (patch mode: the query a compact slot belongs to)
   float* sk = reinterpret_cast<float*>(msm) + size_t(warp) * 2 * P;   // [P] distance
   int* sv = reinterpret_cast<int*>(sk + P);                           // [P] slot = part * k_in + r
   const int total = parts * k_in;
@@ -100,8 +102,8 @@ knn_merge_kernel(const float* __restrict__ dist_parts, const int* __restrict__ i
   }
   for (int r = lane; r < k; r += 32) {
     const bool ok = r < S && sv[r] != 0x7fffffff;
-    out_dist[qi * k + r] = ok ? sk[r] : kInf;
-    out_idx[qi * k + r] = ok ? gidx(sv[r]) : -1;
+    out_dist[qo * k + r] = ok ? sk[r] : kInf;
+    out_idx[qo * k + r] = ok ? gidx(sv[r]) : -1;
   }
   // global certificate of the reduced-candidate protocol: every row a shard did NOT re-rank lies at distance >= that
   // shard's lower bound, so the merged top-k is exact iff its k-th distance is below every shard's bound
@@ -109,13 +111,17 @@ knn_merge_kernel(const float* __restrict__ dist_parts, const int* __restrict__ i
     float lb = kInf;
     for (int p = 0; p < parts; ++p) lb = fminf(lb, lb_parts[size_t(p) * lb_stride + qi]);
     const float dk = (k - 1 < S) ? sk[k - 1] : kInf;
-    if (!(dk < lb)) atomicAdd(&status[0], 1);
+    const bool unc = !(dk < lb);
+    if (unc) atomicAdd(&status[0], 1);
+    // per-query flag for the per-query exact fallback: the merged k-th distance (an upper bound of the true one, +inf
+    // when fewer than k candidates were merged) of an uncertified query, -1 for a certified one
+    if (out_flag) out_flag[qi] = unc ? (dk == dk ? dk : kInf) : -1.f;
   }
 }
 
 int run(const float* dist_parts, const int* idx_parts, int64_t part_stride, const int64_t* idx_base, int parts, int64_t nq,
         int k_in, int k, const float* lb_parts, int64_t lb_stride, float* out_dist, int64_t* out_idx, int* status,
-        cudaStream_t s) {
+        cudaStream_t s, float* out_flag, const int* count_ptr, const int* row_map) {
   MMSIM_REQUIRE(dist_parts && idx_parts && idx_base && out_dist && out_idx, MMSIM_ERR_ARG, "knn_merge: null pointer argument");
   MMSIM_REQUIRE(parts >= 1 && k >= 1 && k_in >= 1 && nq >= 0 && part_stride >= nq * k_in && (!lb_parts || status), MMSIM_ERR_ARG,
                 "knn_merge: bad sizes parts=%d nq=%lld k=%d", parts, (long long)nq, k);
@@ -126,7 +132,8 @@ int run(const float* dist_parts, const int* idx_parts, int64_t part_stride, cons
   const size_t smem = size_t(WARPS) * P * 8;
   MMSIM_CUDA_CHECK(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   knn_merge_kernel<<<unsigned((nq + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(dist_parts, idx_parts, part_stride, idx_base, parts, nq, k_in, k, P,
-                                                                              lb_parts, lb_stride, out_dist, out_idx, status);
+                                                                              lb_parts, lb_stride, out_dist, out_idx, status, out_flag,
+                                                                              count_ptr, row_map);
   MMSIM_CUDA_CHECK(cudaGetLastError());
   return MMSIM_OK;
 }

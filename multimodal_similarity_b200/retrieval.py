@@ -53,7 +53,22 @@ def knn_raw(q: torch.Tensor, g: torch.Tensor, k: int, exclude_self: bool = False
                                       dist.data_ptr(), idx.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(),
                                       stream_handle(dev), int(phases))
     _lib.check(rc, "mmsim_knn_f32")
+    status._mmsim_finish = _finisher(q, g, k, exclude_self, self_offset, dist, idx, status, ws)
     return dist, idx, status
+
+
+def _finisher(q, g, k, exclude_self, self_offset, dist, idx, status, ws):
+    """One more wave of the streaming exact scan for the queries a call left queued (``mmsim_knn_finish_f32``); q / g are
+    the device arrays of that call, whose workspace still holds the queue."""
+    def run():
+        lib = _lib.load()
+        dev = q.device
+        with torch.cuda.device(dev):
+            rc = lib.mmsim_knn_finish_f32(q.data_ptr(), q.shape[0], g.data_ptr(), g.shape[0], q.shape[1], k, int(bool(exclude_self)),
+                                          int(self_offset), dist.data_ptr(), idx.data_ptr(), status.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), stream_handle(dev))
+        _lib.check(rc, "mmsim_knn_finish_f32")
+    return run
 
 
 def knn_host(q_host: torch.Tensor, g_host: torch.Tensor, k: int, exclude_self: bool = False, self_offset: int = 0, *,
@@ -82,8 +97,8 @@ def knn_host(q_host: torch.Tensor, g_host: torch.Tensor, k: int, exclude_self: b
             or q_stage.dtype != torch.float32 or g_stage.dtype != torch.float32 or q_stage.device != dev or g_stage.device != dev:
         raise ValueError("stage must be contiguous float32 CUDA tensors shaped like q_host and g_host")
     nbytes = ctypes.c_size_t()
-    _lib.check(lib.mmsim_knn_workspace_bytes(nq, ng, d, k, ctypes.byref(nbytes)), "mmsim_knn_workspace_bytes")
-    ws = workspace("knn", nbytes.value, dev)
+    _lib.check(lib.mmsim_knn_host_workspace_bytes(nq, ng, d, k, ctypes.byref(nbytes)), "mmsim_knn_host_workspace_bytes")
+    ws = workspace("knn_host", nbytes.value, dev)
     if out is None:
         dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
         idx = torch.empty((nq, k), dtype=torch.int32, device=dev)
@@ -95,16 +110,25 @@ def knn_host(q_host: torch.Tensor, g_host: torch.Tensor, k: int, exclude_self: b
                                     dist.data_ptr(), idx.data_ptr(), status.data_ptr(), q_stage.data_ptr(), g_stage.data_ptr(),
                                     ws.data_ptr(), ws.numel(), stream_handle(dev))
     _lib.check(rc, "mmsim_knn_host_f32")
+    status._mmsim_finish = _finisher(q_stage, g_stage, k, exclude_self, self_offset, dist, idx, status, ws)
     return dist, idx, status
 
 
 def check_status(status: torch.Tensor) -> int:
-    """Synchronising check of a knn status word; returns the number of queries that took the exact fallback."""
+    """Synchronising check of a knn status word; returns the number of queries that took the exact fallback.
+    status[1] > status[2]: queries are still queued for the streaming exact scan (the call itself runs one wave of 128) --
+    further waves are launched here until none are left, so the result is exact on return whatever the input."""
     s = status.tolist()
-    if s[1] or s[2]:
-        raise _lib.MmsimError(
-            f"knn: exact fallback could not finish (uncertified={s[0]}, overflow={s[1]}, too_many={s[2]}); the input has "
-            "massive exact ties or values outside the fp16 range")
+    while s[2] < s[1]:
+        finish = getattr(status, "_mmsim_finish", None)
+        if finish is None:
+            raise _lib.MmsimError(f"knn: {s[1] - s[2]} queries are still queued for the exact scan and this status word does "
+                                  "not come from knn_raw / knn_host (call mmsim_knn_finish_f32 with the original arguments)")
+        before = s[2]
+        finish()
+        s = status.tolist()
+        if s[2] <= before:
+            raise _lib.MmsimError(f"knn: the exact scan made no progress (status={s})")
     return s[0]
 
 
@@ -161,12 +185,35 @@ def retrieve_host(queries, gallery, k, *, exclude_self=False, self_offset=0, che
     return dist.numpy().copy(), idx.numpy().astype(np.int64)
 
 
-def retrieve_one(query, database, query_label=None, labels=None, normalize=False, k=None):
-    """The reference's single-query call (src/utils.py:55-81) restricted to the first k neighbours
-    (k defaults to min(N, 112)): returns (dist[idx], idx, ap@k) with ap@k the truncated AP
-    ``sum_{r<=k} P(r) rel(r) / min(k, #positives)`` (the full-ranking AP lives in evaluate())."""
+def retrieve_one(query, database, query_label=None, labels=None, normalize=False):
+    """The reference's single-query call with the reference's return value (src/utils.py:55-81): ``dist`` [N] float32 =
+    ``np.linalg.norm(query - database, axis=1)`` bit for bit (unsorted), ``idx`` [N] int64 = its argsort (ties by index;
+    the reference's introsort leaves tie order unspecified) and ``ap`` = sklearn's average precision of
+    ``labels == query_label`` scored by ``max(dist) - dist`` (None without labels, like the reference's ``ap = None``
+    initialisation would suggest; the reference itself requires labels).  The distances come from the exact kernel in
+    NumPy's summation order (csrc/sqdist.cu); the sort is a stable device sort.  For the k nearest rows of MANY queries
+    use ``retrieve`` -- this per-query form exists for call-site compatibility."""
     if normalize:
         raise NotImplementedError("retrieve_one(normalize=True) is broken in the reference (undefined name, src/utils.py:69)")
+    from .distance import pairwise_distance
+    as_numpy = is_numpy_like(query) and is_numpy_like(database)
+    q = to_cuda_f32(query).reshape(1, -1)
+    g = to_cuda_f32(database, q.device)
+    dist = torch.sqrt(pairwise_distance(q, g)[0])            # IEEE sqrt of the exactly summed squares == np.linalg.norm
+    idx = torch.sort(dist, stable=True).indices               # ascending distance, ties by index
+    ap = None
+    if labels is not None:
+        lab = np.squeeze(labels.cpu().numpy() if torch.is_tensor(labels) else np.asarray(labels))
+        d_np = dist.cpu().numpy()
+        ap = average_precision(lab == query_label, d_np.max() - d_np)       # :76-79
+    if as_numpy:
+        return dist.cpu().numpy(), idx.cpu().numpy(), ap
+    return dist, idx, ap
+
+
+def retrieve_one_topk(query, database, query_label=None, labels=None, k=None):
+    """Top-k form of ``retrieve_one`` (an extension, not the reference's return value): (dist[idx[:k]], idx[:k], AP@k)
+    with AP@k = ``sum_{r<=k} P(r) rel(r) / min(k, #positives)``; k defaults to min(N, 112)."""
     n = database.shape[0]
     k = min(n, _lib.KNN_MAX_K) if k is None else k
     q = np.asarray(query, dtype=np.float32).reshape(1, -1) if is_numpy_like(query) else query.reshape(1, -1)
@@ -245,7 +292,8 @@ def _loo_records(embeddings, labels, normalize, standardize, alpha, aligned, wan
     if normalize:      # src/utils.py:104-105,154-155 (the reference normalises the caller's array in place)
         emb = emb / torch.linalg.vector_norm(emb, dim=1, keepdim=True)
     if standardize:    # :106-109,156-159 (float32 statistics, like NumPy on a float32 array)
-        emb = (emb - emb.mean(dim=0)) / emb.std(dim=0, unbiased=False)
+        # the reference divides by (std + np.finfo(float).tiny) (:108,158): a constant column gives 0, not 0/0
+        emb = (emb - emb.mean(dim=0)) / (emb.std(dim=0, unbiased=False) + float(np.finfo(float).tiny))
     emb = emb.contiguous()
     n, d = emb.shape
     dev = emb.device

@@ -12,9 +12,12 @@ single-GPU result:
                   only ``kp`` << 128 candidates and reports a lower bound for everything it did not re-rank; (3) the
                   candidate lists are exchanged BY QUERY SLICE (one all-to-all: rank r receives every shard's lists for
                   queries [r S, (r+1) S)), each rank merges and certifies its slice only, and one all-gather hands every
-                  rank the merged top-k of all queries -- the merge no longer repeats on every rank.  If any query is
-                  uncertified (adversarial row order, massive ties) the call falls back to ``exact-shards`` -- so the
-                  result is always exact.
+                  rank the merged top-k of all queries -- the merge no longer repeats on every rank.  (4) Queries the
+                  global certificate could not prove (adversarial row order, massive ties) are repaired ONE BY ONE:
+                  every rank computes the exact top-k inside its shard for exactly those queries
+                  (``mmsim_knn_shard_fallback_f32``: a tensor-core re-sweep bounded by the merged k-th distance), the
+                  compact lists are all-gathered and merged into those rows.  Only when more than ``FALLBACK_CAP``
+                  queries are uncertified does the whole call repeat as ``exact-shards`` -- the result is always exact.
 
 The training-loss kernels are not sharded (replicas only).
 """
@@ -31,6 +34,7 @@ from ._util import is_numpy_like, stream_handle, to_cuda_f32
 from .retrieval import check_status, knn_raw
 
 PH_PREP, PH_TENSOR, PH_RERANK, PH_FALLBACK, PH_PIVOT, PH_LADDER = 1, 2, 4, 8, 16, 32
+FALLBACK_CAP = 1024      # uncertified queries repaired one by one per call; beyond that the call repeats as exact-shards
 
 
 def shard_bounds(n_rows: int, world: int, rank: int):
@@ -73,6 +77,8 @@ class ReducedShard:
     def _ws(self, nq, d, k):
         lib = _lib.load()
         n = ctypes.c_size_t()
+        if self.shard.shape[0] == 0:       # an empty shard (more ranks than ceil-sized blocks) has no workspace and no lists
+            return None
         _lib.check(lib.mmsim_knn_workspace_bytes(nq, self.shard.shape[0], d, k, ctypes.byref(n)), "mmsim_knn_workspace_bytes")
         if self.ws is None or self.ws.numel() < n.value:
             self.ws = torch.empty(n.value, dtype=torch.uint8, device=self.shard.device)
@@ -95,7 +101,7 @@ class ReducedShard:
     def stage1(self, q, k, kp, packed):
         """Operand copies + pivot pre-pass; returns this shard's pivot lists [rows, 16] (a view into the workspace)."""
         piv = self._ws(q.shape[0], q.shape[1], k)
-        if self.shard.shape[0] == 0:
+        if piv is None:
             return None
         self._call(q, k, kp, False, 0, PH_PREP | PH_PIVOT, self._views(packed, q.shape[0], kp))
         return piv
@@ -108,6 +114,27 @@ class ReducedShard:
             d_.fill_(float("inf")); i_.fill_(-1); lb_.fill_(float("inf"))
             return
         self._call(q, k, kp, exclude_self, self_offset, PH_LADDER | PH_TENSOR | PH_RERANK, (d_, i_, lb_, st_))
+
+    def fallback(self, q, k, exclude_self, self_offset, flag, cap):
+        """Exact top-k inside this shard for the queries with flag >= 0 (``mmsim_knn_shard_fallback_f32``) -> one int32
+        buffer | distance bits cap x k | shard-local indices cap x k | query of each slot cap | status 8 |."""
+        dev = q.device
+        buf = torch.empty(2 * cap * k + cap + 8, dtype=torch.int32, device=dev)
+        d_ = buf[:cap * k]
+        i_ = buf[cap * k:2 * cap * k]
+        qq = buf[2 * cap * k:2 * cap * k + cap]
+        st = buf[2 * cap * k + cap:]
+        if self.shard.shape[0] == 0:
+            d_.view(torch.float32).fill_(float("inf")); i_.fill_(-1); qq.zero_(); st.zero_()
+            return buf
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            rc = lib.mmsim_knn_shard_fallback_f32(q.data_ptr(), q.shape[0], self.shard.data_ptr(), self.shard.shape[0], q.shape[1], k,
+                                                  int(bool(exclude_self)), int(self_offset - self.lo), flag.data_ptr(), cap,
+                                                  d_.data_ptr(), i_.data_ptr(), qq.data_ptr(), st.data_ptr(), self.ws.data_ptr(),
+                                                  self.ws.numel(), stream_handle(dev))
+        _lib.check(rc, "mmsim_knn_shard_fallback_f32")
+        return buf
 
     @staticmethod
     def packed_elems(nq, kp):
@@ -141,13 +168,14 @@ def merge_certified(gathered: torch.Tensor, bases: torch.Tensor, nq: int, kp: in
     out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
     status = torch.zeros(8, dtype=torch.int32, device=dev)
+    flag = torch.empty(nq, dtype=torch.float32, device=dev)
     base = gathered.data_ptr()
     with torch.cuda.device(dev):
         rc = lib.mmsim_knn_merge_certified(base, base + nq * kp * 4, stride, bases.data_ptr(), parts, nq, kp, k,
                                            base + 2 * nq * kp * 4, stride, out_d.data_ptr(), out_i.data_ptr(),
-                                           status.data_ptr(), stream_handle(dev))
+                                           status.data_ptr(), flag.data_ptr(), stream_handle(dev))
     _lib.check(rc, "mmsim_knn_merge_certified")
-    return out_d, out_i, status
+    return out_d, out_i, status, flag
 
 
 def slice_rows(nq: int, world: int) -> int:
@@ -175,24 +203,28 @@ def pack_slices(packed: torch.Tensor, nq: int, kp: int, world: int) -> torch.Ten
 
 def merge_certified_slice(recv: torch.Tensor, bases: torch.Tensor, n_rows: int, S: int, kp: int, k: int):
     """[parts, S * (2 kp + 1)] lists of ONE query slice (what the all-to-all delivers) -> merged
-    | global indices S x k as int64 (2 x int32; first, so they are 8-byte aligned) | distance bits S x k | status 8 |
+    | global indices S x k as int64 (2 x int32; first, so they are 8-byte aligned) | distance bits S x k |
+    | flag S (float bits: merged k-th distance of an uncertified query, -1 for a certified one) | status 8 |
     as one int32 buffer."""
     lib = _lib.load()
     dev = recv.device
     parts, stride = recv.shape[0], recv.stride(0)
-    res = torch.zeros(S * k * 3 + 8, dtype=torch.int32, device=dev)
+    res = torch.zeros(S * k * 3 + S + 8, dtype=torch.int32, device=dev)
+    res[S * k * 3:S * k * 3 + S] = -1082130432     # bits of -1.0f: rows past the slice's end are "certified"
     base = recv.data_ptr()
     if n_rows > 0:
         with torch.cuda.device(dev):
             rc = lib.mmsim_knn_merge_certified(base, base + S * kp * 4, stride, bases.data_ptr(), parts, n_rows, kp, k,
                                                base + 2 * S * kp * 4, stride, res.data_ptr() + S * k * 8, res.data_ptr(),
-                                               res.data_ptr() + S * k * 12, stream_handle(dev))
+                                               res.data_ptr() + (S * k * 3 + S) * 4, res.data_ptr() + S * k * 12,
+                                               stream_handle(dev))
         _lib.check(rc, "mmsim_knn_merge_certified")
     return res
 
 
 def unpack_merged(allres: torch.Tensor, nq: int, S: int, k: int):
-    """[world, S * 3 k + 8] merged slices -> (dist [nq, k] f32, idx [nq, k] i64, uncertified count tensor)."""
+    """[world, S * 3 k + S + 8] merged slices -> (dist [nq, k] f32, idx [nq, k] i64, uncertified count tensor,
+    flag [nq] f32)."""
     world = allres.shape[0]
     # explicit copies into fresh buffers: the int64 view needs 8-byte aligned rows, and a slice that happens to be a view
     # of `allres` (odd row pitch) would not have them
@@ -202,7 +234,25 @@ def unpack_merged(allres: torch.Tensor, nq: int, S: int, k: int):
     d = torch.empty((nq, k), dtype=torch.int32, device=allres.device)
     d.copy_(allres[:, S * k * 2:S * k * 3].reshape(world * S, k)[:nq])
     d = d.view(torch.float32)
-    return d, i, allres[:, S * k * 3].sum()
+    flag = allres[:, S * k * 3:S * k * 3 + S].reshape(world * S)[:nq].contiguous().view(torch.float32)
+    return d, i, allres[:, S * k * 3 + S].sum(), flag
+
+
+def patch_rows(out_d, out_i, allfb: torch.Tensor, bases: torch.Tensor, cap: int, k: int):
+    """[world, 2 cap k + cap + 8] gathered fallback buffers -> rows of (out_d, out_i) rewritten with the merge of the shards'
+    exact lists (``mmsim_knn_merge_patch``).  Slot -> query map and count are rank 0's (identical on every rank whose shard
+    is not empty; an empty shard contributes +inf lists)."""
+    lib = _lib.load()
+    dev = out_d.device
+    world, stride = allfb.shape[0], allfb.stride(0)
+    base = allfb.data_ptr()
+    src = 0                                           # rank 0's shard is never empty (shard_bounds)
+    row_map = base + (src * stride + 2 * cap * k) * 4
+    count = base + (src * stride + 2 * cap * k + cap) * 4
+    with torch.cuda.device(dev):
+        rc = lib.mmsim_knn_merge_patch(base, base + cap * k * 4, stride, bases.data_ptr(), world, cap, k, count, row_map,
+                                       out_d.data_ptr(), out_i.data_ptr(), stream_handle(dev))
+    _lib.check(rc, "mmsim_knn_merge_patch")
 
 
 class ShardedGallery:
@@ -237,6 +287,8 @@ class ShardedGallery:
         self.dim = int(gallery.shape[1])
         self._reduced = None
         self.last_protocol = None
+        self.last_uncertified = None      # reduced protocol: device scalar, queries the global certificate did not prove
+        self.last_repaired = 0            # ... and how many of them the last call repaired one by one
 
     # -- steps of the exact-shards protocol; tests on CPU boxes replace them to exercise the sharding logic under gloo
     def _to_device(self, x, device):
@@ -263,6 +315,19 @@ class ShardedGallery:
 
     def _retrieve_exact_shards(self, q, k, exclude_self, self_offset, check):
         packed, status = self._local(q, k, exclude_self, self_offset)
+        if check and self.world > 1:
+            # finish queued exact scans BEFORE the collective, and agree on the outcome: either every rank raises or none
+            err = torch.zeros(1, dtype=torch.int32, device=packed.device)
+            try:
+                if status is not None:
+                    check_status(status)
+            except _lib.MmsimError:
+                err += 1
+            dist.all_reduce(err, op=dist.ReduceOp.MAX, group=self.group)
+            if int(err):
+                raise _lib.MmsimError("knn: the exact fallback failed on at least one gallery shard")
+        elif check and status is not None:
+            check_status(status)
         if self.world > 1:
             # dim-0 concatenation layout (accepted by both NCCL and gloo), viewed as [world, 2, Q, k] afterwards
             flat = torch.empty((self.world * 2,) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
@@ -270,13 +335,11 @@ class ShardedGallery:
             gathered = flat.view((self.world,) + tuple(packed.shape))
         else:
             gathered = packed.unsqueeze(0)
-        out = self._merge(gathered, self._bases(packed.device), k)
-        if check and status is not None:
-            check_status(status)
-        return out
+        return self._merge(gathered, self._bases(packed.device), k)
 
-    def _retrieve_reduced(self, q, k, exclude_self, self_offset):
-        """Returns (dist, idx) or None when a query could not be certified (caller falls back to exact-shards)."""
+    def _retrieve_reduced(self, q, k, exclude_self, self_offset, check):
+        """Returns (dist, idx), or None when the call has to be repeated as exact-shards (more than FALLBACK_CAP
+        uncertified queries, or a shard's streaming scan still has queries queued)."""
         nq = q.shape[0]
         kp = reduced_kp(self.world, k)
         if self._reduced is None:
@@ -298,12 +361,28 @@ class ShardedGallery:
         recv = torch.empty_like(send)
         dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
         mine = max(0, min(S, nq - self.rank * S))
-        res = merge_certified_slice(recv, self._bases(dev), mine, S, kp, k)
+        bases = self._bases(dev)
+        res = merge_certified_slice(recv, bases, mine, S, kp, k)
         allres = torch.empty((self.world, res.numel()), dtype=torch.int32, device=dev)
         dist.all_gather_into_tensor(allres.view(-1), res, group=self.group)
-        out_d, out_i, uncertified = unpack_merged(allres, nq, S, k)
-        if int(uncertified) != 0:        # identical on every rank (it is part of the gathered buffer)
+        out_d, out_i, uncertified, flag = unpack_merged(allres, nq, S, k)
+        self.last_uncertified = uncertified           # device scalar, identical on every rank (part of the gathered buffer)
+        if not check:
+            return out_d, out_i                       # the caller inspects last_uncertified (bench.py does, after timing)
+        n_unc = int(uncertified)
+        if n_unc == 0:
+            return out_d, out_i
+        if n_unc > FALLBACK_CAP:
             return None
+        # per-query repair: exact top-k of the uncertified queries inside every shard, all-gather, merge into those rows
+        fb = rs.fallback(q, k, exclude_self, self_offset, flag, FALLBACK_CAP)
+        allfb = torch.empty((self.world, fb.numel()), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allfb.view(-1), fb, group=self.group)
+        st = allfb[:, 2 * FALLBACK_CAP * k + FALLBACK_CAP:].cpu()
+        if bool((st[:, 1] > st[:, 2]).any()):         # a shard's streaming scan has queries left: identical view on every rank
+            return None
+        patch_rows(out_d, out_i, allfb, bases, FALLBACK_CAP, k)
+        self.last_repaired = n_unc
         return out_d, out_i
 
     def retrieve(self, queries, k, *, exclude_self=False, self_offset=0, check=True, protocol="auto"):
@@ -316,8 +395,9 @@ class ShardedGallery:
         k = int(k)
         out = None
         self.last_protocol = "exact-shards"
+        self.last_repaired = 0
         if protocol != "exact-shards" and self.world > 1 and q.is_cuda and reduced_kp(self.world, k) < 128:
-            out = self._retrieve_reduced(q, k, exclude_self, self_offset)
+            out = self._retrieve_reduced(q, k, exclude_self, self_offset, check)
             if out is not None:
                 self.last_protocol = "reduced"
         if out is None:

@@ -116,8 +116,9 @@ def test_slice_packing_roundtrip():
             ll = send[r, 2 * S * kp:].view(torch.float32)
             for n_, q in enumerate(rows):
                 assert torch.equal(dd[n_], d_[q]) and torch.equal(ii[n_], i_[q]) and ll[n_] == lb_[q]
-        # merged slices as merge_certified_slice lays them out: | idx int64 S x k | dist S x k | status 8 |
-        allres = torch.zeros((world, S * k * 3 + 8), dtype=torch.int32)
+        # merged slices as merge_certified_slice lays them out: | idx int64 S x k | dist S x k | flag S | status 8 |
+        allres = torch.zeros((world, S * k * 3 + S + 8), dtype=torch.int32)
+        want_f = torch.where(torch.arange(nq) % 3 == 0, torch.arange(nq, dtype=torch.float32) + 0.5, torch.tensor(-1.0))
         want_d = torch.arange(nq * k, dtype=torch.float32).view(nq, k)
         want_i = (torch.arange(nq * k, dtype=torch.int64).view(nq, k) << 33) + 5          # needs all 64 bits
         for r in range(world):
@@ -125,9 +126,11 @@ def test_slice_packing_roundtrip():
             if hi > lo:
                 allres[r, :(hi - lo) * k * 2] = want_i[lo:hi].contiguous().view(torch.int32).reshape(-1)
                 allres[r, S * k * 2:S * k * 2 + (hi - lo) * k] = want_d[lo:hi].contiguous().view(torch.int32).reshape(-1)
-            allres[r, S * k * 3] = r                                                        # uncertified count of the slice
-        got_d, got_i, unc = unpack_merged(allres, nq, S, k)
+                allres[r, S * k * 3:S * k * 3 + (hi - lo)] = want_f[lo:hi].contiguous().view(torch.int32)
+            allres[r, S * k * 3 + S] = r                                                    # uncertified count of the slice
+        got_d, got_i, unc, got_f = unpack_merged(allres, nq, S, k)
         assert torch.equal(got_d, want_d) and torch.equal(got_i, want_i) and int(unc) == sum(range(world))
+        assert torch.equal(got_f, want_f)
 
 
 def test_presharded_rows_must_follow_shard_bounds():
