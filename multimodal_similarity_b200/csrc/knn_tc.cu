@@ -1388,7 +1388,7 @@ int shard_fallback(const float* Q, int64_t nq, const float* G, int64_t ng, int64
                    const float* flag, int cap, float* out_dist, int* out_idx, int* out_query, int* status, void* ws,
                    size_t ws_bytes, cudaStream_t stream) {
   MMSIM_REQUIRE(Q && G && flag && out_dist && out_idx && out_query && status && ws, MMSIM_ERR_ARG, "knn_shard_fallback: null pointer argument");
-  MMSIM_REQUIRE(nq > 0 && ng > 0 && D > 0 && D <= 4 * KATOM && k >= 1 && k <= KP && cap >= 1 && cap <= nq, MMSIM_ERR_ARG,
+  MMSIM_REQUIRE(nq > 0 && ng > 0 && D > 0 && D <= 4 * KATOM && k >= 1 && k <= KP && cap >= 1, MMSIM_ERR_ARG,
                 "knn_shard_fallback: bad sizes");
   int dev = 0, num_sms = 0;
   MMSIM_CUDA_CHECK(cudaGetDevice(&dev));
