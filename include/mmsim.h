@@ -49,6 +49,9 @@ typedef struct CUstream_st* mmsim_stream_t; /* == cudaStream_t */
 
 MMSIM_API int mmsim_version(void);
 MMSIM_API const char* mmsim_last_error(void);
+/* kernels this library has launched in the calling process so far (reset != 0: return the count and restart it at zero);
+ * what bench.py reports as gpu_launches */
+MMSIM_API int64_t mmsim_kernel_launches(int reset);
 
 /* out[i*ld + j] = dist(A[i,:], B[j,:]) -- replaces utils.cdist(utils.all_diffs(a, b), metric)
  * (src/utils.py:313-341; the TF twins :302-311,343-360 compute the same values).  fp32, evaluated in NumPy's

@@ -17,6 +17,7 @@ EVAL_SMEM_MAX_N = 16385     # largest N whose leave-one-out ranking fits the one
 SIGNATURES = {
     "mmsim_version": (c_int, []),
     "mmsim_last_error": (c_char_p, []),
+    "mmsim_kernel_launches": (c_int64, [c_int]),
     "mmsim_sqdist_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "mmsim_loss_workspace_bytes": (c_int, [c_int64, c_int64, POINTER(c_size_t)]),
     "mmsim_loss_f32": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int,

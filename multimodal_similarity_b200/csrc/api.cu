@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -25,6 +26,11 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static std::atomic<long long> g_launches{0};
+cudaError_t launched() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
 }  // namespace mmsim
 
 using namespace mmsim;
@@ -34,6 +40,10 @@ extern "C" {
 MMSIM_API int mmsim_version(void) { return 100; }  // 0.1.0
 
 MMSIM_API const char* mmsim_last_error(void) { return g_err; }
+
+MMSIM_API int64_t mmsim_kernel_launches(int reset) {
+  return reset ? g_launches.exchange(0) : g_launches.load();
+}
 
 MMSIM_API int mmsim_sqdist_f32(const float* A, int64_t M, const float* B, int64_t N, int64_t D, int metric, float* out, int64_t ld,
                      mmsim_stream_t stream) {

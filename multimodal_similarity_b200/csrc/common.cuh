@@ -11,6 +11,9 @@ namespace mmsim {
 
 // Error codes (MMSIM_OK, MMSIM_ERR_*) come from the public header.
 void set_error(const char* fmt, ...);
+// every kernel launch of the library is followed by MMSIM_CUDA_CHECK(launched()): cudaGetLastError() + one tick of the
+// process-wide launch counter (mmsim_kernel_launches; bench.py reports it as gpu_launches)
+cudaError_t launched();
 
 #define MMSIM_CUDA_CHECK(expr)                                                                  \
   do {                                                                                          \

@@ -192,7 +192,7 @@ int run(const float* E, const int* labels, const int* cls, int64_t N, int64_t D,
   MMSIM_CUDA_CHECK(cudaFuncSetAttribute(eval_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   eval_rank_kernel<<<unsigned(nq), THREADS, smem, s>>>(E, labels, cls, int(N), int(D), C, queries, P, alpha, aligned, ap, npos,
                                                        first, depth, hist, rank);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;
 }
 

@@ -230,18 +230,18 @@ int run_large(const float* E, const int* labels, const int* cls, int64_t N, int6
   void* tmp = w + 4 * seg + align_up(size_t(B + 1) * 4, 256);
   size_t tmp_bytes = sort_temp_bytes(int64_t(items), B);
   seg_offsets_kernel<<<(B + 256) / 256, 256, 0, s>>>(off, B, n);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   for (int64_t q0 = 0; q0 < nq; q0 += B) {
     const int b = int(std::min<int64_t>(B, nq - q0));
     dim3 grid(unsigned(std::min<int64_t>((n + 255) / 256, 4096)), unsigned(b));
     eval_dist_kernel<<<grid, 256, size_t(D) * 4, s>>>(E, int(N), int(D), queries + q0, k_in, v_in);
-    MMSIM_CUDA_CHECK(cudaGetLastError());
+    MMSIM_CUDA_CHECK(::mmsim::launched());
     MMSIM_CUDA_CHECK(cub::DeviceSegmentedRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, int64_t(b) * n, b, off,
                                                               off + 1, 0, 32, s));
     eval_metrics_kernel<<<b, LT, size_t(C) * 4, s>>>(k_out, v_out, labels, cls, int(N), C, queries + q0, alpha, aligned, ap + q0,
                                                      npos + q0, first + q0, depth + q0, hist + size_t(q0) * C,
                                                      rank ? rank + size_t(q0) * n : nullptr);
-    MMSIM_CUDA_CHECK(cudaGetLastError());
+    MMSIM_CUDA_CHECK(::mmsim::launched());
   }
   return MMSIM_OK;
 }

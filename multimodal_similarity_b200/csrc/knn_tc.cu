@@ -1256,7 +1256,7 @@ static int launch_tc(int grid, const CUtensorMap& tq, const CUtensorMap& tg, con
   auto kern = knn_tc_kernel<KATOMS, NEPI, MODE, ABL, false>;
   MMSIM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
   kern<<<grid, 128 + NEPI * 32, S::DYN_BYTES, stream>>>(tq, tg, args);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;
 }
 
@@ -1277,6 +1277,7 @@ static int launch_pair(int grid, const CUtensorMap& tq, const CUtensorMap& tg, c
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   MMSIM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tq, tg, args));
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;
 }
 
@@ -1355,7 +1356,7 @@ static int run_fallback(const Plan& p, uint8_t* w, const float* Q, const float* 
   if (first_wave) {
     fb_prepare_kernel<<<2 * num_sms, FB_THREADS, 0, stream>>>(Q, D, p.Dp, L, gstats, delta_coeff_of(p.Dp), fb_qh, fb_ladder,
                                                               env_int("MMSIM_KNN_FORCE_TIER2"));
-    MMSIM_CUDA_CHECK(cudaGetLastError());
+    MMSIM_CUDA_CHECK(::mmsim::launched());
     CUtensorMap tq, tg;
     int rc = make_tmap(&tq, fb_qh, int64_t(q_rows), p.Dp, BM);
     if (rc) return rc;
@@ -1372,15 +1373,15 @@ static int run_fallback(const Plan& p, uint8_t* w, const float* Q, const float* 
     if (rc) return rc;
     fb_select_kernel<<<4 * num_sms, FB_THREADS, size_t(D) * 4, stream>>>(Q, G, D, log, p.logcap, log_cnt, p.n_tiles, num_sms, budget, L,
                                                                          k, exclude_self, self_offset, out);
-    MMSIM_CUDA_CHECK(cudaGetLastError());
+    MMSIM_CUDA_CHECK(::mmsim::launched());
   }
   fb2_scan_kernel<<<dim3(FB2_CHUNKS, FB2_WAVE), FB_THREADS, size_t(D) * 4, stream>>>(Q, G, ng, D, L, k, exclude_self, self_offset,
                                                                                       part_dist, part_idx);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   fb2_merge_kernel<<<FB2_WAVE, FB_THREADS, 0, stream>>>(L, k, part_dist, part_idx, out);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   fb2_advance_kernel<<<1, 1, 0, stream>>>(L.status, L.cap);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;
 }
 
@@ -1399,7 +1400,7 @@ int shard_fallback(const float* Q, int64_t nq, const float* G, int64_t ng, int64
   uint8_t* w = static_cast<uint8_t*>(ws);
   float* bound = reinterpret_cast<float*>(w + p.off_unc_bound);
   fb_list_from_flags_kernel<<<1, 1024, 0, stream>>>(flag, int(nq), cap, out_query, bound, status);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   FbLists L{status, out_query, bound, reinterpret_cast<int*>(w + p.off_fb2_list), status, cap};
   const FbOut out{out_dist, out_idx, 1};
   return run_fallback(p, w, Q, G, ng, int(D), k, exclude_self, self_offset, L, out, num_sms, true, stream);
@@ -1487,28 +1488,28 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
       const unsigned gb = unsigned(std::min<int64_t>((g_pad + warps_per_block - 1) / warps_per_block, cap));
       prep<<<gb, PREP_THREADS, 0, stream>>>(G, ng, g_pad, int(D), p.Dp, 1.0f, gh, gpack, nullptr, 1,
                                             reinterpret_cast<unsigned int*>(gstats), nullptr);
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
       pack_min_kernel<<<unsigned(p.n_tiles), BN, 0, stream>>>(gpack);
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
     }
     const unsigned qb = unsigned(std::min<int64_t>((nq + warps_per_block - 1) / warps_per_block, cap));
     prep<<<qb, PREP_THREADS, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, 0, nullptr, nullptr);
-    MMSIM_CUDA_CHECK(cudaGetLastError());
+    MMSIM_CUDA_CHECK(::mmsim::launched());
     if (group) {
       // query grouping: anchors = evenly spaced query rows -> nearest anchor of every query (tensor cores) -> stable
       // counting sort -> operand copies of the queries again, in the sweep's order
       const int a_tiles = p.n_anchor / BN;
       anchor_index_kernel<<<(p.n_anchor + 255) / 256, 256, 0, stream>>>(aidx, p.n_anchor, nq);
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
       prep<<<unsigned((p.n_anchor + warps_per_block - 1) / warps_per_block), PREP_THREADS, 0, stream>>>(
           Q, p.n_anchor, p.n_anchor, int(D), p.Dp, 1.0f, ah, apack, nullptr, 1, nullptr, aidx);
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
       // the assign pass reads the per-32-column minima of the pack for its chunk-level early out.  (Round 1 left them
       // uninitialised: the assignment then depended on whatever the workspace held, so two shards with their own
       // workspaces could derive DIFFERENT sweep orders from the same queries and exchange misaligned pivot lists --
       // the uncertified query of tests/test_gpu_merge.py::test_reduced_protocol_with_grouped_queries on a fresh box.)
       pack_min_kernel<<<unsigned(a_tiles), BN, 0, stream>>>(apack);
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
       CUtensorMap tq0, ta;
       int rc0 = make_tmap(&tq0, qh, nq, p.Dp, BM);
       if (rc0) return rc0;
@@ -1524,16 +1525,16 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
       if (rc0) return rc0;
       const size_t hsm = size_t(p.n_anchor) * 4;
       group_hist_kernel<<<p.group_blocks, GROUP_BLOCK, hsm, stream>>>(assign, int(nq), p.n_anchor, ghist);
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
       int* bin_start = ghist + size_t(p.n_anchor) * p.group_blocks;
       group_binscan_kernel<<<(p.n_anchor * 32 + 255) / 256, 256, 0, stream>>>(ghist, p.group_blocks, p.n_anchor, bin_start);
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
       group_scan_kernel<<<1, 1024, 0, stream>>>(bin_start, p.n_anchor);
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
       group_scatter_kernel<<<p.group_blocks, GROUP_BLOCK, hsm, stream>>>(assign, int(nq), p.n_anchor, ghist, bin_start, perm);
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
       prep<<<qb, PREP_THREADS, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, 0, nullptr, perm);
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
     }
   }
 
@@ -1556,7 +1557,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     if ((phases & kPhasePivot) && !p.use_pivots) {   // shard small enough to be logged whole: an empty (+inf) pivot list
       const int64_t n = int64_t(p.n_qblocks) * BM * NPIV;
       fill_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(piv16, n, kInf);
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
     }
     if ((phases & kPhasePivot) && p.use_pivots) {
       // The pre-pass sweeps a compact block holding the sampled gallery rows (sample_row(): every sample_div-th row).
@@ -1577,12 +1578,12 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
         prep<<<sb, PREP_THREADS, 0, stream>>>(s32, p.n_sample, s_pad, int(D), p.Dp, 1.0f, sh, spack, nullptr, 1, nullptr, nullptr);
       } else {
         sample_index_kernel<<<unsigned((p.n_sample + 255) / 256), 256, 0, stream>>>(sidx, p.n_sample, p.sample_div, p.sample_seg);
-        MMSIM_CUDA_CHECK(cudaGetLastError());
+        MMSIM_CUDA_CHECK(::mmsim::launched());
         prep<<<sb, PREP_THREADS, 0, stream>>>(G, p.n_sample, s_pad, int(D), p.Dp, 1.0f, sh, spack, nullptr, 1, nullptr, sidx);
       }
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
       pack_min_kernel<<<unsigned(p.n_sample_tiles), BN, 0, stream>>>(spack);
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
       CUtensorMap ts;
       rc = make_tmap(&ts, sh, p.n_sample, p.Dp, BN);
       if (rc) return rc;
@@ -1595,7 +1596,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     if ((phases & kPhaseLadder) && p.use_pivots) {
       const int rows = p.n_qblocks * BM;
       make_ladder_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(piv16, rows, ladder, ladder_ranks());
-      MMSIM_CUDA_CHECK(cudaGetLastError());
+      MMSIM_CUDA_CHECK(::mmsim::launched());
     }
     if (phases & kPhaseTensor) {
       if (p.n_splits > 1)
@@ -1621,9 +1622,9 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
           prep<<<gb, PREP_THREADS, 0, ps->prep>>>(G + size_t(r0) * D, r1 - r0, r_pad, int(D), p.Dp, 1.0f, gh + size_t(r0) * p.Dp,
                                                   gpack + size_t(t0) * NPACK, nullptr, 1,
                                                   reinterpret_cast<unsigned int*>(gstats), nullptr);
-          MMSIM_CUDA_CHECK(cudaGetLastError());
+          MMSIM_CUDA_CHECK(::mmsim::launched());
           pack_min_kernel<<<unsigned(t1 - t0), BN, 0, ps->prep>>>(gpack + size_t(t0) * NPACK);
-          MMSIM_CUDA_CHECK(cudaGetLastError());
+          MMSIM_CUDA_CHECK(::mmsim::launched());
           MMSIM_CUDA_CHECK(cudaEventRecord(ps->chunk_ready[c], ps->prep));
           cudaStream_t x = (c & 1) && !one_stream ? ps->sweep2 : stream;
           if (x != stream && !used2) {
@@ -1672,7 +1673,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
                                                                shard_kp ? shard_kp : KP, exclude_self, self_offset, out_dist,
                                                                out_idx, shard_kp ? out_lb : nullptr, status, unc_query,
                                                                unc_bound, p.unc_cap, perm, env_int("MMSIM_KNN_FORCE_FALLBACK"));
-    MMSIM_CUDA_CHECK(cudaGetLastError());
+    MMSIM_CUDA_CHECK(::mmsim::launched());
   }
 
   // 4. exact fallback for the uncertified queries (knn_fallback.cuh; the count lives on the device: when it is zero the
@@ -1692,7 +1693,7 @@ int merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t ro
   MMSIM_REQUIRE(parts && out && nparts >= 1 && rows >= 0 && part_stride >= rows * NPIV, MMSIM_ERR_ARG, "merge_pivots: bad arguments");
   if (rows == 0) return MMSIM_OK;
   merge_pivots_kernel<<<unsigned((rows + 127) / 128), 128, 0, stream>>>(parts, nparts, part_stride, int(rows), out);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;
 }
 

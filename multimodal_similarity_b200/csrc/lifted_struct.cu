@@ -180,16 +180,16 @@ int run(const float* E, const int* labels, int64_t N, int64_t D, float margin, f
   float* num_pos = reinterpret_cast<float*>(v0 + 4 * vec);
   if (int rc = sqdist::run(E, N, E, N, D, 0, Dm, N, s)) return rc;
   row_sums_kernel<<<unsigned((N * 32 + T - 1) / T), T, 0, s>>>(Dm, labels, int(N), margin, logS, pos_rows);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   total_kernel<<<1, 1024, 0, s>>>(pos_rows, int(N), num_pos);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   pair_kernel<<<unsigned(N), T, 0, s>>>(Dm, labels, int(N), logS, num_pos, partial, logW);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   finish_kernel<<<1, 256, 0, s>>>(partial, int(N), num_pos, loss);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   if (dE) {
     grad_kernel<<<unsigned(N), T, size_t(N) * 4, s>>>(E, Dm, labels, int(N), int(D), margin, logS, logW, num_pos, dE);
-    MMSIM_CUDA_CHECK(cudaGetLastError());
+    MMSIM_CUDA_CHECK(::mmsim::launched());
   }
   return MMSIM_OK;
 }

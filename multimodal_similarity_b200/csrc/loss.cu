@@ -991,7 +991,7 @@ int run(int kind, const float* E, const float* pids, int64_t N, int64_t D, int s
     }
     if (dE) MMSIM_CUDA_CHECK(cudaMemsetAsync(dE, 0, size_t(N) * D * sizeof(float), stream));
     bh_rows_kernel<<<unsigned((N + BR_R - 1) / BR_R), BR_THREADS, bh_rows_smem(N, D), stream>>>(p);
-    MMSIM_CUDA_CHECK(cudaGetLastError());
+    MMSIM_CUDA_CHECK(::mmsim::launched());
     return MMSIM_OK;
   }
 
@@ -999,6 +999,7 @@ int run(int kind, const float* E, const float* pids, int64_t N, int64_t D, int s
   const dim3 grid(unsigned(L.NBI * L.NBJ)), block(THREADS);
   const void* fn = kernel_for(L.shape, kind);
   MMSIM_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, grid, block, args, L.smem_bytes, stream));
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;
 }
 

@@ -134,7 +134,7 @@ int run(const float* dist_parts, const int* idx_parts, int64_t part_stride, cons
   knn_merge_kernel<<<unsigned((nq + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(dist_parts, idx_parts, part_stride, idx_base, parts, nq, k_in, k, P,
                                                                               lb_parts, lb_stride, out_dist, out_idx, status, out_flag,
                                                                               count_ptr, row_map);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;
 }
 

@@ -84,7 +84,7 @@ int run_mask(const float* dist, int64_t n, int64_t ld, const int* labels, const 
   if (int rc = check_common(dist, n, ld, labels, pairs, count, m, "semihard_mask")) return rc;
   if (m == 0) return MMSIM_OK;
   semihard_mask_kernel<<<unsigned((m * 32 + 127) / 128), 128, 0, s>>>(dist, n, ld, labels, pairs, m, alpha, mask, count);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;
 }
 
@@ -93,7 +93,7 @@ int run_pick(const float* dist, int64_t n, int64_t ld, const int* labels, const 
   if (int rc = check_common(dist, n, ld, labels, picks, neg_idx, p, "semihard_pick")) return rc;
   if (p == 0) return MMSIM_OK;
   semihard_pick_kernel<<<unsigned((p * 32 + 127) / 128), 128, 0, s>>>(dist, n, ld, labels, picks, p, alpha, neg_idx);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;
 }
 

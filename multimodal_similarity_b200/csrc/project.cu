@@ -87,7 +87,7 @@ static int launch(const float* X, int64_t N, int K, const float* W, const float*
                   cudaStream_t s) {
   const size_t smem = (size_t(PM) * (PK + 1) + size_t(PK) * NC * 32) * 4;
   project_normalize_kernel<NC><<<unsigned((N + PM - 1) / PM), PT, smem, s>>>(X, N, K, W, b, E, normalized, eps, out);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;
 }
 

@@ -141,14 +141,14 @@ int run(const float* E, const int* labels, int64_t N, int64_t D, float margin, f
   float* num_pos = reinterpret_cast<float*>(w + align_up(size_t(N) * N * 4, 256) + align_up(size_t(N) * 4, 256));
   if (int rc = sqdist::run(E, N, E, N, D, 0, Dm, N, s)) return rc;
   count_pairs_kernel<<<1, 1024, 0, s>>>(labels, int(N), num_pos);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   if (dE) MMSIM_CUDA_CHECK(cudaMemsetAsync(dE, 0, size_t(N) * D * 4, s));
   const size_t smem = size_t(N) * 8;
   if (smem > 48 * 1024) MMSIM_CUDA_CHECK(cudaFuncSetAttribute(anchor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   anchor_kernel<<<unsigned(N), T, smem, s>>>(E, labels, Dm, int(N), int(D), margin, num_pos, partial, dE);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   finish_kernel<<<1, 256, 0, s>>>(partial, int(N), num_pos, loss);
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;
 }
 

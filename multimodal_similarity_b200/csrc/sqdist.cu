@@ -54,7 +54,7 @@ static int launch(const float* A, int64_t M, const float* B, int64_t N, int D, f
   } else {
     sqdist_exact_kernel<METRIC, false><<<grid, THREADS, 0, s>>>(A, M, B, N, D, out, ld);
   }
-  MMSIM_CUDA_CHECK(cudaGetLastError());
+  MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;
 }
 
