@@ -164,7 +164,8 @@ MMSIM_API int mmsim_knn_pivot_region(int64_t nq, int64_t ng, int64_t D, int k, s
 /* Introspection (tests): the launch geometry chosen for a problem on a device with num_sms SMs.
  * out[0..12) = padded width, K atoms, 128-query blocks, 256-row gallery tiles, gallery splits, tiles per split, grid,
  * log capacity per (query, split), pivot pre-pass used, tiles of the compact gallery sample, sampled rows, workspace bytes,
- * [12], [13] (if n_out >= 14): workspace offsets of the per-(query, split) candidate counts (int32) and final thresholds. */
+ * [12], [13] (if n_out >= 14): workspace offsets of the per-(query, split) candidate counts (int32) and final thresholds;
+ * [14..17) (if n_out >= 17): query-streaming sweep in use, its query chunks and 128-query blocks per chunk. */
 MMSIM_API int mmsim_knn_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, int64_t* out, int n_out);
 MMSIM_API int mmsim_knn_merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t rows, float* out,
                            mmsim_stream_t stream);

@@ -165,10 +165,10 @@ MMSIM_API int mmsim_knn_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_s
   MMSIM_REQUIRE(out && n_out >= 12, MMSIM_ERR_ARG, "knn_plan: need an output array of at least 12 int64");
   MMSIM_REQUIRE(nq > 0 && ng > 0 && D > 0 && D <= 256 && k >= 1 && num_sms >= 1, MMSIM_ERR_ARG, "knn_plan: bad sizes");
   const knn::Plan p = knn::make_plan(nq, ng, D, k, num_sms);
-  const int64_t v[14] = {p.Dp, p.katoms, p.n_qblocks, p.n_tiles, p.n_splits, p.tiles_per_split, p.grid, p.logcap,
+  const int64_t v[17] = {p.Dp, p.katoms, p.n_qblocks, p.n_tiles, p.n_splits, p.tiles_per_split, p.grid, p.logcap,
                          p.use_pivots, p.n_sample_tiles, p.n_sample, int64_t(p.total_bytes),
-                         int64_t(p.off_log_cnt), int64_t(p.off_log_tau)};
-  for (int i = 0; i < 14 && i < n_out; ++i) out[i] = v[i];
+                         int64_t(p.off_log_cnt), int64_t(p.off_log_tau), p.sweepq, p.host_splits, 0};
+  for (int i = 0; i < 17 && i < n_out; ++i) out[i] = v[i];
   return MMSIM_OK;
 }
 

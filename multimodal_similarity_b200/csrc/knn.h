@@ -14,6 +14,10 @@ struct Plan {
   int Dp, katoms;             // padded feature width (multiple of 64) and number of 64-wide K atoms
   int n_qblocks, n_tiles;     // 128-query blocks, 256-row gallery tiles
   int n_splits, tiles_per_split, grid;
+  // query-streaming sweep (knn_sweepq.cuh; the default): one candidate log per query (n_splits == 1), work items are
+  // (gallery tile, query chunk); host-buffer mode copies / sweeps the gallery in host_splits tile ranges
+  int sweepq, host_splits;
+  size_t off_tau, off_state;
   int unc_cap;                // capacity of the uncertified-query lists (= nq: every query may take the exact fallback)
   int logcap, use_pivots;     // candidate log capacity per (query, split); pivot pre-pass used (gallery larger than a log)
   // pivot pre-pass: a systematic sample of the gallery rows (every sample_div-th row, the offset inside the stride changes

@@ -562,6 +562,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         if (SWEEP) {
           // Level 2 (warp has a hit): the same test per 8-column group; level 3 (out of line): the 8 keys of a group.
           // (The query operand was pre-scaled by -2: acc = -2 q.g, key = |g|^2 - 2 q.g.)
+          // (Tried in round 2: levels 2 + 3 as ONE out-of-line function fed through a local-memory copy of the chunk, to
+          // shrink the hot loop's code from 6.5 KB to 3.3 KB -- 27.4 ms instead of 22.7: the 32-register spill + reload per
+          // candidate chunk costs far more than the footprint; profiles/r2_sweep_experiments.txt.)
           const float4 nm8 = lds_f32x4(nrm + (BN + c * 4) * 4);
           const uint32_t mine = (gm[0] < tau - nm8.x ? 1u : 0u) | (gm[1] < tau - nm8.y ? 2u : 0u) |
                                 (gm[2] < tau - nm8.z ? 4u : 0u) | (gm[3] < tau - nm8.w ? 8u : 0u);
@@ -716,6 +719,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     if (PAIR) ptx::tmem_dealloc_pair(tmem_base, 2 * BN); else ptx::tmem_dealloc(tmem_base, 2 * BN);
   }
 }
+
+}  // namespace knn
+}  // namespace mmsim
+#include "knn_sweepq.cuh"
+namespace mmsim {
+namespace knn {
 
 // ------------------------------------------------------------------------------------------------ query grouping
 // The sweep tests 32 query rows x 32 gallery columns per warp step, and a step that finds a candidate costs several times
@@ -876,7 +885,7 @@ __global__ void merge_pivots_kernel(const float* __restrict__ parts, int nparts,
 // One warp per query: pick the KP smallest approximate keys from the sweep's candidate log, recompute those
 // candidates' distances exactly, sort by (distance, index), emit top-k, certify.
 constexpr int RR_WARPS = 4;
-constexpr int RR_STAGE = 1024;             // logged keys per query staged in shared memory for the selection
+constexpr int RR_STAGE = 2048;             // logged keys per query staged in shared memory for the selection
 
 __device__ __forceinline__ uint32_t sortable(uint32_t fbits) { return (fbits & 0x80000000u) ? ~fbits : (fbits | 0x80000000u); }
 __device__ __forceinline__ float unsortable(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
@@ -1143,6 +1152,12 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, bool host_
       best_s = s_eff;
     }
   }
+  // MMSIM_KNN_SWEEP=q: the query-streaming sweep (knn_sweepq.cuh; opt-in: faster pipeline, slower candidate path, no net gain)
+  {
+    const char* e = getenv("MMSIM_KNN_SWEEP");
+    p.sweepq = e && e[0] == 'q';
+  }
+  p.host_splits = int(std::max<int64_t>(1, std::min<int64_t>(8, p.n_tiles / 64)));
   if (host_mode) {
     // Host-buffer mode launches one sweep per split as its rows arrive, two in flight (no wave quantisation to balance):
     // splits are the unit of the copy / sweep pipeline.  8 exposes only the queries' transfer -- 29.4 / 28.2 / 28.0 / 27.1 /
@@ -1152,6 +1167,10 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, bool host_
   if (const char* e = getenv("MMSIM_KNN_SPLITS")) {   // experiment switch
     const int v = atoi(e);
     if (v >= 1 && v <= 16) best_s = std::min(v, p.n_tiles);
+  }
+  if (p.sweepq) {
+    if (host_mode) p.host_splits = std::max(1, std::min(best_s, 16));
+    best_s = 1;                     // one log per query; the gallery tiles are the work items
   }
   p.n_splits = best_s;
   p.tiles_per_split = (p.n_tiles + p.n_splits - 1) / p.n_splits;
@@ -1204,6 +1223,8 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, bool host_
   p.off_log_cnt = take(q_rows * p.n_splits * 4);
   p.off_log_tau = take(q_rows * p.n_splits * 4);
   p.off_split_done = take(q_rows * p.n_splits * 4);
+  p.off_tau = take(q_rows * 4);
+  p.off_state = take(q_rows * 4);
   p.off_unc_query = take(size_t(p.unc_cap) * 4);
   p.off_unc_bound = take(size_t(p.unc_cap) * 4);
   p.off_fb2_list = take(size_t(p.unc_cap) * 4);
@@ -1288,6 +1309,48 @@ static int launch_mode(int katoms, int grid, const CUtensorMap& tq, const CUtens
     case 2: return launch_tc<2, NEPI_SWEEP, MODE, ABL>(grid, tq, tg, args, s);
     case 3: return launch_tc<3, NEPI_SWEEP, MODE, ABL>(grid, tq, tg, args, s);
     default: return launch_tc<4, NEPI_SWEEP, MODE, ABL>(grid, tq, tg, args, s);
+  }
+}
+
+// query chunks of the query-streaming sweep: items = tiles x chunks should fill the persistent grid in whole waves
+static void sweepq_chunks(int n_tiles, int n_qblocks, int num_sms, int* n_qchunks, int* qpc) {
+  int best = 1;
+  double best_eff = 0;
+  for (int c = 1; c <= 16; ++c) {
+    const int per = (n_qblocks + c - 1) / c;
+    if (c > 1 && per < 24) break;                       // an item should amortise loading its gallery tile
+    const int c_eff = (n_qblocks + per - 1) / per;
+    const int64_t items = int64_t(n_tiles) * c_eff;
+    const int64_t waves = (items + num_sms - 1) / num_sms;
+    const double eff = double(n_tiles) * n_qblocks / (double(waves) * num_sms * per) - 0.005 * (c_eff - 1);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = c_eff;
+    }
+  }
+  if (const char* e = getenv("MMSIM_KNN_QCHUNKS")) {   // experiment switch
+    const int v = atoi(e);
+    if (v >= 1 && v <= n_qblocks) best = v;
+  }
+  *qpc = (n_qblocks + best - 1) / best;
+  *n_qchunks = (n_qblocks + *qpc - 1) / *qpc;
+}
+
+template <int KATOMS>
+static int launch_sweepq_k(int grid, const CUtensorMap& tq, const CUtensorMap& tg, const SweepQArgs& args, cudaStream_t stream) {
+  using S = SmemQ<KATOMS>;
+  auto kern = knn_sweepq_kernel<KATOMS, NEPI_SWEEP>;
+  MMSIM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
+  kern<<<grid, 128 + NEPI_SWEEP * 32, S::DYN_BYTES, stream>>>(tq, tg, args);
+  MMSIM_CUDA_CHECK(::mmsim::launched());
+  return MMSIM_OK;
+}
+static int launch_sweepq(int katoms, int grid, const CUtensorMap& tq, const CUtensorMap& tg, const SweepQArgs& args, cudaStream_t s) {
+  switch (katoms) {
+    case 1: return launch_sweepq_k<1>(grid, tq, tg, args, s);
+    case 2: return launch_sweepq_k<2>(grid, tq, tg, args, s);
+    case 3: return launch_sweepq_k<3>(grid, tq, tg, args, s);
+    default: return launch_sweepq_k<4>(grid, tq, tg, args, s);
   }
 }
 
@@ -1603,6 +1666,25 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
         MMSIM_CUDA_CHECK(cudaMemsetAsync(split_done, 0, size_t(p.n_qblocks) * BM * p.n_splits * 4, stream));
       const int abl = sweep_ablation();
       args.close_rows = abl == 8;
+      const int q_rows = p.n_qblocks * BM;
+      float* tau = reinterpret_cast<float*>(w + p.off_tau);
+      unsigned int* state = reinterpret_cast<unsigned int*>(w + p.off_state);
+      SweepQArgs qa{};
+      if (p.sweepq) {
+        // query-streaming sweep (knn_sweepq.cuh): thresholds and cursors are global words, initialised here
+        sweepq_init_kernel<<<(q_rows + 255) / 256, 256, 0, stream>>>(ladder, p.use_pivots, int(nq), q_rows, tau, state, abl == 8);
+        MMSIM_CUDA_CHECK(::mmsim::launched());
+        qa.gpack = gpack; qa.nq = int(nq); qa.n_qblocks = p.n_qblocks;
+        qa.tau = tau; qa.state = state; qa.ladder = ladder; qa.use_pivots = p.use_pivots;
+        qa.log = log; qa.logcap = p.logcap; qa.drop = (abl == 16 || abl == 32) ? abl : 0;
+      }
+      // one launch of the query-streaming sweep over gallery tiles [t0, t1)
+      auto launch_q = [&](int t0, int t1, cudaStream_t x) -> int {
+        SweepQArgs sa = qa;
+        sa.tile_begin = t0; sa.tile_end = t1;
+        sweepq_chunks(t1 - t0, p.n_qblocks, num_sms, &sa.n_qchunks, &sa.qpc);
+        return launch_sweepq(p.katoms, std::min(num_sms, (t1 - t0) * sa.n_qchunks), tq, tg, sa, x);
+      };
       if (host) {
         // host-buffer mode: one launch per gallery split.  Split c's rows are copied (copy stream), converted (prep
         // stream) and swept while the copy of split c + 1 is in flight; the sweeps alternate between the caller's stream
@@ -1611,8 +1693,11 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
         bool used2 = false;
         const char* e1 = getenv("MMSIM_HOST_ONE_STREAM");   // experiment switch: every sweep on the caller's stream
         const bool one_stream = e1 && atoi(e1) == 1;
-        for (int c = 0; c < p.n_splits; ++c) {
-          const int64_t t0 = int64_t(c) * p.tiles_per_split, t1 = std::min<int64_t>(p.n_tiles, t0 + p.tiles_per_split);
+        const int n_chunks = p.sweepq ? p.host_splits : p.n_splits;
+        const int tpc = p.sweepq ? (p.n_tiles + n_chunks - 1) / n_chunks : p.tiles_per_split;
+        for (int c = 0; c < n_chunks; ++c) {
+          const int64_t t0 = int64_t(c) * tpc, t1 = std::min<int64_t>(p.n_tiles, t0 + tpc);
+          if (t0 >= t1) break;
           const int64_t r0 = t0 * BN, r1 = std::min<int64_t>(ng, t1 * BN), r_pad = t1 * BN - r0;
           MMSIM_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(G) + size_t(r0) * D, host->g_host + size_t(r0) * D,
                                            size_t(r1 - r0) * D * 4, cudaMemcpyHostToDevice, ps->copy));
@@ -1632,16 +1717,23 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
             used2 = true;
           }
           MMSIM_CUDA_CHECK(cudaStreamWaitEvent(x, ps->chunk_ready[c], 0));
-          SweepArgs sa = args;
-          sa.item_begin = c * p.n_qblocks;
-          sa.item_end = (c + 1) * p.n_qblocks;
-          rc = launch_mode<MODE_SWEEP, 0>(p.katoms, std::min(num_sms, p.n_qblocks), tq, tg, sa, x);
+          if (p.sweepq) {
+            rc = launch_q(int(t0), int(t1), x);
+          } else {
+            SweepArgs sa = args;
+            sa.item_begin = c * p.n_qblocks;
+            sa.item_end = (c + 1) * p.n_qblocks;
+            rc = launch_mode<MODE_SWEEP, 0>(p.katoms, std::min(num_sms, p.n_qblocks), tq, tg, sa, x);
+          }
           if (rc) return rc;
         }
         if (used2) {
           MMSIM_CUDA_CHECK(cudaEventRecord(ps->sweep2_done, ps->sweep2));
           MMSIM_CUDA_CHECK(cudaStreamWaitEvent(stream, ps->sweep2_done, 0));
         }
+      } else if (p.sweepq) {
+        rc = launch_q(0, p.n_tiles, stream);
+        if (rc) return rc;
       } else if (sweep_pairs() && (abl == 0 || abl == 8)) {
         CUtensorMap tgh;
         rc = make_tmap(&tgh, gh, ng, p.Dp, BN / 2);
@@ -1659,6 +1751,10 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
            : abl == 4 ? launch_mode<MODE_SWEEP, 4>(p.katoms, p.grid, tq, tg, args, stream)
                       : launch_mode<MODE_SWEEP, 0>(p.katoms, p.grid, tq, tg, args, stream);
       if (rc) return rc;
+      if (p.sweepq) {
+        sweepq_finish_kernel<<<(q_rows + 255) / 256, 256, 0, stream>>>(state, tau, q_rows, log_cnt, log_tau);
+        MMSIM_CUDA_CHECK(::mmsim::launched());
+      }
     }
   }
 

@@ -55,6 +55,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking test of a phase (no suspend): true iff the phase with this parity has completed.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trap (a CUDA error the host reports), never as a hung GPU.
 // The slow path is out of line so the many wait sites stay a TRYWAIT + branch (instruction-cache footprint).
 __device__ __forceinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {

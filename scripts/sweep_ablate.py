@@ -11,7 +11,8 @@ g = synth_torch(1_000_000, D, 1000, 12345, dev)
 q = synth_torch(100_000, D, 1000, 12346, dev, centroid_seed=12345)   # same mixture as the gallery
 out = knn_raw(q, g, 100)
 torch.cuda.synchronize()
-for flags in ((0, 8, 0) if os.environ.get("MMSIM_KNN_PAIR") == "1" else (0, 8, 2, 4, 0)):
+legacy = not os.environ.get("MMSIM_KNN_SWEEP", "").startswith("q")     # default: the gallery-streaming kernel
+for flags in ((0, 8, 0) if os.environ.get("MMSIM_KNN_PAIR") == "1" else (0, 8, 16, 32, 0) if not legacy else (0, 8, 2, 4, 0)):
     os.environ["MMSIM_SWEEP_FLAGS"] = str(flags)
     for _ in range(2):
         knn_raw(q, g, 100, phases=2, out=out)

@@ -190,6 +190,22 @@ def test_cta_pair_sweep_matches(rs, monkeypatch):
     monkeypatch.delenv("MMSIM_KNN_PAIR", raising=False)
 
 
+def test_query_streaming_sweep_matches(rs, monkeypatch):
+    """The opt-in query-streaming sweep (MMSIM_KNN_SWEEP=q, csrc/knn_sweepq.cuh: resident gallery tile, streamed query
+    blocks, global thresholds, candidates drained through a shared-memory ring) returns exactly what the default sweep
+    returns -- several gallery tiles per CTA, query chunks, 64- / 128- / 256-d."""
+    import multimodal_similarity_b200 as mm
+    for ng, nq, d, k in ((70000, 1000, 128, 50), (30000, 4500, 64, 30), (20000, 300, 256, 100), (1500, 40, 96, 10)):
+        g = torch.from_numpy(clustered(rs, ng, d, 40)[0]).cuda()
+        q = torch.from_numpy(clustered(rs, nq, d, 40)[0]).cuda()
+        monkeypatch.delenv("MMSIM_KNN_SWEEP", raising=False)
+        d0, i0 = mm.retrieve(q, g, k)
+        monkeypatch.setenv("MMSIM_KNN_SWEEP", "q")
+        d1, i1 = mm.retrieve(q, g, k)
+        assert torch.equal(d0, d1) and torch.equal(i0, i1)
+    monkeypatch.delenv("MMSIM_KNN_SWEEP", raising=False)
+
+
 def test_grouped_queries_exclude_self_vs_oracle(rs):
     """Enough queries and gallery rows for query grouping (sweep order != caller's order): leave-one-out retrieval with
     the queries being gallery rows, spot-checked against the oracle; and grouping on/off give identical results."""

@@ -46,7 +46,7 @@ def test_workspace_query_is_device_independent_upper_bound():
     # call no longer reserves it
     h = ctypes.c_size_t()
     assert lib.mmsim_knn_host_workspace_bytes(100000, 1000000, 128, 100, ctypes.byref(h)) == 0
-    assert n.value < 4e9 < h.value < 9e9
+    assert n.value < 4e9 and n.value < h.value < 9e9
 
 
 def test_sample_rows_are_spread_and_in_range():
