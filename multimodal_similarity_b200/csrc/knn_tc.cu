@@ -885,7 +885,7 @@ __global__ void merge_pivots_kernel(const float* __restrict__ parts, int nparts,
 // One warp per query: pick the KP smallest approximate keys from the sweep's candidate log, recompute those
 // candidates' distances exactly, sort by (distance, index), emit top-k, certify.
 constexpr int RR_WARPS = 4;
-constexpr int RR_STAGE = 2048;             // logged keys per query staged in shared memory for the selection
+constexpr int RR_STAGE = 1024;             // logged keys per query staged in shared memory for the selection (at least)
 
 __device__ __forceinline__ uint32_t sortable(uint32_t fbits) { return (fbits & 0x80000000u) ? ~fbits : (fbits | 0x80000000u); }
 __device__ __forceinline__ float unsortable(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
@@ -898,7 +898,8 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
                   float* __restrict__ out_dist, int* __restrict__ out_idx, float* __restrict__ out_lb,
                   int* __restrict__ status, int* __restrict__ unc_query, float* __restrict__ unc_bound, int unc_cap,
                   const int* __restrict__ perm /* sweep position -> query (query grouping), or null: identity */,
-                  int force_mod /* test hook (MMSIM_KNN_FORCE_FALLBACK=m): every m-th query counts as uncertified */) {
+                  int force_mod /* test hook (MMSIM_KNN_FORCE_FALLBACK=m): every m-th query counts as uncertified */,
+                  int scratch_words /* per-warp scratch: the staged keys of the selection */) {
   // kp <= KP candidates are re-ranked.  out_lb == nullptr: emit the top-k and certify locally (k <= kp).
   // out_lb != nullptr (gallery-shard mode): emit all kp re-ranked candidates (k == kp) plus the lower bound on the
   // true distance of every row of this shard that is NOT among them; the certificate is evaluated after the merge.
@@ -925,46 +926,65 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
     total += min(c, logcap);
     tau_min = fminf(tau_min, log_tau[l0 + s]);
   }
-  uint32_t ustar = 0xffffffffu;   // KP-th smallest key in sortable-uint form
-  // The selection reads every logged key up to 34 times (32 radix passes + 2 gather passes): stage the keys in shared
-  // memory once when they fit (they do unless a log is nearly full), instead of streaming them from L2 every pass.
-  uint32_t* ek = reinterpret_cast<uint32_t*>(rr_smem + RR_WARPS * (D + 2 * KP)) + warp * RR_STAGE;
-  const bool staged = total > kp && total <= RR_STAGE;
-  if (staged) {
-    int base = 0;
-    for (int s = 0; s < n_splits; ++s) {
-      const uint2* ls = log + (l0 + s) * logcap;
-      const int c = min(log_cnt[l0 + s], logcap);
-      for (int e = lane; e < c; e += 32) ek[base + e] = sortable(__ldg(&ls[e].x));
-      base += c;
-    }
-    __syncwarp();
-  }
+  // ---- selection: the candidates are the logged keys below a bound `ub` chosen so that between kp - 8 and kp of them
+  // qualify.  Any bound works for the certificate (every unselected logged row has key >= ub), it only has to be as large
+  // as the kp re-rank slots allow -- so instead of the exact kp-th smallest key (round 1: a 32-pass radix descent + two
+  // gather passes, a third of this kernel's instructions) the bound comes from a bisection over the key range that stops
+  // as soon as the count lands in that window: 1 min/max pass + about 8 counting passes + 1 gather pass.
+  // The keys are staged in shared memory once when they fit (they do unless a log is nearly full).
+  uint32_t ub = 0xffffffffu;      // exclusive bound in sortable-uint form
+  uint32_t* ek = reinterpret_cast<uint32_t*>(rr_smem + RR_WARPS * (D + 2 * KP)) + size_t(warp) * scratch_words;
+  const bool staged = total > kp && total <= scratch_words;
   if (total > kp) {
-    // radix descent, one bit per pass: smallest value u with #{entries <= u} >= kp
-    uint32_t prefix = 0;
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t mid = prefix | ((1u << bit) - 1u);
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    {
+      int base = 0;
+      for (int s = 0; s < n_splits; ++s) {
+        const uint2* ls = log + (l0 + s) * logcap;
+        const int c = min(log_cnt[l0 + s], logcap);
+        for (int e = lane; e < c; e += 32) {
+          const uint32_t u = sortable(__ldg(&ls[e].x));
+          if (staged) ek[base + e] = u;
+          mn = min(mn, u);
+          mx = max(mx, u);
+        }
+        base += c;
+      }
+      mn = __reduce_min_sync(0xffffffffu, mn);
+      mx = __reduce_max_sync(0xffffffffu, mx);
+      __syncwarp();
+    }
+    auto count_below = [&](uint32_t x) {
       int cnt = 0;
       if (staged) {
-        for (int e = lane; e < total; e += 32) cnt += ek[e] <= mid ? 1 : 0;
+        for (int e = lane; e < total; e += 32) cnt += ek[e] < x ? 1 : 0;
       } else {
         for (int s = 0; s < n_splits; ++s) {
           const uint2* ls = log + (l0 + s) * logcap;
           const int c = min(log_cnt[l0 + s], logcap);
-          for (int e = lane; e < c; e += 32) cnt += sortable(__ldg(&ls[e].x)) <= mid ? 1 : 0;
+          for (int e = lane; e < c; e += 32) cnt += sortable(__ldg(&ls[e].x)) < x ? 1 : 0;
         }
       }
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (cnt < kp) prefix |= (1u << bit);
+      return __reduce_add_sync(0xffffffffu, cnt);
+    };
+    // invariant: count_below(lo) <= kp < count_below(hi)   (lo = smallest key: 0 below it; hi = past the largest: all)
+    uint32_t lo = mn, hi = mx == 0xffffffffu ? mx : mx + 1u;
+    const int want = max(kp - 8, 1);
+    while (hi - lo > 1u) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      const int c = count_below(mid);
+      if (c <= kp) {
+        lo = mid;
+        if (c >= want) break;
+      } else {
+        hi = mid;
+      }
     }
-    ustar = prefix;
+    ub = lo;
   }
   __syncwarp();
-  int filled = 0;
-  for (int pass = 0; pass < 2; ++pass) {        // pass 0: keys < u*, pass 1: keys == u* until kp slots are used
-    if (pass == 1 && total <= kp) break;
-    int base = 0;
+  {
+    int filled = 0, base = 0;
     for (int s = 0; s < n_splits; ++s) {
       const uint2* ls = log + (l0 + s) * logcap;
       const int c = min(log_cnt[l0 + s], logcap);
@@ -974,7 +994,7 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
         bool take = false;
         if (e < c) {
           u = staged ? ek[base + e] : sortable(__ldg(&ls[e].x));
-          take = total <= kp ? true : (pass == 0 ? u < ustar : u == ustar);
+          take = total <= kp ? true : u < ub;
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, take);
         const int pos = filled + __popc(bal & ((1u << lane) - 1u));
@@ -989,12 +1009,15 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
   }
   __syncwarp();
   // every gallery row that is not a candidate has an approximate key >= tau (never logged: >= the sweep's final
-  // threshold; logged but not selected: >= the KP-th smallest logged key)
-  const float tau = total > kp ? fminf(tau_min, unsortable(ustar)) : tau_min;
+  // threshold; logged but not selected: >= the selection bound)
+  const float tau = total > kp ? fminf(tau_min, unsortable(ub)) : tau_min;
 
   // ---- exact distances (reference arithmetic): 8 lanes per candidate, 4 candidates per round
   const int self = exclude_self ? int(self_offset + qo) : -1;
   {
+    // (Round 2 tried gathering the rows with 16-byte cp.async into shared memory, eight rows per batch, double-buffered: a
+    // whole 512-byte row per instruction and far more bytes in flight per warp -- and it was SLOWER, 2.9 vs 2.25 ms: the row
+    // buffers halve the resident warps, and reducing from shared memory adds an LDS per element.  gpurun_out/r2_s_bench*.json)
     const int sub = lane & 7, grp = lane >> 3;
     // two independent candidates per lane group and round: twice the loads in flight (the gather is latency-bound:
     // 61% of the stall samples were on the gallery-row loads, profiles/r1_g_rerank.txt)
@@ -1763,12 +1786,15 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   if (phases & kPhaseRerank) {
     const float delta_coeff = delta_coeff_of(p.Dp);
     const int blocks = int((nq + RR_WARPS - 1) / RR_WARPS);
-    const size_t smem = size_t(RR_WARPS) * (size_t(D) + 2 * KP + RR_STAGE) * 4;
+    const int scratch_words = RR_STAGE;               // per-warp scratch: the staged keys of the selection
+    const size_t smem = size_t(RR_WARPS) * (size_t(D) + 2 * KP + scratch_words) * 4;
+    MMSIM_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     knn_rerank_kernel<<<blocks, RR_WARPS * 32, smem, stream>>>(Q, G, int(nq), ng, int(D), log, p.logcap, log_cnt, log_tau,
                                                                p.n_splits, qnorm, qerr, gstats, delta_coeff, shard_kp ? shard_kp : k,
                                                                shard_kp ? shard_kp : KP, exclude_self, self_offset, out_dist,
                                                                out_idx, shard_kp ? out_lb : nullptr, status, unc_query,
-                                                               unc_bound, p.unc_cap, perm, env_int("MMSIM_KNN_FORCE_FALLBACK"));
+                                                               unc_bound, p.unc_cap, perm, env_int("MMSIM_KNN_FORCE_FALLBACK"),
+                                                               scratch_words);
     MMSIM_CUDA_CHECK(::mmsim::launched());
   }
 
