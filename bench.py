@@ -535,18 +535,17 @@ def main():
     # ---- e2e: pinned host buffers in, host result out, every step
     q_host = queries.cpu().pin_memory()
     g_host = sg.shard.cpu().pin_memory()
-    res_d = torch.empty((Q, k), dtype=torch.float32).pin_memory()
-    res_i = torch.empty((Q, k), dtype=out_i.dtype).pin_memory()
+    if world == 1:
+        res_d = torch.empty((Q, k), dtype=torch.float32).pin_memory()
+        res_i = torch.empty((Q, k), dtype=out_i.dtype).pin_memory()
 
     st_e2e = torch.empty(8, dtype=torch.int32, device=dev)
 
     if world > 1:
-        # Device staging buffers that persist across steps, like the workspace: the inputs are copied INTO them every
-        # step.  (A fresh ShardedGallery per step re-allocates its multi-GB workspace from torch's caching allocator,
-        # which fragments and falls back to cudaMalloc / cudaFree erratically: 22 vs 31 ms per step at N = 2,
-        # profiles/r1_i_e2e_sharded_n2.txt.)
-        q_stage = torch.empty_like(queries)
+        # The shard of the end-to-end gallery object is a device STAGING buffer that persists across steps, like the
+        # workspace: retrieve_host copies this rank's rows into it from pinned host memory every step.
         sg_e2e = ShardedGallery(torch.empty_like(sg.shard), presharded=True, row_offset=lo, total_rows=G)
+        e2e_slice = [None]
 
     def step_e2e():
         if world == 1:
@@ -556,11 +555,9 @@ def main():
             # under UVA): the device->host transfer of the result overlaps the kernel instead of following it
             d_, i_, st = knn_raw(qd, gd, k, out=(res_d, res_i, st_e2e))
         else:
-            q_stage.copy_(q_host, non_blocking=True)
-            sg_e2e.shard.copy_(g_host, non_blocking=True)
-            d_, i_ = sg_e2e.retrieve(q_stage, k, check=False)
-            res_d.copy_(d_, non_blocking=True)
-            res_i.copy_(i_, non_blocking=True)
+            # every rank: its gallery shard + its 1/N slice of the queries up (the slices are all-gathered over NVLink, the
+            # shard upload overlaps the query exchange and preparation), its slice of the merged result down
+            d_, i_, e2e_slice[0] = sg_e2e.retrieve_host(q_host, k, gallery_host=g_host)
         return d_, i_
 
     # N = 1: the C-ABI call that takes the HOST buffers (mmsim_knn_host_f32) -- the gallery goes over split by split while
@@ -598,12 +595,21 @@ def main():
     ms_e2e, _ = timed(step_e2e, e2e_steps)
     if world == 1:   # the zero-copy result equals the device-resident one of the timed steps
         assert torch.equal(res_d, out_d.cpu()) and torch.equal(res_i, out_i.cpu()), "e2e result differs from the device result"
+        h2d = int((q_host.numel() + g_host.numel()) * 4)
+        d2h = int(res_d.numel() * 4 + res_i.numel() * res_i.element_size())
+        d2h_how = "re-rank kernel writes the result rows into pinned host memory (zero-copy)"
+    else:            # this rank's slice of the end-to-end result equals the same rows of the device-resident one
+        ed, ei = step_e2e()
+        qlo, qhi = e2e_slice[0]
+        assert torch.equal(ed, out_d[qlo:qhi].cpu()) and torch.equal(ei, out_i[qlo:qhi].cpu()), "e2e result differs from the device result"
+        e2e_path = ("ShardedGallery.retrieve_host: every rank uploads its gallery shard and 1/N of the queries (all-gathered over "
+                    "NVLink; the shard upload overlaps the query exchange and preparation) and downloads its query slice of the result")
+        h2d = int((Q * D + G * D) * 4)              # summed over the ranks: every gallery row and every query once
+        d2h = int(Q * k * 12)                       # ... and every result row once (f32 distance + int64 index)
+        d2h_how = "each rank copies its merged query slice (the slices tile the queries)"
     e2e = {"value": Q * e2e_steps / (ms_e2e / 1e3), "unit": "queries/s",
-           "h2d_bytes_per_step": int((q_host.numel() + g_host.numel()) * 4),
-           "d2h_bytes_per_step": int(res_d.numel() * 4 + res_i.numel() * res_i.element_size()),
-           "ms_per_step": ms_e2e / e2e_steps,
-           "path": e2e_path,
-           "d2h": "re-rank kernel writes the result rows into pinned host memory (zero-copy)" if world == 1 else "copy after the merge"}
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "bytes_are": "summed over all ranks",
+           "ms_per_step": ms_e2e / e2e_steps, "path": e2e_path, "d2h": d2h_how}
 
     # ---- roofline of the dominant kernel (knn_tc_kernel), timed alone on its stream via the phase mask
     tc_reps = max(3, min(a.steps, 10))
@@ -620,44 +626,52 @@ def main():
             phase_ms[name] = m_ / 3
     else:
         # the reduced sharded protocol, stage by stage (same calls ShardedGallery.retrieve makes)
-        from multimodal_similarity_b200.sharded import (ReducedShard, merge_certified_slice, merge_pivots_into, pack_slices,
-                                                        reduced_kp, slice_rows, unpack_merged)
+        from multimodal_similarity_b200.sharded import ReducedShard, merge_certified_slice, merge_pivots_into, reduced_kp, slice_rows
         kp = reduced_kp(world, k)
         rs_ = ReducedShard(sg.shard, lo)
-        packed = torch.empty(ReducedShard.packed_elems(Q, kp), dtype=torch.int32, device=dev)
-        rows = -(-Q // 128) * 128
-        piv = rs_.stage1(queries, k, kp, packed)
-        allpiv = torch.empty((world * rows, 16), dtype=torch.float32, device=dev)
         S = slice_rows(Q, world)
-        send = pack_slices(packed, Q, kp, world)
+        stride = S * (2 * kp + 1)
+        send = torch.empty((world, stride), dtype=torch.int32, device=dev)
+        st_ = torch.empty(8, dtype=torch.int32, device=dev)
+        rows = -(-Q // 128) * 128
+        piv = rs_.stage1(queries, k, kp, send, st_)
+        allpiv = torch.empty((world * rows, 16), dtype=torch.float32, device=dev)
         recv = torch.empty_like(send)
         mine = max(0, min(S, Q - rank * S))
-        res_holder = [merge_certified_slice(recv, sg._bases(dev), 0, S, kp, k)]
-        allres = torch.empty((world, res_holder[0].numel()), dtype=torch.int32, device=dev)
-        views = ReducedShard._views(packed, Q, kp)
+        bases = sg._bases(dev)
+        flat = send.view(-1)
+        views = (flat.view(torch.float32), flat[S * kp:], flat.view(torch.float32)[2 * S * kp:], st_)
+        holder = [None]
+        out_d_f = torch.empty((world * S, k), dtype=torch.float32, device=dev)
+        out_i_f = torch.empty((world * S, k), dtype=torch.int32, device=dev)
+        allmeta = torch.empty((world, S + 8), dtype=torch.int32, device=dev)
 
         def ag_piv():
-            dist.all_gather_into_tensor(allpiv, piv.contiguous())
+            dist.all_gather_into_tensor(allpiv, piv)
             merge_pivots_into(allpiv.view(world, rows, 16), piv)
 
         def a2a_lists():
-            dist.all_to_all_single(recv.view(-1), pack_slices(packed, Q, kp, world).view(-1))
+            dist.all_to_all_single(recv.view(-1), send.view(-1))
 
         def merge_slice():
-            res_holder[0] = merge_certified_slice(recv, sg._bases(dev), mine, S, kp, k)
+            holder[0] = merge_certified_slice(recv, bases, mine, S, kp, k, True)
 
         def ag_res():
-            dist.all_gather_into_tensor(allres.view(-1), res_holder[0])
-            unpack_merged(allres, Q, S, k)
+            d_, i_, m_ = holder[0]
+            dist.all_gather_into_tensor(out_d_f, d_)
+            dist.all_gather_into_tensor(out_i_f, i_)
+            dist.all_gather_into_tensor(allmeta.view(-1), m_)
+            return out_i_f[:Q].to(torch.int64)
 
+        call = lambda ph, sl=0, sd=0: rs_._call(queries, k, kp, False, 0, ph, views, sl, sd)  # noqa: E731
         ag_piv()
-        rs_.stage2(queries, k, kp, False, 0, packed)
+        rs_.stage2(queries, k, kp, False, 0, send, st_, S)
         a2a_lists(); merge_slice(); ag_res()
-        stages = (("prep", lambda: rs_._call(queries, k, kp, False, 0, 1, views)),
-                  ("pivot_prepass", lambda: rs_._call(queries, k, kp, False, 0, 16, views)),
+        stages = (("prep", lambda: call(1)),
+                  ("pivot_prepass", lambda: call(16)),
                   ("allgather_merge_pivots", ag_piv),
-                  ("ladder", lambda: rs_._call(queries, k, kp, False, 0, 32, views)),
-                  ("select_rerank_kp%d" % kp, lambda: rs_._call(queries, k, kp, False, 0, 4, views)),
+                  ("ladder", lambda: call(32)),
+                  ("select_rerank_kp%d" % kp, lambda: call(4, S, stride)),
                   ("alltoall_candidate_lists", a2a_lists),
                   ("merge_certified_slice", merge_slice),
                   ("allgather_merged", ag_res))
@@ -665,7 +679,7 @@ def main():
             fn()
             m_, _ = timed(fn, 3)
             phase_ms[name] = m_ / 3
-        sweep = lambda: rs_._call(queries, k, kp, False, 0, 2, views)  # noqa: E731
+        sweep = lambda: call(2)  # noqa: E731
         sweep()
         ms_tc, _ = timed(sweep, tc_reps)
         ms_tc /= tc_reps

@@ -109,6 +109,8 @@ MMSIM_API int mmsim_knn_f32(const float* Q, int64_t nq, const float* G, int64_t 
 #define MMSIM_KNN_PHASE_PIVOT 16   /* tcgen05 pre-pass over a gallery sample: the 16 smallest sampled keys per query */
 #define MMSIM_KNN_PHASE_LADDER 32  /* pivot list -> threshold ladder (after an optional cross-shard merge of the lists) */
 #define MMSIM_KNN_PHASE_ALL 63
+#define MMSIM_KNN_PHASE_PREP_Q 128 /* mmsim_knn_shard_f32 only: the query half of PREP (operand copies + query grouping) ... */
+#define MMSIM_KNN_PHASE_PREP_G 256 /* ... and the gallery half (operand copies, norm pack), each on its own */
 MMSIM_API int mmsim_knn_f32_phases(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
                          int64_t self_offset, float* out_dist, int32_t* out_idx, int32_t* status, void* ws, size_t ws_bytes,
                          mmsim_stream_t stream, int phases);
@@ -156,10 +158,14 @@ MMSIM_API int mmsim_knn_merge(const float* dist_parts, const int32_t* idx_parts,
  *      those rows of the merged result.  Only if more than `cap` queries are flagged, or its streaming scan has queries
  *      left (status[1] > status[2]), does the caller repeat the whole call with the plain per-shard mmsim_knn_f32 +
  *      mmsim_knn_merge path (multimodal_similarity_b200/sharded.py).
- * kp is the caller's choice (sharded.py: twice the expected share of the 128 best keys per shard plus a margin). */
+ * kp is the caller's choice (sharded.py: twice the expected share of the 128 best keys per shard plus a margin).
+ * slice_rows > 0 (step 3): the re-rank kernel writes query q's row into block q / slice_rows (blocks slice_stride 32-bit
+ * words apart, counted from out_dist / out_idx / out_lb) at row q % slice_rows -- with out_idx = out_dist + slice_rows * kp
+ * and out_lb = out_dist + 2 * slice_rows * kp that is exactly the buffer an all-to-all by query slice sends.
+ * mmsim_knn_merge_certified writes int64 (out_idx_bits 64) or, when every global index fits 31 bits, int32 indices. */
 MMSIM_API int mmsim_knn_shard_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int kp, int exclude_self,
                         int64_t self_offset, float* out_dist, int32_t* out_idx, float* out_lb, int32_t* status, void* ws,
-                        size_t ws_bytes, mmsim_stream_t stream, int phases);
+                        size_t ws_bytes, mmsim_stream_t stream, int phases, int64_t slice_rows, int64_t slice_stride);
 MMSIM_API int mmsim_knn_pivot_region(int64_t nq, int64_t ng, int64_t D, int k, size_t* offset, size_t* bytes);
 /* Introspection (tests): the launch geometry chosen for a problem on a device with num_sms SMs.
  * out[0..12) = padded width, K atoms, 128-query blocks, 256-row gallery tiles, gallery splits, tiles per split, grid,
@@ -171,8 +177,8 @@ MMSIM_API int mmsim_knn_merge_pivots(const float* parts, int nparts, int64_t par
                            mmsim_stream_t stream);
 MMSIM_API int mmsim_knn_merge_certified(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride,
                               const int64_t* idx_base, int parts, int64_t nq, int k_in, int k, const float* lb_parts,
-                              int64_t lb_stride, float* out_dist, int64_t* out_idx, int32_t* status, float* out_flag,
-                              mmsim_stream_t stream);
+                              int64_t lb_stride, float* out_dist, void* out_idx, int out_idx_bits, int32_t* status,
+                              float* out_flag, mmsim_stream_t stream);
 MMSIM_API int mmsim_knn_shard_fallback_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
                                  int64_t self_offset, const float* flag, int cap, float* out_dist, int32_t* out_idx,
                                  int32_t* out_query, int32_t* status, void* ws, size_t ws_bytes, mmsim_stream_t stream);

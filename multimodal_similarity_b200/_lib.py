@@ -38,12 +38,12 @@ SIGNATURES = {
     "mmsim_knn_host_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int64,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mmsim_knn_shard_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int64,
-                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_int]),
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_int64, c_int64]),
     "mmsim_knn_pivot_region": (c_int, [c_int64, c_int64, c_int64, c_int, POINTER(c_size_t), POINTER(c_size_t)]),
     "mmsim_knn_plan": (c_int, [c_int64, c_int64, c_int64, c_int, c_int, POINTER(c_int64), c_int]),
     "mmsim_knn_merge_pivots": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p]),
     "mmsim_knn_merge_certified": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int64, c_int, c_int, c_void_p,
-                                          c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                          c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "mmsim_semihard_mask_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p,
                                         c_void_p]),
     "mmsim_semihard_pick_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p]),

@@ -145,11 +145,12 @@ MMSIM_API int mmsim_evaluate_f32(const float* E, const int32_t* labels, const in
 
 MMSIM_API int mmsim_knn_shard_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int kp, int exclude_self,
                         int64_t self_offset, float* out_dist, int32_t* out_idx, float* out_lb, int32_t* status, void* ws,
-                        size_t ws_bytes, mmsim_stream_t stream, int phases) {
-  MMSIM_REQUIRE(phases > 0 && phases <= knn::kPhaseAll, MMSIM_ERR_ARG, "knn_shard: phases must be a mask in 1..63");
+                        size_t ws_bytes, mmsim_stream_t stream, int phases, int64_t slice_rows, int64_t slice_stride) {
+  MMSIM_REQUIRE(phases > 0 && (phases & ~(knn::kPhaseAll | knn::kPhasePrepQ | knn::kPhasePrepG)) == 0, MMSIM_ERR_ARG,
+                "knn_shard: phases must be a mask of MMSIM_KNN_PHASE_*");
   MMSIM_REQUIRE(kp >= 1 && kp <= knn::KP, MMSIM_ERR_ARG, "knn_shard: kp must be in 1..%d", knn::KP);
   return knn::run(Q, nq, G, ng, D, k, exclude_self, self_offset, out_dist, out_idx, status, ws, ws_bytes,
-                  reinterpret_cast<cudaStream_t>(stream), phases, kp, out_lb);
+                  reinterpret_cast<cudaStream_t>(stream), phases, kp, out_lb, nullptr, slice_rows, slice_stride);
 }
 
 MMSIM_API int mmsim_knn_pivot_region(int64_t nq, int64_t ng, int64_t D, int k, size_t* offset, size_t* bytes) {
@@ -179,10 +180,11 @@ MMSIM_API int mmsim_knn_merge_pivots(const float* parts, int nparts, int64_t par
 
 MMSIM_API int mmsim_knn_merge_certified(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride,
                               const int64_t* idx_base, int parts, int64_t nq, int k_in, int k, const float* lb_parts,
-                              int64_t lb_stride, float* out_dist, int64_t* out_idx, int32_t* status, float* out_flag,
-                              mmsim_stream_t stream) {
+                              int64_t lb_stride, float* out_dist, void* out_idx, int out_idx_bits, int32_t* status,
+                              float* out_flag, mmsim_stream_t stream) {
+  MMSIM_REQUIRE(out_idx_bits == 32 || out_idx_bits == 64, MMSIM_ERR_ARG, "knn_merge_certified: out_idx_bits must be 32 or 64");
   return merge::run(dist_parts, idx_parts, part_stride, idx_base, parts, nq, k_in, k, lb_parts, lb_stride, out_dist, out_idx,
-                    status, reinterpret_cast<cudaStream_t>(stream), out_flag);
+                    status, reinterpret_cast<cudaStream_t>(stream), out_flag, nullptr, nullptr, out_idx_bits == 32);
 }
 
 MMSIM_API int mmsim_semihard_mask_f32(const float* dist, int64_t n, int64_t ld, const int32_t* labels, const int32_t* pairs,

@@ -35,7 +35,8 @@ struct Plan {
 Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, bool host_mode = false);
 
 enum : int { kPhasePrep = 1, kPhaseTensor = 2, kPhaseRerank = 4, kPhaseFallback = 8, kPhasePivot = 16, kPhaseLadder = 32, kPhaseAll = 63,
-             kPhaseFinish = 64 /* one more tier-2 wave of the exact fallback (mmsim_knn_finish_f32); not part of kPhaseAll */ };
+             kPhaseFinish = 64 /* one more tier-2 wave of the exact fallback (mmsim_knn_finish_f32); not part of kPhaseAll */,
+             kPhasePrepQ = 128, kPhasePrepG = 256 /* the two halves of kPhasePrep on their own */ };
 
 // gallery row of sample j (host and device agree: the host-buffer call copies these rows with strided 2-D copies)
 __host__ __device__ inline int64_t sample_row(int64_t j, int div, int seg) {
@@ -52,7 +53,8 @@ struct HostPipe {
 
 int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
         float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream, int phases = kPhaseAll,
-        int shard_kp = 0, float* out_lb = nullptr, const HostPipe* host = nullptr);
+        int shard_kp = 0, float* out_lb = nullptr, const HostPipe* host = nullptr, int64_t slice_rows = 0,
+        int64_t slice_stride = 0);
 
 constexpr int kPivotsPerRow = 16;  // floats per query row in the pivot region of the workspace
 int merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t rows, float* out, cudaStream_t stream);

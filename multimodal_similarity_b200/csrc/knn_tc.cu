@@ -899,7 +899,10 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
                   int* __restrict__ status, int* __restrict__ unc_query, float* __restrict__ unc_bound, int unc_cap,
                   const int* __restrict__ perm /* sweep position -> query (query grouping), or null: identity */,
                   int force_mod /* test hook (MMSIM_KNN_FORCE_FALLBACK=m): every m-th query counts as uncertified */,
-                  int scratch_words /* per-warp scratch: the staged keys of the selection */) {
+                  int scratch_words /* per-warp scratch: the staged keys of the selection */,
+                  int slice_rows, int64_t slice_stride /* gallery-shard mode, slice_rows > 0: query qo's outputs go to block
+                  qo / slice_rows (blocks slice_stride words apart) at row qo % slice_rows -- the layout the all-to-all of the
+                  candidate lists sends, written directly */) {
   // kp <= KP candidates are re-ranked.  out_lb == nullptr: emit the top-k and certify locally (k <= kp).
   // out_lb != nullptr (gallery-shard mode): emit all kp re-ranked candidates (k == kp) plus the lower bound on the
   // true distance of every row of this shard that is NOT among them; the certificate is evaluated after the merge.
@@ -1084,10 +1087,11 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
     }
   }
 
+  const size_t o_row = slice_rows > 0 ? size_t(qo / slice_rows) * size_t(slice_stride) + size_t(qo % slice_rows) * k : size_t(qo) * k;
   for (int r = lane; r < k; r += 32) {
     const float d = sk[r];
-    out_dist[size_t(qo) * k + r] = d;
-    out_idx[size_t(qo) * k + r] = (d < kInf) ? sv[r] : -1;
+    out_dist[o_row + r] = d;
+    out_idx[o_row + r] = (d < kInf) ? sv[r] : -1;
   }
 
   // ---- certificate: lower bound on the true distance of every row that is not a candidate
@@ -1107,7 +1111,7 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
     }
     if (force_mod > 0 && qo % force_mod == 0) lb = -kInf;
     if (out_lb) {
-      out_lb[qo] = lb;
+      out_lb[slice_rows > 0 ? size_t(qo / slice_rows) * size_t(slice_stride) + size_t(qo % slice_rows) : size_t(qo)] = lb;
     } else {
       const float dk = sk[k - 1];
       if (!(dk < lb)) {
@@ -1494,7 +1498,9 @@ int shard_fallback(const float* Q, int64_t nq, const float* G, int64_t ng, int64
 
 int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
         float* out_dist, int* out_idx, int* status, void* ws, size_t ws_bytes, cudaStream_t stream, int phases, int shard_kp,
-        float* out_lb, const HostPipe* host) {
+        float* out_lb, const HostPipe* host, int64_t slice_rows, int64_t slice_stride) {
+  MMSIM_REQUIRE(slice_rows == 0 || (shard_kp != 0 && slice_rows > 0 && slice_stride >= slice_rows * (2 * shard_kp + 1)), MMSIM_ERR_ARG,
+                "knn: the slice layout belongs to gallery-shard mode (stride >= slice_rows * (2 kp + 1))");
   MMSIM_REQUIRE(!host || (phases == kPhaseAll && shard_kp == 0 && host->q_host && host->g_host), MMSIM_ERR_ARG,
                 "knn_host: host-buffer mode runs all phases of an unsharded call");
   MMSIM_REQUIRE(shard_kp == 0 || (out_lb && shard_kp >= 1 && shard_kp <= KP), MMSIM_ERR_ARG,
@@ -1558,7 +1564,10 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   }
 
   // 1. operand copies: fp16 rows, norm pack (+ per-8 / per-32 column minima), rounding-error norms
-  if (phases & kPhasePrep) {
+  // (kPhasePrepG / kPhasePrepQ: the gallery half and the query half on their own -- the sharded end-to-end path prepares the
+  // queries while the gallery shard is still on its way from the host)
+  const bool prep_g = (phases & (kPhasePrep | kPhasePrepG)) != 0, prep_q = (phases & (kPhasePrep | kPhasePrepQ)) != 0;
+  if (prep_g) {
     MMSIM_CUDA_CHECK(cudaMemsetAsync(gstats, 0, 64, stream));
     if (host) {
       // host-buffer mode: the gallery is copied and prepared split by split next to the sweeps (below); only the queries
@@ -1578,6 +1587,8 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
       pack_min_kernel<<<unsigned(p.n_tiles), BN, 0, stream>>>(gpack);
       MMSIM_CUDA_CHECK(::mmsim::launched());
     }
+  }
+  if (prep_q) {
     const unsigned qb = unsigned(std::min<int64_t>((nq + warps_per_block - 1) / warps_per_block, cap));
     prep<<<qb, PREP_THREADS, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, 0, nullptr, nullptr);
     MMSIM_CUDA_CHECK(::mmsim::launched());
@@ -1794,7 +1805,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
                                                                shard_kp ? shard_kp : KP, exclude_self, self_offset, out_dist,
                                                                out_idx, shard_kp ? out_lb : nullptr, status, unc_query,
                                                                unc_bound, p.unc_cap, perm, env_int("MMSIM_KNN_FORCE_FALLBACK"),
-                                                               scratch_words);
+                                                               scratch_words, int(slice_rows), slice_stride);
     MMSIM_CUDA_CHECK(::mmsim::launched());
   }
 

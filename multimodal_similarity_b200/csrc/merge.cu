@@ -21,8 +21,10 @@ __global__ void __launch_bounds__(WARPS * 32)
 knn_merge_kernel(const float* __restrict__ dist_parts, const int* __restrict__ idx_parts,
                  int64_t part_stride, const int64_t* __restrict__ idx_base, int parts, int64_t nq, int k_in, int k, int P,
                  const float* __restrict__ lb_parts, int64_t lb_stride, float* __restrict__ out_dist,
-                 int64_t* __restrict__ out_idx, int* __restrict__ status, float* __restrict__ out_flag,
+                 void* __restrict__ out_idx_v, int idx32, int* __restrict__ status, float* __restrict__ out_flag,
                  const int* __restrict__ count_ptr, const int* __restrict__ row_map) {
+  int64_t* out_idx = static_cast<int64_t*>(out_idx_v);
+  int* out_idx32 = static_cast<int*>(out_idx_v);         // idx32: global indices fit 31 bits (half the bytes on the wire)
   extern __shared__ __align__(8) unsigned char msm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t qi = int64_t(blockIdx.x) * WARPS + warp;
@@ -103,7 +105,8 @@ knn_merge_kernel(const float* __restrict__ dist_parts, const int* __restrict__ i
   for (int r = lane; r < k; r += 32) {
     const bool ok = r < S && sv[r] != 0x7fffffff;
     out_dist[qo * k + r] = ok ? sk[r] : kInf;
-    out_idx[qo * k + r] = ok ? gidx(sv[r]) : -1;
+    const int64_t gi = ok ? gidx(sv[r]) : -1;
+    if (idx32) out_idx32[qo * k + r] = int(gi); else out_idx[qo * k + r] = gi;
   }
   // global certificate of the reduced-candidate protocol: every row a shard did NOT re-rank lies at distance >= that
   // shard's lower bound, so the merged top-k is exact iff its k-th distance is below every shard's bound
@@ -120,8 +123,8 @@ knn_merge_kernel(const float* __restrict__ dist_parts, const int* __restrict__ i
 }
 
 int run(const float* dist_parts, const int* idx_parts, int64_t part_stride, const int64_t* idx_base, int parts, int64_t nq,
-        int k_in, int k, const float* lb_parts, int64_t lb_stride, float* out_dist, int64_t* out_idx, int* status,
-        cudaStream_t s, float* out_flag, const int* count_ptr, const int* row_map) {
+        int k_in, int k, const float* lb_parts, int64_t lb_stride, float* out_dist, void* out_idx, int* status,
+        cudaStream_t s, float* out_flag, const int* count_ptr, const int* row_map, int idx32) {
   MMSIM_REQUIRE(dist_parts && idx_parts && idx_base && out_dist && out_idx, MMSIM_ERR_ARG, "knn_merge: null pointer argument");
   MMSIM_REQUIRE(parts >= 1 && k >= 1 && k_in >= 1 && nq >= 0 && part_stride >= nq * k_in && (!lb_parts || status), MMSIM_ERR_ARG,
                 "knn_merge: bad sizes parts=%d nq=%lld k=%d", parts, (long long)nq, k);
@@ -132,7 +135,7 @@ int run(const float* dist_parts, const int* idx_parts, int64_t part_stride, cons
   const size_t smem = size_t(WARPS) * P * 8;
   MMSIM_CUDA_CHECK(cudaFuncSetAttribute(knn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   knn_merge_kernel<<<unsigned((nq + WARPS - 1) / WARPS), WARPS * 32, smem, s>>>(dist_parts, idx_parts, part_stride, idx_base, parts, nq, k_in, k, P,
-                                                                              lb_parts, lb_stride, out_dist, out_idx, status, out_flag,
+                                                                              lb_parts, lb_stride, out_dist, out_idx, idx32, status, out_flag,
                                                                               count_ptr, row_map);
   MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;

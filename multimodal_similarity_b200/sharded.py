@@ -33,7 +33,7 @@ from . import _lib
 from ._util import is_numpy_like, stream_handle, to_cuda_f32
 from .retrieval import check_status, knn_raw
 
-PH_PREP, PH_TENSOR, PH_RERANK, PH_FALLBACK, PH_PIVOT, PH_LADDER = 1, 2, 4, 8, 16, 32
+PH_PREP, PH_TENSOR, PH_RERANK, PH_FALLBACK, PH_PIVOT, PH_LADDER, PH_PREP_Q, PH_PREP_G = 1, 2, 4, 8, 16, 32, 128, 256
 FALLBACK_CAP = 1024      # uncertified queries repaired one by one per call; beyond that the call repeats as exact-shards
 
 
@@ -87,7 +87,7 @@ class ReducedShard:
                    "mmsim_knn_pivot_region")
         return self.ws[off.value:off.value + nb.value].view(torch.float32).view(-1, 16)
 
-    def _call(self, q, k, kp, exclude_self, self_offset, phases, out):
+    def _call(self, q, k, kp, exclude_self, self_offset, phases, out, slice_rows=0, slice_stride=0):
         lib = _lib.load()
         dev = q.device
         d_, i_, lb_, st_ = out
@@ -95,25 +95,34 @@ class ReducedShard:
             rc = lib.mmsim_knn_shard_f32(q.data_ptr(), q.shape[0], self.shard.data_ptr(), self.shard.shape[0], q.shape[1], k, kp,
                                          int(bool(exclude_self)), int(self_offset - self.lo), d_.data_ptr(), i_.data_ptr(),
                                          lb_.data_ptr(), st_.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
-                                         stream_handle(dev), phases)
+                                         stream_handle(dev), phases, slice_rows, slice_stride)
         _lib.check(rc, "mmsim_knn_shard_f32")
 
-    def stage1(self, q, k, kp, packed):
-        """Operand copies + pivot pre-pass; returns this shard's pivot lists [rows, 16] (a view into the workspace)."""
+    def stage1(self, q, k, kp, send, status, phases=PH_PREP | PH_PIVOT):
+        """Operand copies + pivot pre-pass (or the given part of them); returns this shard's pivot lists [rows, 16] (a view
+        into the workspace; None for an empty shard)."""
         piv = self._ws(q.shape[0], q.shape[1], k)
         if piv is None:
             return None
-        self._call(q, k, kp, False, 0, PH_PREP | PH_PIVOT, self._views(packed, q.shape[0], kp))
+        self._call(q, k, kp, False, 0, phases, (send, send, send, status))     # (these phases write no outputs)
         return piv
 
-    def stage2(self, q, k, kp, exclude_self, self_offset, packed):
-        """Threshold ladder from the (merged) pivot lists, sweep, reduced exact re-rank -> fills `packed`."""
-        nq = q.shape[0]
-        d_, i_, lb_, st_ = self._views(packed, nq, kp)
+    def stage2(self, q, k, kp, exclude_self, self_offset, send, status, S):
+        """Threshold ladder from the (merged) pivot lists, sweep, reduced exact re-rank.  The re-rank kernel writes the
+        candidate lists straight into ``send`` [world, S (2 kp + 1)] int32, the buffer the all-to-all by query slice sends:
+        for every destination rank | distance bits S x kp | shard-local indices S x kp | lower-bound bits S |."""
+        stride = S * (2 * kp + 1)
+        flat = send.view(-1)
         if self.shard.shape[0] == 0:
-            d_.fill_(float("inf")); i_.fill_(-1); lb_.fill_(float("inf"))
+            v = send.view(-1, stride)
+            v[:, :S * kp] = 2139095040            # +inf bits
+            v[:, S * kp:2 * S * kp] = -1
+            v[:, 2 * S * kp:] = 2139095040
+            status.zero_()
             return
-        self._call(q, k, kp, exclude_self, self_offset, PH_LADDER | PH_TENSOR | PH_RERANK, (d_, i_, lb_, st_))
+        d_ = flat.view(torch.float32)
+        self._call(q, k, kp, exclude_self, self_offset, PH_LADDER | PH_TENSOR | PH_RERANK,
+                   (d_, flat[S * kp:], d_[2 * S * kp:], status), S, stride)
 
     def fallback(self, q, k, exclude_self, self_offset, flag, cap):
         """Exact top-k inside this shard for the queries with flag >= 0 (``mmsim_knn_shard_fallback_f32``) -> one int32
@@ -136,19 +145,6 @@ class ReducedShard:
         _lib.check(rc, "mmsim_knn_shard_fallback_f32")
         return buf
 
-    @staticmethod
-    def packed_elems(nq, kp):
-        return 2 * nq * kp + nq + 8
-
-    @staticmethod
-    def _views(packed, nq, kp):
-        """int32 buffer [2*nq*kp + nq + 8]: distance bits | shard-local indices | lower-bound bits | status."""
-        d_ = packed[:nq * kp].view(torch.float32).view(nq, kp)
-        i_ = packed[nq * kp:2 * nq * kp].view(nq, kp)
-        lb_ = packed[2 * nq * kp:2 * nq * kp + nq].view(torch.float32)
-        st_ = packed[2 * nq * kp + nq:]
-        return d_, i_, lb_, st_
-
 
 def merge_pivots_into(piv_parts: torch.Tensor, out: torch.Tensor):
     """[parts, rows, 16] pivot lists -> out [rows, 16]: the 16 smallest of the union (mmsim_knn_merge_pivots)."""
@@ -160,88 +156,36 @@ def merge_pivots_into(piv_parts: torch.Tensor, out: torch.Tensor):
     _lib.check(rc, "mmsim_knn_merge_pivots")
 
 
-def merge_certified(gathered: torch.Tensor, bases: torch.Tensor, nq: int, kp: int, k: int):
-    """[parts, packed_elems] gathered stage-2 buffers -> (dist [Q,k], idx [Q,k] i64, status [8] i32; status[0] = uncertified)."""
-    lib = _lib.load()
-    dev = gathered.device
-    parts, stride = gathered.shape[0], gathered.stride(0)
-    out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    status = torch.zeros(8, dtype=torch.int32, device=dev)
-    flag = torch.empty(nq, dtype=torch.float32, device=dev)
-    base = gathered.data_ptr()
-    with torch.cuda.device(dev):
-        rc = lib.mmsim_knn_merge_certified(base, base + nq * kp * 4, stride, bases.data_ptr(), parts, nq, kp, k,
-                                           base + 2 * nq * kp * 4, stride, out_d.data_ptr(), out_i.data_ptr(),
-                                           status.data_ptr(), flag.data_ptr(), stream_handle(dev))
-    _lib.check(rc, "mmsim_knn_merge_certified")
-    return out_d, out_i, status, flag
-
-
 def slice_rows(nq: int, world: int) -> int:
     """Queries per merge slice: ceil(nq / world) (the last slices may be short or empty)."""
     return -(-nq // world)
 
 
-def pack_slices(packed: torch.Tensor, nq: int, kp: int, world: int) -> torch.Tensor:
-    """Stage-2 buffer of one shard -> [world, S * (2 kp + 1)] int32: for every destination rank j the rows of its query
-    slice as | distance bits S x kp | shard-local indices S x kp | lower-bound bits S | (rows past nq are padding)."""
-    S = slice_rows(nq, world)
-    d_, i_, lb_, _ = ReducedShard._views(packed, nq, kp)
-    out = torch.empty((world, S * (2 * kp + 1)), dtype=torch.int32, device=packed.device)
-    pad = world * S - nq
-    def rows(t, width):
-        t = t.view(torch.int32).reshape(nq, width)
-        if pad:
-            t = torch.cat((t, t.new_zeros((pad, width))))
-        return t.view(world, S * width)
-    out[:, :S * kp] = rows(d_, kp)
-    out[:, S * kp:2 * S * kp] = rows(i_, kp)
-    out[:, 2 * S * kp:] = rows(lb_, 1)
-    return out
-
-
-def merge_certified_slice(recv: torch.Tensor, bases: torch.Tensor, n_rows: int, S: int, kp: int, k: int):
-    """[parts, S * (2 kp + 1)] lists of ONE query slice (what the all-to-all delivers) -> merged
-    | global indices S x k as int64 (2 x int32; first, so they are 8-byte aligned) | distance bits S x k |
-    | flag S (float bits: merged k-th distance of an uncertified query, -1 for a certified one) | status 8 |
-    as one int32 buffer."""
+def merge_certified_slice(recv: torch.Tensor, bases: torch.Tensor, n_rows: int, S: int, kp: int, k: int, idx32: bool):
+    """[parts, S (2 kp + 1)] candidate lists of ONE query slice (what the all-to-all delivers) -> merged
+    (dist [S, k] f32, idx [S, k] int32 or int64 GLOBAL indices, meta [S + 8] int32 = | flag S (float bits: the merged k-th
+    distance of an uncertified query, -1 for a certified one or a row past the slice's end) | status 8 |)."""
     lib = _lib.load()
     dev = recv.device
     parts, stride = recv.shape[0], recv.stride(0)
-    res = torch.zeros(S * k * 3 + S + 8, dtype=torch.int32, device=dev)
-    res[S * k * 3:S * k * 3 + S] = -1082130432     # bits of -1.0f: rows past the slice's end are "certified"
+    out_d = torch.empty((S, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((S, k), dtype=torch.int32 if idx32 else torch.int64, device=dev)
+    meta = torch.zeros(S + 8, dtype=torch.int32, device=dev)
+    meta[:S] = -1082130432                         # bits of -1.0f
     base = recv.data_ptr()
     if n_rows > 0:
         with torch.cuda.device(dev):
             rc = lib.mmsim_knn_merge_certified(base, base + S * kp * 4, stride, bases.data_ptr(), parts, n_rows, kp, k,
-                                               base + 2 * S * kp * 4, stride, res.data_ptr() + S * k * 8, res.data_ptr(),
-                                               res.data_ptr() + (S * k * 3 + S) * 4, res.data_ptr() + S * k * 12,
-                                               stream_handle(dev))
+                                               base + 2 * S * kp * 4, stride, out_d.data_ptr(), out_i.data_ptr(),
+                                               32 if idx32 else 64, meta.data_ptr() + S * 4, meta.data_ptr(), stream_handle(dev))
         _lib.check(rc, "mmsim_knn_merge_certified")
-    return res
-
-
-def unpack_merged(allres: torch.Tensor, nq: int, S: int, k: int):
-    """[world, S * 3 k + S + 8] merged slices -> (dist [nq, k] f32, idx [nq, k] i64, uncertified count tensor,
-    flag [nq] f32)."""
-    world = allres.shape[0]
-    # explicit copies into fresh buffers: the int64 view needs 8-byte aligned rows, and a slice that happens to be a view
-    # of `allres` (odd row pitch) would not have them
-    i = torch.empty((nq, 2 * k), dtype=torch.int32, device=allres.device)
-    i.copy_(allres[:, :S * k * 2].reshape(world * S, 2 * k)[:nq])
-    i = i.view(torch.int64)
-    d = torch.empty((nq, k), dtype=torch.int32, device=allres.device)
-    d.copy_(allres[:, S * k * 2:S * k * 3].reshape(world * S, k)[:nq])
-    d = d.view(torch.float32)
-    flag = allres[:, S * k * 3:S * k * 3 + S].reshape(world * S)[:nq].contiguous().view(torch.float32)
-    return d, i, allres[:, S * k * 3 + S].sum(), flag
+    return out_d, out_i, meta
 
 
 def patch_rows(out_d, out_i, allfb: torch.Tensor, bases: torch.Tensor, cap: int, k: int):
-    """[world, 2 cap k + cap + 8] gathered fallback buffers -> rows of (out_d, out_i) rewritten with the merge of the shards'
-    exact lists (``mmsim_knn_merge_patch``).  Slot -> query map and count are rank 0's (identical on every rank whose shard
-    is not empty; an empty shard contributes +inf lists)."""
+    """[world, 2 cap k + cap + 8] gathered fallback buffers -> rows of (out_d, out_i int64) rewritten with the merge of the
+    shards' exact lists (``mmsim_knn_merge_patch``).  Slot -> query map and count are rank 0's (identical on every rank whose
+    shard is not empty; an empty shard contributes +inf lists)."""
     lib = _lib.load()
     dev = out_d.device
     world, stride = allfb.shape[0], allfb.stride(0)
@@ -286,6 +230,7 @@ class ShardedGallery:
         self.hi = self.lo + int(self.shard.shape[0])
         self.dim = int(gallery.shape[1])
         self._reduced = None
+        self._copy_stream, self._q_all, self._host_out = None, None, None     # retrieve_host: copy stream, staging, pinned results
         self.last_protocol = None
         self.last_uncertified = None      # reduced protocol: device scalar, queries the global certificate did not prove
         self.last_repaired = 0            # ... and how many of them the last call repaired one by one
@@ -337,53 +282,135 @@ class ShardedGallery:
             gathered = packed.unsqueeze(0)
         return self._merge(gathered, self._bases(packed.device), k)
 
-    def _retrieve_reduced(self, q, k, exclude_self, self_offset, check):
-        """Returns (dist, idx), or None when the call has to be repeated as exact-shards (more than FALLBACK_CAP
-        uncertified queries, or a shard's streaming scan still has queries queued)."""
+    def _reduced_slice(self, q, k, exclude_self, self_offset, ready_gallery=None):
+        """Stages of the reduced protocol up to this rank's merged query slice: (dist [S, k], idx [S, k] global, meta).
+        ``ready_gallery``: an event the gallery-dependent work waits for (end-to-end path: the shard is still uploading while
+        the queries are prepared)."""
         nq = q.shape[0]
         kp = reduced_kp(self.world, k)
         if self._reduced is None:
             self._reduced = ReducedShard(self.shard, self.lo)
         rs = self._reduced
         dev = q.device
-        packed = torch.empty(ReducedShard.packed_elems(nq, kp), dtype=torch.int32, device=dev)
-        piv = rs.stage1(q, k, kp, packed)
+        S = slice_rows(nq, self.world)
+        send = torch.empty((self.world, S * (2 * kp + 1)), dtype=torch.int32, device=dev)
+        status = torch.empty(8, dtype=torch.int32, device=dev)
+        if ready_gallery is None:
+            piv = rs.stage1(q, k, kp, send, status)
+        else:
+            rs.stage1(q, k, kp, send, status, phases=PH_PREP_Q)
+            torch.cuda.current_stream(dev).wait_event(ready_gallery)
+            piv = rs.stage1(q, k, kp, send, status, phases=PH_PREP_G | PH_PIVOT)
         rows = -(-nq // 128) * 128
         mine = piv if piv is not None else torch.full((rows, 16), float("inf"), device=dev)
         allpiv = torch.empty((self.world * rows, 16), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(allpiv, mine.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(allpiv, mine, group=self.group)
         if piv is not None:
             merge_pivots_into(allpiv.view(self.world, rows, 16), piv)
-        rs.stage2(q, k, kp, exclude_self, self_offset, packed)
-        # merge by query slice: all-to-all of the candidate lists, merge + certify my slice, all-gather of the results
-        S = slice_rows(nq, self.world)
-        send = pack_slices(packed, nq, kp, self.world)
+        rs.stage2(q, k, kp, exclude_self, self_offset, send, status, S)
+        # merge by query slice: all-to-all of the candidate lists, merge + certify my slice
         recv = torch.empty_like(send)
         dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
-        mine = max(0, min(S, nq - self.rank * S))
-        bases = self._bases(dev)
-        res = merge_certified_slice(recv, bases, mine, S, kp, k)
-        allres = torch.empty((self.world, res.numel()), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(allres.view(-1), res, group=self.group)
-        out_d, out_i, uncertified, flag = unpack_merged(allres, nq, S, k)
+        n_mine = max(0, min(S, nq - self.rank * S))
+        return merge_certified_slice(recv, self._bases(dev), n_mine, S, kp, k, self.total < 2 ** 31) + (S,)
+
+    def _repair(self, q, k, exclude_self, self_offset, out_d, out_i, flag, n_unc):
+        """Per-query repair of the rows the global certificate did not prove (identical decisions on every rank).
+        Returns False when the call has to be repeated as exact-shards."""
+        if n_unc > FALLBACK_CAP:
+            return False
+        dev = q.device
+        fb = self._reduced.fallback(q, k, exclude_self, self_offset, flag, FALLBACK_CAP)
+        allfb = torch.empty((self.world, fb.numel()), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allfb.view(-1), fb, group=self.group)
+        st = allfb[:, 2 * FALLBACK_CAP * k + FALLBACK_CAP:].cpu()
+        if bool((st[:, 1] > st[:, 2]).any()):         # a shard's streaming scan has queries left: identical view on every rank
+            return False
+        patch_rows(out_d, out_i, allfb, self._bases(dev), FALLBACK_CAP, k)
+        self.last_repaired = n_unc
+        return True
+
+    def _retrieve_reduced(self, q, k, exclude_self, self_offset, check):
+        """Returns (dist, idx), or None when the call has to be repeated as exact-shards (more than FALLBACK_CAP
+        uncertified queries, or a shard's streaming scan still has queries queued)."""
+        nq = q.shape[0]
+        dev = q.device
+        my_d, my_i, meta, S = self._reduced_slice(q, k, exclude_self, self_offset)
+        # the merged slices go straight into the final arrays (three all-gathers, no repacking)
+        out_d = torch.empty((self.world * S, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((self.world * S, k), dtype=my_i.dtype, device=dev)
+        allmeta = torch.empty((self.world, S + 8), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(out_d, my_d, group=self.group)
+        dist.all_gather_into_tensor(out_i, my_i, group=self.group)
+        dist.all_gather_into_tensor(allmeta.view(-1), meta, group=self.group)
+        out_d, out_i = out_d[:nq], out_i[:nq]
+        if out_i.dtype != torch.int64:
+            out_i = out_i.to(torch.int64)
+        uncertified = allmeta[:, S].sum()
         self.last_uncertified = uncertified           # device scalar, identical on every rank (part of the gathered buffer)
         if not check:
             return out_d, out_i                       # the caller inspects last_uncertified (bench.py does, after timing)
         n_unc = int(uncertified)
         if n_unc == 0:
             return out_d, out_i
-        if n_unc > FALLBACK_CAP:
+        flag = allmeta[:, :S].reshape(-1)[:nq].contiguous().view(torch.float32)
+        if not self._repair(q, k, exclude_self, self_offset, out_d, out_i, flag, n_unc):
             return None
-        # per-query repair: exact top-k of the uncertified queries inside every shard, all-gather, merge into those rows
-        fb = rs.fallback(q, k, exclude_self, self_offset, flag, FALLBACK_CAP)
-        allfb = torch.empty((self.world, fb.numel()), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(allfb.view(-1), fb, group=self.group)
-        st = allfb[:, 2 * FALLBACK_CAP * k + FALLBACK_CAP:].cpu()
-        if bool((st[:, 1] > st[:, 2]).any()):         # a shard's streaming scan has queries left: identical view on every rank
-            return None
-        patch_rows(out_d, out_i, allfb, bases, FALLBACK_CAP, k)
-        self.last_repaired = n_unc
         return out_d, out_i
+
+    def retrieve_host(self, queries_host, k, *, gallery_host=None, exclude_self=False, self_offset=0):
+        """End-to-end form of ``retrieve`` for inputs in page-locked HOST memory (reduced protocol, CUDA only).
+
+        queries_host   the full [Q, D] float32 query array, the same on every rank (SPMD).  Each rank uploads only ITS 1/world
+                       slice over PCIe; the slices are all-gathered over NVLink.
+        gallery_host   optional: this rank's shard rows in page-locked host memory, uploaded again by this call (the
+                       benchmark's end-to-end contract: every input starts on the host).  The upload runs on a copy stream
+                       while the queries are exchanged, converted and grouped.
+        Returns (dist [n, k] float32, idx [n, k] int64 global indices, (q_lo, q_hi)): THIS rank's query slice of the result in
+        page-locked host memory -- the ranks' slices tile the queries, no rank downloads what another one already has.
+        A query the global certificate cannot prove makes the call fall back to ``retrieve`` (every rank, same decision)."""
+        if self.world == 1 or not self.shard.is_cuda:
+            raise _lib.MmsimError("retrieve_host is the multi-GPU end-to-end path; use retrieval.retrieve_host on one GPU")
+        k = int(k)
+        dev = self.shard.device
+        nq, d = queries_host.shape
+        if d != self.dim:
+            raise ValueError(f"queries are {d}-d but the gallery is {self.dim}-d")
+        S = slice_rows(nq, self.world)
+        q_lo, q_hi = min(nq, self.rank * S), min(nq, self.rank * S + S)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        if self._q_all is None or tuple(self._q_all.shape) != (self.world * S, d):
+            self._q_all = torch.zeros((self.world * S, d), dtype=torch.float32, device=dev)
+        main = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event(); start.record(main)
+        ev_q, ev_g = torch.cuda.Event(), torch.cuda.Event()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(start)          # earlier work on the caller's stream may still read these buffers
+            if q_hi > q_lo:
+                self._q_all[q_lo:q_hi].copy_(queries_host[q_lo:q_hi], non_blocking=True)
+            ev_q.record()
+            if gallery_host is not None:
+                self.shard.copy_(gallery_host, non_blocking=True)
+            ev_g.record()
+        main.wait_event(ev_q)
+        dist.all_gather_into_tensor(self._q_all, self._q_all[self.rank * S:self.rank * S + S], group=self.group)
+        q = self._q_all[:nq]
+        my_d, my_i, meta, S = self._reduced_slice(q, k, exclude_self, self_offset, ready_gallery=ev_g)
+        n = q_hi - q_lo
+        if self._host_out is None or self._host_out[0].shape != (S, k):
+            self._host_out = (torch.empty((S, k), dtype=torch.float32).pin_memory(), torch.empty((S, k), dtype=torch.int64).pin_memory())
+        h_d, h_i = self._host_out
+        h_d[:n].copy_(my_d[:n], non_blocking=True)
+        h_i[:n].copy_(my_i[:n].to(torch.int64), non_blocking=True)      # (widened on the device: 12 k x 100 words)
+        # uncertified queries anywhere?  (a 4-byte all-reduce; the copy above is in flight meanwhile)
+        unc = meta[S:S + 1].clone()
+        dist.all_reduce(unc, group=self.group)
+        self.last_uncertified = unc[0]
+        if int(unc) != 0:                                 # synchronises: the host buffers are complete as well
+            out_d, out_i = self.retrieve(q, k, exclude_self=exclude_self, self_offset=self_offset)
+            return out_d[q_lo:q_hi].cpu(), out_i[q_lo:q_hi].cpu(), (q_lo, q_hi)
+        return h_d[:n], h_i[:n], (q_lo, q_hi)
 
     def retrieve(self, queries, k, *, exclude_self=False, self_offset=0, check=True, protocol="auto"):
         as_numpy = is_numpy_like(queries)

@@ -46,50 +46,53 @@ def test_sharded_gallery_single_process(rs):
 
 
 def _simulate_reduced(g, q, k, R, exclude_self, repair=False):
-    """The reduced sharded protocol with R simulated ranks in one process (collectives replaced by torch.stack).
-    repair=True adds the per-query exact fallback of the uncertified queries and returns the repaired result."""
-    from multimodal_similarity_b200.sharded import (FALLBACK_CAP, ReducedShard, merge_certified, merge_pivots_into, patch_rows,
-                                                    reduced_kp, shard_bounds)
+    """The reduced sharded protocol with R simulated ranks in one process (collectives replaced by torch.stack): pivot
+    pre-pass per shard, merged pivot lists, sweep + reduced re-rank written in the slice-major exchange layout, merge +
+    global certificate per query slice.  repair=True adds the per-query exact fallback of the uncertified queries.
+    Returns ((dist, idx int64, [uncertified], flag), kp)."""
+    from multimodal_similarity_b200.sharded import (FALLBACK_CAP, ReducedShard, merge_certified_slice, merge_pivots_into, patch_rows,
+                                                    reduced_kp, shard_bounds, slice_rows)
     n, nq = g.shape[0], q.shape[0]
     kp = reduced_kp(R, k)
-    shards, packed, pivs, bases = [], [], [], []
+    S = slice_rows(nq, R)
+    shards, sends, stats, pivs, bases = [], [], [], [], []
     for r in range(R):
         lo, hi = shard_bounds(n, R, r)
         shards.append(ReducedShard(g[lo:hi].contiguous(), lo))
-        packed.append(torch.empty(ReducedShard.packed_elems(nq, kp), dtype=torch.int32, device="cuda"))
+        sends.append(torch.empty((R, S * (2 * kp + 1)), dtype=torch.int32, device="cuda"))
+        stats.append(torch.empty(8, dtype=torch.int32, device="cuda"))
         bases.append(lo)
     for r in range(R):
-        pivs.append(shards[r].stage1(q, k, kp, packed[r]))
-    allpiv = torch.stack(pivs)                       # the all-gather
+        pivs.append(shards[r].stage1(q, k, kp, sends[r], stats[r]))
+    allpiv = torch.stack(pivs)                       # the all-gather of the pivot lists
     for r in range(R):
         merge_pivots_into(allpiv, pivs[r])
     for r in range(R):
-        shards[r].stage2(q, k, kp, exclude_self, 0, packed[r])
-    gathered = torch.stack(packed)                   # the second all-gather
-    whole = merge_certified(gathered, torch.tensor(bases, device="cuda"), nq, kp, k)
-    # the production path merges by query slice (all-to-all + all-gather): simulate it and require identical results
-    from multimodal_similarity_b200.sharded import merge_certified_slice, pack_slices, slice_rows, unpack_merged
-    S = slice_rows(nq, R)
-    sends = [pack_slices(packed[r], nq, kp, R) for r in range(R)]
+        shards[r].stage2(q, k, kp, exclude_self, 0, sends[r], stats[r], S)
     bases_t = torch.tensor(bases, device="cuda")
-    res = []
-    for r in range(R):                               # rank r receives slice r of every shard
+    ds, is_, metas = [], [], []
+    for r in range(R):                               # the all-to-all: rank r receives slice r of every shard
         recv = torch.stack([sends[src][r] for src in range(R)])
-        res.append(merge_certified_slice(recv, bases_t, max(0, min(S, nq - r * S)), S, kp, k))
-    sd, si, unc, flag = unpack_merged(torch.stack(res), nq, S, k)
-    assert int(unc) == int(whole[2][0]) and torch.equal(flag, whole[3])
+        d_, i_, m_ = merge_certified_slice(recv, bases_t, max(0, min(S, nq - r * S)), S, kp, k, True)
+        assert i_.dtype == torch.int32
+        ds.append(d_); is_.append(i_); metas.append(m_)
+    sd = torch.cat(ds)[:nq].contiguous()             # the three all-gathers
+    si = torch.cat(is_)[:nq].to(torch.int64)
+    allmeta = torch.stack(metas)
+    flag = allmeta[:, :S].reshape(-1)[:nq].contiguous().view(torch.float32)
+    unc = allmeta[:, S].sum().reshape(1)
     assert int((flag >= 0).sum()) == int(unc)
-    # certified rows agree between the whole-batch merge and the slice merge (uncertified rows too: same kernel)
-    assert torch.equal(sd, whole[0]) and torch.equal(si, whole[1])
+    # the 64-bit index form of the merge gives the same rows
+    d64, i64, _ = merge_certified_slice(torch.stack([sends[src][0] for src in range(R)]), bases_t, min(S, nq), S, kp, k, False)
+    assert i64.dtype == torch.int64 and torch.equal(i64[:min(S, nq)], si[:min(S, nq)]) and torch.equal(d64[:min(S, nq)], sd[:min(S, nq)])
     if repair and int(unc) > 0:
         assert int(unc) <= FALLBACK_CAP
         fbs = [shards[r].fallback(q, k, exclude_self, 0, flag, FALLBACK_CAP) for r in range(R)]
-        allfb = torch.stack(fbs)                     # the third all-gather
+        allfb = torch.stack(fbs)                     # the all-gather of the repair lists
         st = allfb[:, 2 * FALLBACK_CAP * k + FALLBACK_CAP:].cpu()
         assert bool((st[:, 0] == int(unc)).all()) and bool((st[:, 1] == st[:, 2]).all()), st
         patch_rows(sd, si, allfb, bases_t, FALLBACK_CAP, k)
-        return (sd, si, whole[2], flag), kp
-    return whole, kp
+    return (sd, si, unc, flag), kp
 
 
 @pytest.mark.parametrize("R", [2, 4, 8])
@@ -172,6 +175,7 @@ def test_shards_derive_the_same_sweep_order(rs):
     _lib.check(_lib.load().mmsim_knn_workspace_bytes(4200, 15000, 64, 20, ctypes.byref(n)), "ws")
     a.ws = torch.zeros(n.value, dtype=torch.uint8, device="cuda")
     b.ws = torch.full((n.value,), 0x7f, dtype=torch.uint8, device="cuda")
-    pa = a.stage1(q, 20, kp, torch.empty(ReducedShard.packed_elems(4200, kp), dtype=torch.int32, device="cuda")).clone()
-    pb = b.stage1(q, 20, kp, torch.empty(ReducedShard.packed_elems(4200, kp), dtype=torch.int32, device="cuda")).clone()
+    scratch, st = torch.empty(64, dtype=torch.int32, device="cuda"), torch.empty(8, dtype=torch.int32, device="cuda")
+    pa = a.stage1(q, 20, kp, scratch, st).clone()
+    pb = b.stage1(q, 20, kp, scratch, st).clone()
     assert torch.equal(pa, pb)

@@ -96,41 +96,23 @@ def test_shard_bounds_cover_and_partition():
             assert all(lo <= hi for lo, hi in b)
 
 
-def test_slice_packing_roundtrip():
-    """Host-side layout of the reduced protocol's exchange (pure tensor ops, runs on CPU): pack_slices lays every
-    destination rank's query slice out contiguously, unpack_merged reassembles the all-gathered merged slices."""
-    from multimodal_similarity_b200.sharded import ReducedShard, pack_slices, slice_rows, unpack_merged
-    for nq, kp, k, world in ((10, 3, 2, 4), (7, 5, 5, 2), (1, 2, 1, 3), (64, 47, 10, 8)):
-        S = slice_rows(nq, world)
-        packed = torch.zeros(ReducedShard.packed_elems(nq, kp), dtype=torch.int32)
-        d_, i_, lb_, st_ = ReducedShard._views(packed, nq, kp)
-        d_.copy_(torch.arange(nq * kp, dtype=torch.float32).view(nq, kp) + 0.5)
-        i_.copy_(torch.arange(nq * kp, dtype=torch.int32).view(nq, kp) * 3)
-        lb_.copy_(torch.arange(nq, dtype=torch.float32) + 0.25)
-        send = pack_slices(packed, nq, kp, world)
-        assert send.shape == (world, S * (2 * kp + 1))
-        for r in range(world):
-            rows = range(r * S, min(nq, (r + 1) * S))
-            dd = send[r, :S * kp].view(torch.float32).view(S, kp)
-            ii = send[r, S * kp:2 * S * kp].view(S, kp)
-            ll = send[r, 2 * S * kp:].view(torch.float32)
-            for n_, q in enumerate(rows):
-                assert torch.equal(dd[n_], d_[q]) and torch.equal(ii[n_], i_[q]) and ll[n_] == lb_[q]
-        # merged slices as merge_certified_slice lays them out: | idx int64 S x k | dist S x k | flag S | status 8 |
-        allres = torch.zeros((world, S * k * 3 + S + 8), dtype=torch.int32)
-        want_f = torch.where(torch.arange(nq) % 3 == 0, torch.arange(nq, dtype=torch.float32) + 0.5, torch.tensor(-1.0))
-        want_d = torch.arange(nq * k, dtype=torch.float32).view(nq, k)
-        want_i = (torch.arange(nq * k, dtype=torch.int64).view(nq, k) << 33) + 5          # needs all 64 bits
-        for r in range(world):
-            lo, hi = r * S, min(nq, (r + 1) * S)
-            if hi > lo:
-                allres[r, :(hi - lo) * k * 2] = want_i[lo:hi].contiguous().view(torch.int32).reshape(-1)
-                allres[r, S * k * 2:S * k * 2 + (hi - lo) * k] = want_d[lo:hi].contiguous().view(torch.int32).reshape(-1)
-                allres[r, S * k * 3:S * k * 3 + (hi - lo)] = want_f[lo:hi].contiguous().view(torch.int32)
-            allres[r, S * k * 3 + S] = r                                                    # uncertified count of the slice
-        got_d, got_i, unc, got_f = unpack_merged(allres, nq, S, k)
-        assert torch.equal(got_d, want_d) and torch.equal(got_i, want_i) and int(unc) == sum(range(world))
-        assert torch.equal(got_f, want_f)
+def test_slice_layout_addresses():
+    """Host-side arithmetic of the reduced protocol's exchange buffer (what mmsim_knn_shard_f32 writes with slice_rows > 0 and
+    the all-to-all sends): query q lives in block q // S at row q % S; the blocks of all ranks tile the padded query range."""
+    from multimodal_similarity_b200.sharded import reduced_kp, slice_rows
+    for nq, world, k in ((10, 4, 2), (7, 2, 5), (1, 3, 1), (100000, 8, 100)):
+        S, kp = slice_rows(nq, world), reduced_kp(world, k)
+        assert world * S >= nq and (S - 1) * world < nq
+        stride = S * (2 * kp + 1)
+        seen = set()
+        for q in (0, nq // 2, nq - 1):
+            blk, row = divmod(q, S)
+            assert blk < world
+            d0, i0, lb = blk * stride + row * kp, blk * stride + S * kp + row * kp, blk * stride + 2 * S * kp + row
+            assert d0 + kp <= blk * stride + S * kp < i0 + kp <= blk * stride + 2 * S * kp <= lb < (blk + 1) * stride
+            seen.add((blk, row))
+        assert len(seen) == len({0, nq // 2, nq - 1})
+        assert 1 <= kp <= 128 and (world == 1 or kp < 128 or k > 100)
 
 
 def test_presharded_rows_must_follow_shard_bounds():
