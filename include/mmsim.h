@@ -181,7 +181,19 @@ MMSIM_API int mmsim_knn_merge_certified(const float* dist_parts, const int32_t* 
                               float* out_flag, mmsim_stream_t stream);
 MMSIM_API int mmsim_knn_shard_fallback_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
                                  int64_t self_offset, const float* flag, int cap, float* out_dist, int32_t* out_idx,
-                                 int32_t* out_query, int32_t* status, void* ws, size_t ws_bytes, mmsim_stream_t stream);
+                                 int32_t* out_query, int32_t* status, void* ws, size_t ws_bytes, mmsim_stream_t stream,
+                                 int host_layout /* != 0: the workspace was filled through mmsim_knn_shard_host_f32 */);
+/* mmsim_knn_shard_f32 for a shard whose rows live in HOST memory (page-locked g_host[ng*D]; g_stage[ng*D] is the device
+ * buffer for the float32 copy): Q is on the device already.  The call with MMSIM_KNN_PHASE_PREP_G queues EVERY host->device
+ * copy of the shard on an internal copy stream -- the 1/61 sample the pivot pre-pass needs first, then the rows split by
+ * split, each split converted as it lands -- and returns; the later phases (PIVOT, then LADDER | TENSOR | RERANK after the
+ * pivot exchange) wait only for the pieces they read, so the upload runs under the query preparation, the exchange of the
+ * pivot lists and the sweeps of the earlier splits.  Workspace: mmsim_knn_host_workspace_bytes; all phases of one
+ * retrieval must go through this entry point (the two layouts differ). */
+MMSIM_API int mmsim_knn_shard_host_f32(const float* Q, int64_t nq, const float* g_host, float* g_stage, int64_t ng, int64_t D, int k,
+                             int kp, int exclude_self, int64_t self_offset, float* out_dist, int32_t* out_idx, float* out_lb,
+                             int32_t* status, void* ws, size_t ws_bytes, mmsim_stream_t stream, int phases, int64_t slice_rows,
+                             int64_t slice_stride);
 /* rows row_map[s] (s < min(*count, cap); count and row_map on the device) of out_dist / out_idx [*, k] = merge of the
  * `parts` compact lists of slot s (layout as mmsim_knn_merge with nq = cap) */
 MMSIM_API int mmsim_knn_merge_patch(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride, const int64_t* idx_base,

@@ -117,9 +117,10 @@ MMSIM_API int mmsim_knn_finish_f32(const float* Q, int64_t nq, const float* G, i
 
 MMSIM_API int mmsim_knn_shard_fallback_f32(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self,
                                  int64_t self_offset, const float* flag, int cap, float* out_dist, int32_t* out_idx,
-                                 int32_t* out_query, int32_t* status, void* ws, size_t ws_bytes, mmsim_stream_t stream) {
+                                 int32_t* out_query, int32_t* status, void* ws, size_t ws_bytes, mmsim_stream_t stream,
+                                 int host_layout) {
   return knn::shard_fallback(Q, nq, G, ng, D, k, exclude_self, self_offset, flag, cap, out_dist, out_idx, out_query, status, ws,
-                             ws_bytes, reinterpret_cast<cudaStream_t>(stream));
+                             ws_bytes, reinterpret_cast<cudaStream_t>(stream), host_layout != 0);
 }
 
 MMSIM_API int mmsim_knn_merge_patch(const float* dist_parts, const int32_t* idx_parts, int64_t part_stride, const int64_t* idx_base,
@@ -151,6 +152,19 @@ MMSIM_API int mmsim_knn_shard_f32(const float* Q, int64_t nq, const float* G, in
   MMSIM_REQUIRE(kp >= 1 && kp <= knn::KP, MMSIM_ERR_ARG, "knn_shard: kp must be in 1..%d", knn::KP);
   return knn::run(Q, nq, G, ng, D, k, exclude_self, self_offset, out_dist, out_idx, status, ws, ws_bytes,
                   reinterpret_cast<cudaStream_t>(stream), phases, kp, out_lb, nullptr, slice_rows, slice_stride);
+}
+
+MMSIM_API int mmsim_knn_shard_host_f32(const float* Q, int64_t nq, const float* g_host, float* g_stage, int64_t ng, int64_t D, int k,
+                             int kp, int exclude_self, int64_t self_offset, float* out_dist, int32_t* out_idx, float* out_lb,
+                             int32_t* status, void* ws, size_t ws_bytes, mmsim_stream_t stream, int phases, int64_t slice_rows,
+                             int64_t slice_stride) {
+  MMSIM_REQUIRE(g_host && g_stage, MMSIM_ERR_ARG, "knn_shard_host: null host gallery or staging pointer");
+  MMSIM_REQUIRE(phases > 0 && (phases & ~(knn::kPhaseAll | knn::kPhasePrepQ | knn::kPhasePrepG)) == 0, MMSIM_ERR_ARG,
+                "knn_shard_host: phases must be a mask of MMSIM_KNN_PHASE_*");
+  MMSIM_REQUIRE(kp >= 1 && kp <= knn::KP, MMSIM_ERR_ARG, "knn_shard_host: kp must be in 1..%d", knn::KP);
+  const knn::HostPipe hp{nullptr, g_host};
+  return knn::run(Q, nq, g_stage, ng, D, k, exclude_self, self_offset, out_dist, out_idx, status, ws, ws_bytes,
+                  reinterpret_cast<cudaStream_t>(stream), phases, kp, out_lb, &hp, slice_rows, slice_stride);
 }
 
 MMSIM_API int mmsim_knn_pivot_region(int64_t nq, int64_t ng, int64_t D, int k, size_t* offset, size_t* bytes) {

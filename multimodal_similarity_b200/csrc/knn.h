@@ -66,7 +66,7 @@ int merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t ro
 // cap: nothing beyond cap is computed), status[1] - status[2] = tier-2 queries still pending (see knn_fallback.cuh).
 int shard_fallback(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
                    const float* flag, int cap, float* out_dist, int* out_idx, int* out_query, int* status, void* ws,
-                   size_t ws_bytes, cudaStream_t stream);
+                   size_t ws_bytes, cudaStream_t stream, bool host_layout = false /* the workspace was filled by host-buffer calls */);
 
 }  // namespace knn
 }  // namespace mmsim

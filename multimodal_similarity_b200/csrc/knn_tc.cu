@@ -1477,14 +1477,14 @@ static int run_fallback(const Plan& p, uint8_t* w, const float* Q, const float* 
 
 int shard_fallback(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k, int exclude_self, int64_t self_offset,
                    const float* flag, int cap, float* out_dist, int* out_idx, int* out_query, int* status, void* ws,
-                   size_t ws_bytes, cudaStream_t stream) {
+                   size_t ws_bytes, cudaStream_t stream, bool host_layout) {
   MMSIM_REQUIRE(Q && G && flag && out_dist && out_idx && out_query && status && ws, MMSIM_ERR_ARG, "knn_shard_fallback: null pointer argument");
   MMSIM_REQUIRE(nq > 0 && ng > 0 && D > 0 && D <= 4 * KATOM && k >= 1 && k <= KP && cap >= 1, MMSIM_ERR_ARG,
                 "knn_shard_fallback: bad sizes");
   int dev = 0, num_sms = 0;
   MMSIM_CUDA_CHECK(cudaGetDevice(&dev));
   MMSIM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  const Plan p = make_plan(nq, ng, D, k, num_sms, false);
+  const Plan p = make_plan(nq, ng, D, k, num_sms, host_layout);
   MMSIM_REQUIRE(ws_bytes >= p.total_bytes, MMSIM_ERR_WORKSPACE, "knn_shard_fallback: workspace too small (%zu < %zu)", ws_bytes,
                 p.total_bytes);
   uint8_t* w = static_cast<uint8_t*>(ws);
@@ -1501,8 +1501,10 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
         float* out_lb, const HostPipe* host, int64_t slice_rows, int64_t slice_stride) {
   MMSIM_REQUIRE(slice_rows == 0 || (shard_kp != 0 && slice_rows > 0 && slice_stride >= slice_rows * (2 * shard_kp + 1)), MMSIM_ERR_ARG,
                 "knn: the slice layout belongs to gallery-shard mode (stride >= slice_rows * (2 kp + 1))");
-  MMSIM_REQUIRE(!host || (phases == kPhaseAll && shard_kp == 0 && host->q_host && host->g_host), MMSIM_ERR_ARG,
-                "knn_host: host-buffer mode runs all phases of an unsharded call");
+  // host-buffer mode: the gallery always comes from the host; the queries too (unsharded call: all phases at once), or they
+  // are on the device already (gallery-shard mode: phases as the sharded protocol needs them, kPhasePrepG first)
+  MMSIM_REQUIRE(!host || (host->g_host && (host->q_host ? (phases == kPhaseAll && shard_kp == 0) : shard_kp != 0)), MMSIM_ERR_ARG,
+                "knn_host: host-buffer mode needs the host gallery, and either host queries (all phases, unsharded) or shard mode");
   MMSIM_REQUIRE(shard_kp == 0 || (out_lb && shard_kp >= 1 && shard_kp <= KP), MMSIM_ERR_ARG,
                 "knn: shard mode needs out_lb and 1 <= kp <= %d", KP);
   MMSIM_REQUIRE(Q && G && out_dist && out_idx && status && ws, MMSIM_ERR_ARG, "knn: null pointer argument");
@@ -1570,14 +1572,47 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   if (prep_g) {
     MMSIM_CUDA_CHECK(cudaMemsetAsync(gstats, 0, 64, stream));
     if (host) {
-      // host-buffer mode: the gallery is copied and prepared split by split next to the sweeps (below); only the queries
-      // are needed now.  Everything queued earlier on the caller's stream -- a previous call still reading the staging
-      // buffers or this workspace -- precedes the copies.
+      // host-buffer mode: EVERY host -> device copy of the call is queued here, on the copy stream, in the order the
+      // kernels need the data: the queries (unsharded call), the gallery sample of the pivot pre-pass (strided 2-D copies:
+      // the pre-pass, and with it the first sweep, does not wait for the gallery), then the gallery split by split, each
+      // split converted on the prep stream as it lands.  The phases below only wait for the events.  Everything queued
+      // earlier on the caller's stream -- a previous call still reading the staging buffers or this workspace -- precedes
+      // the copies.
       MMSIM_CUDA_CHECK(cudaEventRecord(ps->start, stream));
       MMSIM_CUDA_CHECK(cudaStreamWaitEvent(ps->copy, ps->start, 0));
-      MMSIM_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(Q), host->q_host, size_t(nq) * D * 4, cudaMemcpyHostToDevice, ps->copy));
-      MMSIM_CUDA_CHECK(cudaEventRecord(ps->q_in, ps->copy));
-      MMSIM_CUDA_CHECK(cudaStreamWaitEvent(stream, ps->q_in, 0));
+      if (host->q_host) {
+        MMSIM_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(Q), host->q_host, size_t(nq) * D * 4, cudaMemcpyHostToDevice, ps->copy));
+        MMSIM_CUDA_CHECK(cudaEventRecord(ps->q_in, ps->copy));
+        MMSIM_CUDA_CHECK(cudaStreamWaitEvent(stream, ps->q_in, 0));
+      }
+      if (p.use_pivots) {
+        for (int64_t j0 = 0; j0 < p.n_sample; j0 += p.sample_seg) {
+          const int64_t j1 = std::min<int64_t>(p.n_sample, j0 + p.sample_seg);
+          MMSIM_CUDA_CHECK(cudaMemcpy2DAsync(s32 + size_t(j0) * D, size_t(D) * 4, host->g_host + size_t(sample_row(j0, p.sample_div, p.sample_seg)) * D,
+                                             size_t(p.sample_div) * D * 4, size_t(D) * 4, size_t(j1 - j0), cudaMemcpyHostToDevice,
+                                             ps->copy));
+        }
+        MMSIM_CUDA_CHECK(cudaEventRecord(ps->sample_in, ps->copy));
+      }
+      const int n_chunks = p.sweepq ? p.host_splits : p.n_splits;
+      const int tpc = p.sweepq ? (p.n_tiles + n_chunks - 1) / n_chunks : p.tiles_per_split;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int64_t t0 = int64_t(c) * tpc, t1 = std::min<int64_t>(p.n_tiles, t0 + tpc);
+        if (t0 >= t1) break;
+        const int64_t r0 = t0 * BN, r1 = std::min<int64_t>(ng, t1 * BN), r_pad = t1 * BN - r0;
+        MMSIM_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(G) + size_t(r0) * D, host->g_host + size_t(r0) * D,
+                                         size_t(r1 - r0) * D * 4, cudaMemcpyHostToDevice, ps->copy));
+        MMSIM_CUDA_CHECK(cudaEventRecord(ps->chunk_in[c], ps->copy));
+        MMSIM_CUDA_CHECK(cudaStreamWaitEvent(ps->prep, ps->chunk_in[c], 0));
+        const unsigned gb = unsigned(std::min<int64_t>((r_pad + warps_per_block - 1) / warps_per_block, cap));
+        prep<<<gb, PREP_THREADS, 0, ps->prep>>>(G + size_t(r0) * D, r1 - r0, r_pad, int(D), p.Dp, 1.0f, gh + size_t(r0) * p.Dp,
+                                                gpack + size_t(t0) * NPACK, nullptr, 1,
+                                                reinterpret_cast<unsigned int*>(gstats), nullptr);
+        MMSIM_CUDA_CHECK(::mmsim::launched());
+        pack_min_kernel<<<unsigned(t1 - t0), BN, 0, ps->prep>>>(gpack + size_t(t0) * NPACK);
+        MMSIM_CUDA_CHECK(::mmsim::launched());
+        MMSIM_CUDA_CHECK(cudaEventRecord(ps->chunk_ready[c], ps->prep));
+      }
     } else {
       const int64_t g_pad = int64_t(p.n_tiles) * BN;
       const unsigned gb = unsigned(std::min<int64_t>((g_pad + warps_per_block - 1) / warps_per_block, cap));
@@ -1664,14 +1699,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
       const int64_t s_pad = int64_t(p.n_sample_tiles) * BN;
       const unsigned sb = unsigned(std::min<int64_t>((s_pad + warps_per_block - 1) / warps_per_block, cap));
       if (host) {
-        for (int64_t j0 = 0; j0 < p.n_sample; j0 += p.sample_seg) {
-          const int64_t j1 = std::min<int64_t>(p.n_sample, j0 + p.sample_seg);
-          MMSIM_CUDA_CHECK(cudaMemcpy2DAsync(s32 + size_t(j0) * D, size_t(D) * 4, host->g_host + size_t(sample_row(j0, p.sample_div, p.sample_seg)) * D,
-                                             size_t(p.sample_div) * D * 4, size_t(D) * 4, size_t(j1 - j0), cudaMemcpyHostToDevice,
-                                             ps->copy));
-        }
-        MMSIM_CUDA_CHECK(cudaEventRecord(ps->sample_in, ps->copy));
-        MMSIM_CUDA_CHECK(cudaStreamWaitEvent(stream, ps->sample_in, 0));
+        MMSIM_CUDA_CHECK(cudaStreamWaitEvent(stream, ps->sample_in, 0));       // (copied by the kPhasePrep block)
         prep<<<sb, PREP_THREADS, 0, stream>>>(s32, p.n_sample, s_pad, int(D), p.Dp, 1.0f, sh, spack, nullptr, 1, nullptr, nullptr);
       } else {
         sample_index_kernel<<<unsigned((p.n_sample + 255) / 256), 256, 0, stream>>>(sidx, p.n_sample, p.sample_div, p.sample_seg);
@@ -1720,9 +1748,10 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
         return launch_sweepq(p.katoms, std::min(num_sms, (t1 - t0) * sa.n_qchunks), tq, tg, sa, x);
       };
       if (host) {
-        // host-buffer mode: one launch per gallery split.  Split c's rows are copied (copy stream), converted (prep
-        // stream) and swept while the copy of split c + 1 is in flight; the sweeps alternate between the caller's stream
-        // and a second one so that the CTAs of the next sweep fill the SMs the last wave of the previous one leaves idle.
+        // host-buffer mode: one launch per gallery split.  Split c's rows were queued for copy (copy stream) and conversion
+        // (prep stream) by the kPhasePrep block; it is swept while the copy of split c + 1 is in flight.  The sweeps alternate
+        // between the caller's stream and a second one so that the CTAs of the next sweep fill the SMs the last wave of the
+        // previous one leaves idle.
         MMSIM_CUDA_CHECK(cudaEventRecord(ps->ladder, stream));
         bool used2 = false;
         const char* e1 = getenv("MMSIM_HOST_ONE_STREAM");   // experiment switch: every sweep on the caller's stream
@@ -1732,19 +1761,6 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
         for (int c = 0; c < n_chunks; ++c) {
           const int64_t t0 = int64_t(c) * tpc, t1 = std::min<int64_t>(p.n_tiles, t0 + tpc);
           if (t0 >= t1) break;
-          const int64_t r0 = t0 * BN, r1 = std::min<int64_t>(ng, t1 * BN), r_pad = t1 * BN - r0;
-          MMSIM_CUDA_CHECK(cudaMemcpyAsync(const_cast<float*>(G) + size_t(r0) * D, host->g_host + size_t(r0) * D,
-                                           size_t(r1 - r0) * D * 4, cudaMemcpyHostToDevice, ps->copy));
-          MMSIM_CUDA_CHECK(cudaEventRecord(ps->chunk_in[c], ps->copy));
-          MMSIM_CUDA_CHECK(cudaStreamWaitEvent(ps->prep, ps->chunk_in[c], 0));
-          const unsigned gb = unsigned(std::min<int64_t>((r_pad + warps_per_block - 1) / warps_per_block, cap));
-          prep<<<gb, PREP_THREADS, 0, ps->prep>>>(G + size_t(r0) * D, r1 - r0, r_pad, int(D), p.Dp, 1.0f, gh + size_t(r0) * p.Dp,
-                                                  gpack + size_t(t0) * NPACK, nullptr, 1,
-                                                  reinterpret_cast<unsigned int*>(gstats), nullptr);
-          MMSIM_CUDA_CHECK(::mmsim::launched());
-          pack_min_kernel<<<unsigned(t1 - t0), BN, 0, ps->prep>>>(gpack + size_t(t0) * NPACK);
-          MMSIM_CUDA_CHECK(::mmsim::launched());
-          MMSIM_CUDA_CHECK(cudaEventRecord(ps->chunk_ready[c], ps->prep));
           cudaStream_t x = (c & 1) && !one_stream ? ps->sweep2 : stream;
           if (x != stream && !used2) {
             MMSIM_CUDA_CHECK(cudaStreamWaitEvent(x, ps->ladder, 0));

@@ -70,8 +70,11 @@ def merge_parts(dist_parts: torch.Tensor, idx_parts: torch.Tensor, idx_base: tor
 class ReducedShard:
     """State of one shard in the reduced protocol (its own workspace: the pivot lists live inside it)."""
 
-    def __init__(self, shard: torch.Tensor, lo: int):
+    def __init__(self, shard: torch.Tensor, lo: int, gallery_host: torch.Tensor | None = None):
+        """gallery_host: the shard's rows in page-locked host memory -- every retrieval uploads them again, in pieces, under
+        the rest of the pipeline (``mmsim_knn_shard_host_f32``); ``shard`` is then only the device staging buffer."""
         self.shard, self.lo = shard, lo
+        self.gallery_host = gallery_host
         self.ws = None
 
     def _ws(self, nq, d, k):
@@ -79,7 +82,8 @@ class ReducedShard:
         n = ctypes.c_size_t()
         if self.shard.shape[0] == 0:       # an empty shard (more ranks than ceil-sized blocks) has no workspace and no lists
             return None
-        _lib.check(lib.mmsim_knn_workspace_bytes(nq, self.shard.shape[0], d, k, ctypes.byref(n)), "mmsim_knn_workspace_bytes")
+        size_fn = lib.mmsim_knn_workspace_bytes if self.gallery_host is None else lib.mmsim_knn_host_workspace_bytes
+        _lib.check(size_fn(nq, self.shard.shape[0], d, k, ctypes.byref(n)), "mmsim_knn_workspace_bytes")
         if self.ws is None or self.ws.numel() < n.value:
             self.ws = torch.empty(n.value, dtype=torch.uint8, device=self.shard.device)
         off, nb = ctypes.c_size_t(), ctypes.c_size_t()
@@ -92,10 +96,17 @@ class ReducedShard:
         dev = q.device
         d_, i_, lb_, st_ = out
         with torch.cuda.device(dev):
-            rc = lib.mmsim_knn_shard_f32(q.data_ptr(), q.shape[0], self.shard.data_ptr(), self.shard.shape[0], q.shape[1], k, kp,
-                                         int(bool(exclude_self)), int(self_offset - self.lo), d_.data_ptr(), i_.data_ptr(),
-                                         lb_.data_ptr(), st_.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
-                                         stream_handle(dev), phases, slice_rows, slice_stride)
+            if self.gallery_host is None:
+                rc = lib.mmsim_knn_shard_f32(q.data_ptr(), q.shape[0], self.shard.data_ptr(), self.shard.shape[0], q.shape[1], k, kp,
+                                             int(bool(exclude_self)), int(self_offset - self.lo), d_.data_ptr(), i_.data_ptr(),
+                                             lb_.data_ptr(), st_.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+                                             stream_handle(dev), phases, slice_rows, slice_stride)
+            else:
+                rc = lib.mmsim_knn_shard_host_f32(q.data_ptr(), q.shape[0], self.gallery_host.data_ptr(), self.shard.data_ptr(),
+                                                  self.shard.shape[0], q.shape[1], k, kp, int(bool(exclude_self)),
+                                                  int(self_offset - self.lo), d_.data_ptr(), i_.data_ptr(), lb_.data_ptr(),
+                                                  st_.data_ptr(), self.ws.data_ptr(), self.ws.numel(), stream_handle(dev), phases,
+                                                  slice_rows, slice_stride)
         _lib.check(rc, "mmsim_knn_shard_f32")
 
     def stage1(self, q, k, kp, send, status, phases=PH_PREP | PH_PIVOT):
@@ -141,7 +152,7 @@ class ReducedShard:
             rc = lib.mmsim_knn_shard_fallback_f32(q.data_ptr(), q.shape[0], self.shard.data_ptr(), self.shard.shape[0], q.shape[1], k,
                                                   int(bool(exclude_self)), int(self_offset - self.lo), flag.data_ptr(), cap,
                                                   d_.data_ptr(), i_.data_ptr(), qq.data_ptr(), st.data_ptr(), self.ws.data_ptr(),
-                                                  self.ws.numel(), stream_handle(dev))
+                                                  self.ws.numel(), stream_handle(dev), int(self.gallery_host is not None))
         _lib.check(rc, "mmsim_knn_shard_fallback_f32")
         return buf
 
@@ -231,6 +242,7 @@ class ShardedGallery:
         self.dim = int(gallery.shape[1])
         self._reduced = None
         self._copy_stream, self._q_all, self._host_out = None, None, None     # retrieve_host: copy stream, staging, pinned results
+        self._reduced_host = None                                              # ... and the shard state fed from host memory
         self.last_protocol = None
         self.last_uncertified = None      # reduced protocol: device scalar, queries the global certificate did not prove
         self.last_repaired = 0            # ... and how many of them the last call repaired one by one
@@ -282,25 +294,21 @@ class ShardedGallery:
             gathered = packed.unsqueeze(0)
         return self._merge(gathered, self._bases(packed.device), k)
 
-    def _reduced_slice(self, q, k, exclude_self, self_offset, ready_gallery=None):
+    def _reduced_slice(self, q, k, exclude_self, self_offset, rs=None, gallery_queued=False):
         """Stages of the reduced protocol up to this rank's merged query slice: (dist [S, k], idx [S, k] global, meta).
-        ``ready_gallery``: an event the gallery-dependent work waits for (end-to-end path: the shard is still uploading while
-        the queries are prepared)."""
+        ``rs``: the shard state to use (end-to-end path: one whose gallery rows come from the host; its gallery copies were
+        queued by the caller already -- ``gallery_queued`` -- so only the query half of the preparation is left)."""
         nq = q.shape[0]
         kp = reduced_kp(self.world, k)
-        if self._reduced is None:
-            self._reduced = ReducedShard(self.shard, self.lo)
-        rs = self._reduced
+        if rs is None:
+            if self._reduced is None:
+                self._reduced = ReducedShard(self.shard, self.lo)
+            rs = self._reduced
         dev = q.device
         S = slice_rows(nq, self.world)
         send = torch.empty((self.world, S * (2 * kp + 1)), dtype=torch.int32, device=dev)
         status = torch.empty(8, dtype=torch.int32, device=dev)
-        if ready_gallery is None:
-            piv = rs.stage1(q, k, kp, send, status)
-        else:
-            rs.stage1(q, k, kp, send, status, phases=PH_PREP_Q)
-            torch.cuda.current_stream(dev).wait_event(ready_gallery)
-            piv = rs.stage1(q, k, kp, send, status, phases=PH_PREP_G | PH_PIVOT)
+        piv = rs.stage1(q, k, kp, send, status, phases=(PH_PREP_Q if gallery_queued else PH_PREP) | PH_PIVOT)
         rows = -(-nq // 128) * 128
         mine = piv if piv is not None else torch.full((rows, 16), float("inf"), device=dev)
         allpiv = torch.empty((self.world * rows, 16), dtype=torch.float32, device=dev)
@@ -364,8 +372,9 @@ class ShardedGallery:
         queries_host   the full [Q, D] float32 query array, the same on every rank (SPMD).  Each rank uploads only ITS 1/world
                        slice over PCIe; the slices are all-gathered over NVLink.
         gallery_host   optional: this rank's shard rows in page-locked host memory, uploaded again by this call (the
-                       benchmark's end-to-end contract: every input starts on the host).  The upload runs on a copy stream
-                       while the queries are exchanged, converted and grouped.
+                       benchmark's end-to-end contract: every input starts on the host).  The library copies it in pieces on
+                       its own stream (``mmsim_knn_shard_host_f32``): the pivot sample first, then split by split, under the
+                       query exchange, the query preparation and the sweeps of the earlier splits.
         Returns (dist [n, k] float32, idx [n, k] int64 global indices, (q_lo, q_hi)): THIS rank's query slice of the result in
         page-locked host memory -- the ranks' slices tile the queries, no rank downloads what another one already has.
         A query the global certificate cannot prove makes the call fall back to ``retrieve`` (every rank, same decision)."""
@@ -378,25 +387,33 @@ class ShardedGallery:
             raise ValueError(f"queries are {d}-d but the gallery is {self.dim}-d")
         S = slice_rows(nq, self.world)
         q_lo, q_hi = min(nq, self.rank * S), min(nq, self.rank * S + S)
+        if gallery_host is not None and (self._reduced_host is None or self._reduced_host.gallery_host is not gallery_host):
+            self._reduced_host = ReducedShard(self.shard, self.lo, gallery_host)
+        rs = self._reduced_host if gallery_host is not None else None
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(dev)
         if self._q_all is None or tuple(self._q_all.shape) != (self.world * S, d):
             self._q_all = torch.zeros((self.world * S, d), dtype=torch.float32, device=dev)
         main = torch.cuda.current_stream(dev)
         start = torch.cuda.Event(); start.record(main)
-        ev_q, ev_g = torch.cuda.Event(), torch.cuda.Event()
+        ev_q = torch.cuda.Event()
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(start)          # earlier work on the caller's stream may still read these buffers
             if q_hi > q_lo:
                 self._q_all[q_lo:q_hi].copy_(queries_host[q_lo:q_hi], non_blocking=True)
             ev_q.record()
-            if gallery_host is not None:
-                self.shard.copy_(gallery_host, non_blocking=True)
-            ev_g.record()
+        q = self._q_all[:nq]
+        if rs is not None and self.shard.shape[0] > 0:
+            # queue the shard's host -> device copies now (sample first, then split by split: the library's copy stream);
+            # they run under the query exchange, the query preparation and the sweeps of the earlier splits
+            kp = reduced_kp(self.world, k)
+            dummy = torch.empty(8, dtype=torch.int32, device=dev)
+            rs._ws(nq, d, k)
+            rs._call(q, k, kp, False, 0, PH_PREP_G, (dummy, dummy, dummy, dummy))
         main.wait_event(ev_q)
         dist.all_gather_into_tensor(self._q_all, self._q_all[self.rank * S:self.rank * S + S], group=self.group)
-        q = self._q_all[:nq]
-        my_d, my_i, meta, S = self._reduced_slice(q, k, exclude_self, self_offset, ready_gallery=ev_g)
+        my_d, my_i, meta, S = self._reduced_slice(q, k, exclude_self, self_offset, rs=rs,
+                                                   gallery_queued=rs is not None and self.shard.shape[0] > 0)
         n = q_hi - q_lo
         if self._host_out is None or self._host_out[0].shape != (S, k):
             self._host_out = (torch.empty((S, k), dtype=torch.float32).pin_memory(), torch.empty((S, k), dtype=torch.int64).pin_memory())

@@ -45,7 +45,7 @@ def test_sharded_gallery_single_process(rs):
     assert np.array_equal(d, ref_d) and i.dtype == np.int64
 
 
-def _simulate_reduced(g, q, k, R, exclude_self, repair=False):
+def _simulate_reduced(g, q, k, R, exclude_self, repair=False, host_gallery=False):
     """The reduced sharded protocol with R simulated ranks in one process (collectives replaced by torch.stack): pivot
     pre-pass per shard, merged pivot lists, sweep + reduced re-rank written in the slice-major exchange layout, merge +
     global certificate per query slice.  repair=True adds the per-query exact fallback of the uncertified queries.
@@ -56,14 +56,23 @@ def _simulate_reduced(g, q, k, R, exclude_self, repair=False):
     kp = reduced_kp(R, k)
     S = slice_rows(nq, R)
     shards, sends, stats, pivs, bases = [], [], [], [], []
+    from multimodal_similarity_b200.sharded import PH_PIVOT, PH_PREP, PH_PREP_G, PH_PREP_Q
     for r in range(R):
         lo, hi = shard_bounds(n, R, r)
-        shards.append(ReducedShard(g[lo:hi].contiguous(), lo))
+        if host_gallery:      # the shard's rows live in pinned host memory; the device tensor is only a staging buffer
+            shards.append(ReducedShard(torch.full_like(g[lo:hi], float("nan")), lo, g[lo:hi].cpu().pin_memory()))
+        else:
+            shards.append(ReducedShard(g[lo:hi].contiguous(), lo))
         sends.append(torch.empty((R, S * (2 * kp + 1)), dtype=torch.int32, device="cuda"))
         stats.append(torch.empty(8, dtype=torch.int32, device="cuda"))
         bases.append(lo)
     for r in range(R):
-        pivs.append(shards[r].stage1(q, k, kp, sends[r], stats[r]))
+        if host_gallery:      # as ShardedGallery.retrieve_host: queue the shard's copies first, then the query half + pre-pass
+            shards[r]._ws(nq, q.shape[1], k)
+            shards[r]._call(q, k, kp, False, 0, PH_PREP_G, (stats[r], stats[r], stats[r], stats[r]))
+            pivs.append(shards[r].stage1(q, k, kp, sends[r], stats[r], phases=PH_PREP_Q | PH_PIVOT))
+        else:
+            pivs.append(shards[r].stage1(q, k, kp, sends[r], stats[r]))
     allpiv = torch.stack(pivs)                       # the all-gather of the pivot lists
     for r in range(R):
         merge_pivots_into(allpiv, pivs[r])
@@ -106,6 +115,19 @@ def test_reduced_protocol_equals_unsharded(R, exclude_self, rs):
     (md, mi, status, _), kp = _simulate_reduced(g, q, k, R, exclude_self)
     assert kp < 128
     assert int(status[0]) == 0, f"{int(status[0])} uncertified queries with randomly ordered rows"
+    full_d, full_i = mm.retrieve(q, g, k, exclude_self=exclude_self)
+    assert torch.equal(md, full_d) and torch.equal(mi, full_i)
+
+
+@pytest.mark.parametrize("R,exclude_self,n,d,k", [(2, False, 40000, 128, 100), (4, True, 70000, 64, 30), (8, False, 9000, 256, 10)])
+def test_reduced_protocol_with_host_gallery(R, exclude_self, n, d, k, rs):
+    """The shards' rows come from page-locked host memory (mmsim_knn_shard_host_f32: sample first, then split by split under
+    the sweeps) -- same result as the unsharded device call, including the per-query repair path's workspace layout."""
+    import multimodal_similarity_b200 as mm
+    x, _ = clustered(rs, n, d, 50)
+    g = torch.from_numpy(x).cuda()
+    q = g[:700].clone() if exclude_self else torch.from_numpy(clustered(rs, 700, d, 50)[0]).cuda()
+    (md, mi, unc, _), kp = _simulate_reduced(g, q, k, R, exclude_self, repair=True, host_gallery=True)
     full_d, full_i = mm.retrieve(q, g, k, exclude_self=exclude_self)
     assert torch.equal(md, full_d) and torch.equal(mi, full_i)
 
