@@ -227,14 +227,32 @@ MMSIM_API int mmsim_evaluate_f32(const float* E, const int32_t* labels, const in
                        const int32_t* queries, int64_t nq, double alpha, int aligned, double* ap, int32_t* npos,
                        int32_t* first, int32_t* depth, int32_t* hist, int32_t* rank, mmsim_stream_t stream);
 
-/* The same records for galleries of any size (N - 1 rows per ranking no longer fit in shared memory): exact distances,
- * a segmented radix sort and one streaming pass per query, in batches that fit the caller's workspace
- * (mmsim_evaluate_large_workspace_bytes; 256-byte aligned).  Same arguments and results as mmsim_evaluate_f32. */
+/* The same records in the workspace form, for galleries of any size: register-tiled exact distances of a batch of queries
+ * to all rows (the embeddings are read once per 32 queries, not once per query), then per query
+ *   path 1  N <= 24,576: a stable radix sort of the N keys in shared memory + one streaming metrics pass, one CTA per query
+ *   path 2  any N: a segmented device radix sort and one streaming pass per query
+ * in batches that fit the caller's workspace (mmsim_evaluate_large_workspace_bytes covers both paths; 256-byte aligned).
+ * Same arguments and results as mmsim_evaluate_f32.  mmsim_evaluate_ws_f32 takes the path (0 = path 1 when it fits, else 2);
+ * mmsim_evaluate_large_f32 is path 2. */
+#define MMSIM_EVAL_PATH_AUTO 0
+#define MMSIM_EVAL_PATH_SMEM_SORT 1
+#define MMSIM_EVAL_PATH_SEGMENTED_SORT 2
 MMSIM_API int mmsim_evaluate_large_workspace_bytes(int64_t N, int64_t nq, size_t* bytes);
 MMSIM_API int mmsim_evaluate_large_f32(const float* E, const int32_t* labels, const int32_t* cls, int64_t N, int64_t D, int C,
                              const int32_t* queries, int64_t nq, double alpha, int aligned, double* ap, int32_t* npos,
                              int32_t* first, int32_t* depth, int32_t* hist, int32_t* rank, void* workspace,
                              size_t workspace_bytes, mmsim_stream_t stream);
+MMSIM_API int mmsim_evaluate_ws_f32(const float* E, const int32_t* labels, const int32_t* cls, int64_t N, int64_t D, int C,
+                          const int32_t* queries, int64_t nq, double alpha, int aligned, double* ap, int32_t* npos,
+                          int32_t* first, int32_t* depth, int32_t* hist, int32_t* rank, void* workspace, size_t workspace_bytes,
+                          mmsim_stream_t stream, int path);
+
+/* The confusion-matrix accumulation of utils.evaluate (src/utils.py:214-220) from the per-query records above:
+ * cm[row] += (hist[q] / depth[q]).astype(float32) for every query q with npos[q] > 0 and class qcls[q] == row, in query
+ * order (sequential float32 adds, bit-identical to the reference's loop); count[row] = number of such queries.
+ * hist [nq, C], depth / npos / qcls [nq], cm [C, C] float32, count [C]. */
+MMSIM_API int mmsim_evaluate_confusion_f32(const int32_t* hist, const int32_t* depth, const int32_t* npos, const int32_t* qcls,
+                                 int64_t nq, int C, float* cm, int32_t* count, mmsim_stream_t stream);
 
 /* Embedding head: out[r] = l2_normalize(X[r] @ W + b) -- networks.CUBLayer.forward (src/networks.py:376-380, xw_plus_b)
  * followed by tf.nn.l2_normalize(logits, axis=-1, epsilon) (src/base_model_CUB.py:197-201): y * rsqrt(max(sum(y^2), epsilon)).

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("MMSIM_LIB_OUT") or os.path.join(HERE, "libmmsim.so")
-SOURCES = ["api.cu", "knn_tc.cu", "loss.cu", "sqdist.cu", "merge.cu", "eval.cu", "eval_large.cu", "mining.cu", "project.cu", "semihard_loss.cu", "lifted_struct.cu"]
+SOURCES = ["api.cu", "knn_tc.cu", "loss.cu", "sqdist.cu", "merge.cu", "eval.cu", "eval_large.cu", "eval_fast.cu", "mining.cu", "project.cu", "semihard_loss.cu", "lifted_struct.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -220,7 +220,20 @@ MMSIM_API int mmsim_evaluate_large_f32(const float* E, const int32_t* labels, co
                              int32_t* first, int32_t* depth, int32_t* hist, int32_t* rank, void* workspace,
                              size_t workspace_bytes, mmsim_stream_t stream) {
   return eval::run_large(E, labels, cls, N, D, C, queries, nq, alpha, aligned, ap, npos, first, depth, hist, rank, workspace,
-                         workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+                         workspace_bytes, reinterpret_cast<cudaStream_t>(stream), eval::kPathSegmentedSort);
+}
+
+MMSIM_API int mmsim_evaluate_ws_f32(const float* E, const int32_t* labels, const int32_t* cls, int64_t N, int64_t D, int C,
+                          const int32_t* queries, int64_t nq, double alpha, int aligned, double* ap, int32_t* npos,
+                          int32_t* first, int32_t* depth, int32_t* hist, int32_t* rank, void* workspace, size_t workspace_bytes,
+                          mmsim_stream_t stream, int path) {
+  return eval::run_large(E, labels, cls, N, D, C, queries, nq, alpha, aligned, ap, npos, first, depth, hist, rank, workspace,
+                         workspace_bytes, reinterpret_cast<cudaStream_t>(stream), path);
+}
+
+MMSIM_API int mmsim_evaluate_confusion_f32(const int32_t* hist, const int32_t* depth, const int32_t* npos, const int32_t* qcls,
+                                 int64_t nq, int C, float* cm, int32_t* count, mmsim_stream_t stream) {
+  return eval::confusion(hist, depth, npos, qcls, nq, C, cm, count, reinterpret_cast<cudaStream_t>(stream));
 }
 
 MMSIM_API int mmsim_project_normalize_f32(const float* X, int64_t N, int64_t K, const float* W, const float* b, int64_t E,

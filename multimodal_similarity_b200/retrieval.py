@@ -279,13 +279,22 @@ def average_precision(y_true, score):
 
 
 # --------------------------------------------------------------------------- leave-one-out evaluation (K5)
-EVAL_FORCE_LARGE = False    # tests: route every evaluation through the gallery-scale path (csrc/eval_large.cu)
+# Which kernels run the evaluation (tests force each one and compare the records):
+#   "auto"       workspace form: tiled exact distances + shared-memory radix sort per query (N <= 24,576), else + segmented sort
+#   "smem"       force the shared-memory sort path (csrc/eval_fast.cu)
+#   "segmented"  force the segmented-sort path (csrc/eval_large.cu)
+#   "fused"      the one-CTA-per-query kernel of round 1 (csrc/eval.cu: distances + bitonic sort fused, N <= 16385)
+EVAL_PATH = "auto"
+EVAL_FORCE_LARGE = False    # older switch: True == EVAL_PATH "segmented"
+_EVAL_PATHS = {"auto": 0, "smem": 1, "segmented": 2}
 
 
-def _loo_records(embeddings, labels, normalize, standardize, alpha, aligned, want_rank=False, queries=None):
+def _loo_records(embeddings, labels, normalize, standardize, alpha, aligned, want_rank=False, queries=None, confusion=False,
+                 want_hist=False):
     """Run the per-query evaluation kernels for every foreground row (or the rows in ``queries``); returns host-side
-    records.  Galleries whose ranking fits in shared memory (N <= 16385) take the fused one-CTA-per-query kernel
-    (csrc/eval.cu), larger ones the exact-distance + segmented-sort + streaming-metrics path (csrc/eval_large.cu)."""
+    records (one upload of the integer arrays, one read-back per result array).  ``confusion``: also accumulate the
+    reference's confusion matrix on the device (``mmsim_evaluate_confusion_f32``) instead of handing back the [nq, C]
+    histograms."""
     lib = _lib.load()
     lab_np = np.squeeze(labels.cpu().numpy() if torch.is_tensor(labels) else np.asarray(labels)).astype(np.int32)
     emb = to_cuda_f32(embeddings)
@@ -303,44 +312,57 @@ def _loo_records(embeddings, labels, normalize, standardize, alpha, aligned, wan
     else:
         queries_np = np.asarray(queries, dtype=np.int32)
     nq, C = int(queries_np.size), int(classes.size)
-    lab = torch.from_numpy(lab_np).to(dev)
-    cls = torch.from_numpy(cls_np.astype(np.int32)).to(dev)
-    queries = torch.from_numpy(queries_np).to(dev)
+    qcls_np = cls_np[queries_np].astype(np.int32)
+    packed = torch.from_numpy(np.concatenate([lab_np, cls_np.astype(np.int32), queries_np, qcls_np])).to(dev)
+    lab, cls, queries, qcls = packed[:n], packed[n:2 * n], packed[2 * n:2 * n + nq], packed[2 * n + nq:]
     ap = torch.empty(nq, dtype=torch.float64, device=dev)
-    ints = torch.empty((3, max(nq, 1)), dtype=torch.int32, device=dev)
+    ints = torch.empty((4, max(nq, 1)), dtype=torch.int32, device=dev)          # npos, first, depth, hist[q, class of q]
     hist = torch.empty((max(nq, 1), C), dtype=torch.int32, device=dev)
     rank = torch.empty((nq, n - 1), dtype=torch.int32, device=dev) if want_rank else None
+    path = "segmented" if EVAL_FORCE_LARGE else EVAL_PATH
+    if path == "fused" and n > _lib.EVAL_SMEM_MAX_N:
+        path = "auto"
     with torch.cuda.device(dev):
-        if n > _lib.EVAL_SMEM_MAX_N or EVAL_FORCE_LARGE:
-            nbytes = ctypes.c_size_t()
-            _lib.check(lib.mmsim_evaluate_large_workspace_bytes(n, nq, ctypes.byref(nbytes)), "mmsim_evaluate_large_workspace_bytes")
-            ws = workspace("eval_large", nbytes.value, dev)
-            rc = lib.mmsim_evaluate_large_f32(emb.data_ptr(), lab.data_ptr(), cls.data_ptr(), n, d, C, queries.data_ptr(), nq,
-                                              float(alpha), int(bool(aligned)), ap.data_ptr(), ints[0].data_ptr(),
-                                              ints[1].data_ptr(), ints[2].data_ptr(), hist.data_ptr(), _lib.ptr(rank),
-                                              ws.data_ptr(), ws.numel(), stream_handle(dev))
-        else:
+        if path == "fused":
             rc = lib.mmsim_evaluate_f32(emb.data_ptr(), lab.data_ptr(), cls.data_ptr(), n, d, C, queries.data_ptr(), nq,
                                         float(alpha), int(bool(aligned)), ap.data_ptr(), ints[0].data_ptr(), ints[1].data_ptr(),
                                         ints[2].data_ptr(), hist.data_ptr(), _lib.ptr(rank), stream_handle(dev))
-    _lib.check(rc, "mmsim_evaluate_f32")
+        else:
+            nbytes = ctypes.c_size_t()
+            _lib.check(lib.mmsim_evaluate_large_workspace_bytes(n, nq, ctypes.byref(nbytes)), "mmsim_evaluate_large_workspace_bytes")
+            ws = workspace("eval_large", nbytes.value, dev)
+            rc = lib.mmsim_evaluate_ws_f32(emb.data_ptr(), lab.data_ptr(), cls.data_ptr(), n, d, C, queries.data_ptr(), nq,
+                                           float(alpha), int(bool(aligned)), ap.data_ptr(), ints[0].data_ptr(),
+                                           ints[1].data_ptr(), ints[2].data_ptr(), hist.data_ptr(), _lib.ptr(rank),
+                                           ws.data_ptr(), ws.numel(), stream_handle(dev), _EVAL_PATHS[path])
+        _lib.check(rc, "mmsim_evaluate_f32")
+        rec = dict(classes=classes.tolist(), labels=lab_np, queries=queries_np, qcls=qcls_np, n=n)
+        if nq:
+            ints[3, :nq] = hist[:nq].gather(1, qcls.to(torch.int64)[:, None])[:, 0]
+        if confusion:
+            cm = torch.empty((C, C), dtype=torch.float32, device=dev)
+            count = torch.empty(C, dtype=torch.int32, device=dev)
+            _lib.check(lib.mmsim_evaluate_confusion_f32(hist.data_ptr(), ints[2].data_ptr(), ints[0].data_ptr(), qcls.data_ptr(),
+                                                        nq, C, cm.data_ptr(), count.data_ptr(), stream_handle(dev)),
+                       "mmsim_evaluate_confusion_f32")
+            rec["cm"], rec["count"] = cm.cpu().numpy(), count.cpu().numpy()
     ints = ints.cpu().numpy()
-    rec = dict(classes=classes.tolist(), labels=lab_np, queries=queries_np, ap=ap.cpu().numpy(), npos=ints[0][:nq],
-               first=ints[1][:nq], depth=ints[2][:nq], hist=hist.cpu().numpy()[:nq], n=n)
+    rec.update(ap=ap.cpu().numpy(), npos=ints[0][:nq], first=ints[1][:nq], depth=ints[2][:nq], selfhist=ints[3][:nq])
     if want_rank:
         rec["rank"] = rank
+    if want_hist:
+        rec["hist"] = hist.cpu().numpy()[:nq]
     return rec
 
 
 def evaluate_simple(embeddings, labels, normalize=False, standardize=False, alpha=0.5, aligned=False):
     """Leave-one-out retrieval over all foreground rows -> (mAP, mPrec@alpha, R@1) (src/utils.py:83-138).
 
-    ``aligned=False`` keeps the reference's label lookup for mPrec / R@1 (see csrc/eval.cu); queries without any
+    ``aligned=False`` keeps the reference's label lookup for mPrec / R@1 (see csrc/eval_metrics.cuh); queries without any
     positive are skipped like the reference's nan-AP branch (:118-123)."""
     r = _loo_records(embeddings, labels, normalize, standardize, alpha, aligned)
     ok = r["npos"] > 0
-    qcls = np.searchsorted(r["classes"], r["labels"][r["queries"]])
-    prec = r["hist"][np.arange(len(qcls)), qcls] / r["depth"]
+    prec = r["selfhist"] / r["depth"]
     return np.mean(r["ap"][ok]), np.mean(prec[ok]), np.mean((r["first"][ok] < 1).astype(np.int64))
 
 
@@ -348,24 +370,21 @@ def evaluate(embeddings, labels, normalize=False, standardize=False, alpha=0.5, 
     """Leave-one-out retrieval -> (mAP, mAP_event, mPrec, confusion, count, recall) exactly as src/utils.py:140-229:
     per-class mAP dict, confusion = {"confusion_matrix": float32 [C,C], "labels": [...]}, count int32 [C,1],
     recall = [R@1, R@2, R@4, R@8, R@16, R@32]."""
-    r = _loo_records(embeddings, labels, normalize, standardize, alpha, aligned)
+    r = _loo_records(embeddings, labels, normalize, standardize, alpha, aligned, confusion=True)
     classes, lab = r["classes"], r["labels"]
     ok = np.nonzero(r["npos"] > 0)[0]
-    qlab = lab[r["queries"][ok]]
-    qcls = np.searchsorted(classes, qlab)
+    qcls = r["qcls"][ok]
     aps = r["ap"][ok]
-    frac = r["hist"][ok] / r["depth"][ok][:, None]                      # python int / int -> float64 (:252)
     mAP = np.mean(aps)
-    mPrec = np.mean(frac[np.arange(len(ok)), qcls])
-    mAP_event = {}
-    for a, l in zip(aps, qlab.tolist()):
-        mAP_event.setdefault(l, []).append(a)
-    mAP_event = {l: np.mean(v) for l, v in mAP_event.items()}
-    cm = np.zeros((len(classes), len(classes)), dtype="float32")
-    count = np.zeros((len(classes), 1), dtype="int32")
-    for n_, row in enumerate(qcls):                                     # sequential float32 accumulation (:214-220)
-        cm[row] += frac[n_].astype(np.float32)
-        count[row] += 1
+    mPrec = np.mean(r["selfhist"][ok] / r["depth"][ok])                 # python int / int -> float64 (:252)
+    # per-class mean AP, keyed in order of first appearance like the reference's dict (:206-212); np.mean over the class's
+    # APs in query order == np.mean of the reference's list
+    order = np.argsort(qcls, kind="stable")
+    bounds = np.flatnonzero(np.r_[True, qcls[order][1:] != qcls[order][:-1], True])
+    groups = sorted((order[a:b] for a, b in zip(bounds[:-1], bounds[1:])), key=lambda g: g[0])
+    mAP_event = {classes[int(qcls[g[0]])]: np.mean(aps[g]) for g in groups}
+    cm = r["cm"]                                                        # sequential float32 accumulation (:214-220), on the device
+    count = r["count"].reshape(-1, 1).astype("int32")
     cm[1:] /= count[1:]                                                 # :222 (assumes class 0 is row 0)
     count[0] = (lab == 0).sum()                                         # :223
     confusion = {"confusion_matrix": cm, "labels": classes}

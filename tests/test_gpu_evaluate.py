@@ -79,18 +79,19 @@ def test_cub_shape_recall(rs):
     assert got[0] == pytest.approx(ref[0], abs=1e-12) and got[5] == ref[5]
 
 
-# ---------------------------------------------------------------------------------------------- gallery-scale path
-@pytest.fixture
-def force_large():
+# ------------------------------------------------------------------------- the three kernel paths of the evaluation
+@pytest.fixture(params=["smem", "segmented", "fused"])
+def eval_path(request):
     from multimodal_similarity_b200 import retrieval
-    retrieval.EVAL_FORCE_LARGE = True
-    yield
-    retrieval.EVAL_FORCE_LARGE = False
+    retrieval.EVAL_PATH = request.param
+    yield request.param
+    retrieval.EVAL_PATH = "auto"
 
 
 @pytest.mark.parametrize("name", ["hdd", "cub", "fused"])
-def test_large_path_golden(name, force_large):
-    """csrc/eval_large.cu (exact distances + segmented sort + streaming metrics) against the reference's own outputs."""
+def test_every_path_golden(name, eval_path):
+    """Tiled distances + shared-memory radix sort (csrc/eval_fast.cu), + segmented sort (csrc/eval_large.cu) and the fused
+    one-CTA-per-query kernel (csrc/eval.cu), each against the reference's own outputs."""
     import multimodal_similarity_b200 as mm
     g = golden(f"eval_{name}.npz")
     got = mm.evaluate(g["x"].copy(), g["labels"].copy(), alpha=float(g["alpha"]))
@@ -101,32 +102,56 @@ def test_large_path_golden(name, force_large):
     assert np.allclose(s, g["simple"], atol=1e-12)
 
 
-@pytest.mark.parametrize("n,d,c,bg,alpha", [(64, 16, 3, 0.3, 0.5), (1300, 96, 6, 0.5, 1.0), (300, 256, 40, 0.1, 0.0)])
-def test_large_path_equals_fused_kernel(n, d, c, bg, alpha, rs, force_large):
+def _records(path, x, lab, alpha, aligned, **kw):
     from multimodal_similarity_b200 import retrieval
+    retrieval.EVAL_PATH = path
+    try:
+        return retrieval._loo_records(x, lab, False, False, alpha, aligned, want_rank=True, want_hist=True, **kw)
+    finally:
+        retrieval.EVAL_PATH = "auto"
+
+
+# sizes on both sides of every launch shape of the sort kernel (512, 2048, 4096, 6144 items) and feature widths with one
+# summation leaf (16, 100: 8-wide body + tail), two (160, 256), a deeper tree (250) and the sequential form (7)
+@pytest.mark.parametrize("n,d,c,bg,alpha", [(64, 16, 3, 0.3, 0.5), (1300, 96, 6, 0.5, 1.0), (300, 256, 40, 0.1, 0.0), (512, 100, 5, 0.2, 0.5),
+                                            (513, 160, 9, 0.0, 0.7), (2049, 250, 4, 0.1, 0.5), (4097, 7, 12, 0.0, 0.5),
+                                            (6145, 32, 30, 0.3, 0.25)])
+def test_paths_agree_record_by_record(n, d, c, bg, alpha, rs):
     x, lab = clustered(rs, n, d, c, background=bg)
-    x[7] = x[3]; x[11] = x[3]                       # exact ties: both paths order by (distance, index)
+    x[7] = x[3]; x[11] = x[3]                       # exact ties: every path orders by (distance, index)
+    qs = None if n <= 1300 else np.nonzero(lab > 0)[0][:: max(1, n // 200)]
     for aligned in (False, True):
-        retrieval.EVAL_FORCE_LARGE = True
-        a = retrieval._loo_records(x, lab, False, False, alpha, aligned, want_rank=True)
-        retrieval.EVAL_FORCE_LARGE = False
-        b = retrieval._loo_records(x, lab, False, False, alpha, aligned, want_rank=True)
-        for key in ("npos", "first", "depth", "hist"):
-            assert np.array_equal(a[key], b[key]), key
-        assert np.allclose(a["ap"], b["ap"], rtol=0, atol=1e-12)
-        assert np.array_equal(a["rank"].cpu().numpy(), b["rank"].cpu().numpy())
+        ref = _records("fused", x, lab, alpha, aligned, queries=qs)
+        for path in ("smem", "segmented"):
+            got = _records(path, x, lab, alpha, aligned, queries=qs)
+            for key in ("npos", "first", "depth", "hist", "selfhist"):
+                assert np.array_equal(got[key], ref[key]), (path, key)
+            assert np.allclose(got["ap"], ref["ap"], rtol=0, atol=1e-12)
+            assert np.array_equal(got["rank"].cpu().numpy(), ref["rank"].cpu().numpy())
 
 
-def test_large_gallery_vs_oracle(rs):
-    """BASELINE config 4's leave-one-out form: 20,000 fused 2 x 128-d rows, HDD-style labels -- beyond the shared-memory
-    kernel.  A handful of queries against the oracle's per-query arithmetic."""
-    from multimodal_similarity_b200 import retrieval
+def test_tiled_distances_are_numpy_bits(rs):
+    """The register-tiled distance kernel feeds both sort paths: the ranking's distances must be the reference's float32
+    np.linalg.norm bits for every summation shape (one leaf, leaf + tail, two leaves, deeper trees)."""
+    for n, d in ((700, 128), (333, 100), (257, 160), (130, 256), (90, 250), (65, 8), (50, 1024)):
+        x, lab = clustered(rs, n, d, 4)
+        rec = _records("smem", x, lab, 0.5, True, queries=[0, n // 2, n - 1])
+        rank = rec["rank"].cpu().numpy()
+        for n_, i in enumerate((0, n // 2, n - 1)):
+            dist = O.l2_to_all(x[i], np.delete(x, i, 0))
+            assert np.array_equal(rank[n_], np.lexsort((np.arange(n - 1), dist))), (n, d, i)
+
+
+@pytest.mark.parametrize("path", ["auto", "segmented"])
+def test_large_gallery_vs_oracle(rs, path):
+    """BASELINE config 4's leave-one-out form: 20,000 fused 2 x 128-d rows, HDD-style labels (7 classes: thousands of
+    positives per query).  A handful of queries against the oracle's per-query arithmetic."""
     cam, lab = clustered(rs, 20000, 128, 7, first_label=0)          # label 0 = background
     sens, _ = clustered(rs, 20000, 128, 7)
     x = np.concatenate((cam, sens), axis=1)
     qs = [int(q) for q in np.nonzero(lab > 0)[0][[0, 1, 777, 5000, -1]]]
     for aligned in (False, True):
-        rec = retrieval._loo_records(x, lab, False, False, 0.5, aligned, queries=qs)
+        rec = _records(path, x, lab, 0.5, aligned, queries=qs)
         for n_, i in enumerate(qs):
             gl = np.delete(lab, i)
             dist, order, ap = O.retrieve_one(x[i], np.delete(x, i, 0), lab[i], gl)
@@ -139,3 +164,30 @@ def test_large_gallery_vs_oracle(rs):
             assert rec["hist"][n_][rec["classes"].index(int(lab[i]))] / depth == pytest.approx(p, abs=1e-12)
             for c, v in conf.items():
                 assert rec["hist"][n_][rec["classes"].index(int(c))] / depth == pytest.approx(v, abs=1e-12)
+
+
+def test_beyond_the_shared_memory_sort(rs):
+    """N = 30,000 > 24,576: the workspace form falls through to the segmented sort on its own."""
+    x, lab = clustered(rs, 30000, 32, 50)
+    qs = [0, 12345, 29999]
+    rec = _records("auto", x, lab, 0.5, True, queries=qs)
+    rank = rec["rank"].cpu().numpy()
+    for n_, i in enumerate(qs):
+        gl = np.delete(lab, i)
+        dist, order, ap = O.retrieve_one(x[i], np.delete(x, i, 0), lab[i], gl)
+        assert np.array_equal(rank[n_], np.lexsort((np.arange(29999), dist)))
+        assert rec["ap"][n_] == pytest.approx(ap, abs=1e-12)
+
+
+def test_evaluate_host_assembly_matches_oracle_on_few_classes(rs):
+    """Few classes, many queries per class: the device-side confusion accumulation adds thousands of float32 rows per class
+    in query order -- bit-identical to the reference's python loop."""
+    import multimodal_similarity_b200 as mm
+    x, lab = clustered(rs, 3000, 64, 4, background=0.2)
+    ref = O.evaluate(x, lab, alpha=0.5)
+    got = mm.evaluate(x, lab, alpha=0.5)
+    assert got[0] == pytest.approx(ref[0], abs=1e-12) and got[2] == pytest.approx(ref[2], abs=1e-12)
+    assert list(got[1].keys()) == list(ref[1].keys())
+    assert np.allclose(list(got[1].values()), list(ref[1].values()), rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(got[3]["confusion_matrix"], ref[3]["confusion_matrix"])
+    assert np.array_equal(got[4], ref[4]) and got[5] == ref[5]
