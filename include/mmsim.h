@@ -171,7 +171,11 @@ MMSIM_API int mmsim_knn_pivot_region(int64_t nq, int64_t ng, int64_t D, int k, s
  * out[0..12) = padded width, K atoms, 128-query blocks, 256-row gallery tiles, gallery splits, tiles per split, grid,
  * log capacity per (query, split), pivot pre-pass used, tiles of the compact gallery sample, sampled rows, workspace bytes,
  * [12], [13] (if n_out >= 14): workspace offsets of the per-(query, split) candidate counts (int32) and final thresholds;
- * [14..17) (if n_out >= 17): query-streaming sweep in use, its query chunks and 128-query blocks per chunk. */
+ * [14], [15]: query-streaming sweep in use, gallery splits of the host-buffer call; [16..20) (if n_out >= 20): workspace
+ * offsets of the candidate log (uint2 {key bits, gallery row} [query * splits + split][capacity]), of the fp16 operand
+ * copies (queries pre-scaled by -2, then the gallery; rows of `padded width` halves) and of the gallery norm pack
+ * ([tile][320] floats, the first 256 the rows' squared norms); [20]: anchors of the query grouping (0: sweep order ==
+ * query order). */
 MMSIM_API int mmsim_knn_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, int64_t* out, int n_out);
 MMSIM_API int mmsim_knn_merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t rows, float* out,
                            mmsim_stream_t stream);
@@ -250,9 +254,11 @@ MMSIM_API int mmsim_evaluate_ws_f32(const float* E, const int32_t* labels, const
 /* The confusion-matrix accumulation of utils.evaluate (src/utils.py:214-220) from the per-query records above:
  * cm[row] += (hist[q] / depth[q]).astype(float32) for every query q with npos[q] > 0 and class qcls[q] == row, in query
  * order (sequential float32 adds, bit-identical to the reference's loop); count[row] = number of such queries.
- * hist [nq, C], depth / npos / qcls [nq], cm [C, C] float32, count [C]. */
+ * hist [nq, C], depth / npos / qcls [nq], cm [C, C] float32, count [C]; lists [nq] is scratch and list_off[C] the
+ * exclusive prefix sum of the number of queries per class (where each class's query list starts in `lists`). */
 MMSIM_API int mmsim_evaluate_confusion_f32(const int32_t* hist, const int32_t* depth, const int32_t* npos, const int32_t* qcls,
-                                 int64_t nq, int C, float* cm, int32_t* count, mmsim_stream_t stream);
+                                 int64_t nq, int C, float* cm, int32_t* count, int32_t* lists, const int32_t* list_off,
+                                 mmsim_stream_t stream);
 
 /* Embedding head: out[r] = l2_normalize(X[r] @ W + b) -- networks.CUBLayer.forward (src/networks.py:376-380, xw_plus_b)
  * followed by tf.nn.l2_normalize(logits, axis=-1, epsilon) (src/base_model_CUB.py:197-201): y * rsqrt(max(sum(y^2), epsilon)).

@@ -180,10 +180,13 @@ MMSIM_API int mmsim_knn_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_s
   MMSIM_REQUIRE(out && n_out >= 12, MMSIM_ERR_ARG, "knn_plan: need an output array of at least 12 int64");
   MMSIM_REQUIRE(nq > 0 && ng > 0 && D > 0 && D <= 256 && k >= 1 && num_sms >= 1, MMSIM_ERR_ARG, "knn_plan: bad sizes");
   const knn::Plan p = knn::make_plan(nq, ng, D, k, num_sms);
-  const int64_t v[17] = {p.Dp, p.katoms, p.n_qblocks, p.n_tiles, p.n_splits, p.tiles_per_split, p.grid, p.logcap,
+  // [12..] workspace offsets for tests that inspect a finished call (tests/test_gpu_certificate.py): candidate-log counters,
+  // thresholds and entries, the fp16 operand copies and the gallery norm pack
+  const int64_t v[21] = {p.Dp, p.katoms, p.n_qblocks, p.n_tiles, p.n_splits, p.tiles_per_split, p.grid, p.logcap,
                          p.use_pivots, p.n_sample_tiles, p.n_sample, int64_t(p.total_bytes),
-                         int64_t(p.off_log_cnt), int64_t(p.off_log_tau), p.sweepq, p.host_splits, 0};
-  for (int i = 0; i < 17 && i < n_out; ++i) out[i] = v[i];
+                         int64_t(p.off_log_cnt), int64_t(p.off_log_tau), p.sweepq, p.host_splits, int64_t(p.off_log),
+                         int64_t(p.off_qh), int64_t(p.off_gh), int64_t(p.off_gpack), p.n_anchor};
+  for (int i = 0; i < 21 && i < n_out; ++i) out[i] = v[i];
   return MMSIM_OK;
 }
 
@@ -232,8 +235,9 @@ MMSIM_API int mmsim_evaluate_ws_f32(const float* E, const int32_t* labels, const
 }
 
 MMSIM_API int mmsim_evaluate_confusion_f32(const int32_t* hist, const int32_t* depth, const int32_t* npos, const int32_t* qcls,
-                                 int64_t nq, int C, float* cm, int32_t* count, mmsim_stream_t stream) {
-  return eval::confusion(hist, depth, npos, qcls, nq, C, cm, count, reinterpret_cast<cudaStream_t>(stream));
+                                 int64_t nq, int C, float* cm, int32_t* count, int32_t* lists, const int32_t* list_off,
+                                 mmsim_stream_t stream) {
+  return eval::confusion(hist, depth, npos, qcls, nq, C, cm, count, lists, list_off, reinterpret_cast<cudaStream_t>(stream));
 }
 
 MMSIM_API int mmsim_project_normalize_f32(const float* X, int64_t N, int64_t K, const float* W, const float* b, int64_t E,

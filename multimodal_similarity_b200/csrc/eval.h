@@ -27,6 +27,6 @@ int launch_sort_metrics(const uint32_t* keys, int64_t ldk, const int* labels, co
                         int nqb, double alpha, int aligned, double* ap, int* npos, int* first, int* depth, int* hist, int* rank,
                         cudaStream_t s);
 int confusion(const int* hist, const int* depth, const int* npos, const int* qcls, int64_t nq, int C, float* cm, int* count,
-              cudaStream_t s);
+              int* lists, const int* list_off, cudaStream_t s);
 }
 }  // namespace mmsim

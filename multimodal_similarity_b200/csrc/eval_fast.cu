@@ -217,13 +217,13 @@ eval_sort_metrics_kernel(const uint32_t* __restrict__ keys, int64_t ldk, const i
                          int N, int C, const int* __restrict__ queries, double alpha, int aligned, double* __restrict__ out_ap,
                          int* __restrict__ out_npos, int* __restrict__ out_first, int* __restrict__ out_depth,
                          int* __restrict__ out_hist, int* __restrict__ out_rank) {
-  constexpr int NW = NT / 32, CAP = NT * IPT;
-  static_assert(IPT % 2 == 0 && CAP <= 65536, "two 16-bit row indices per register");
+  constexpr int NW = NT / 32, CAP = NT * IPT, CP = 257;
+  static_assert(IPT % 2 == 0 && CAP <= 65536 && NW % 8 == 0, "two 16-bit row indices per register");
   extern __shared__ __align__(16) unsigned char esm[];
   uint32_t* sk = reinterpret_cast<uint32_t*>(esm);                  // [CAP] key bits
   uint16_t* si = reinterpret_cast<uint16_t*>(sk + CAP);             // [CAP] original row
-  int* cnt = reinterpret_cast<int*>(si + CAP);                      // [256][NW] digit counters, one column per warp
-  int* lhist = cnt + 256 * NW;                                      // [C]
+  int* cnt = reinterpret_cast<int*>(si + CAP);                      // [NW][CP] digit counters, one row per warp (odd pitch:
+  int* lhist = cnt + CP * NW;                                       //   lanes with different digits hit different banks); [C]
   __shared__ int wtot[32];
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -238,7 +238,7 @@ eval_sort_metrics_kernel(const uint32_t* __restrict__ keys, int64_t ldk, const i
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = pass * 8;
     // ---- A: load my items (warp `warp` owns the contiguous items [base, base + 32 IPT)), count digits per warp
-    for (int x = t; x < 256 * NW; x += NT) cnt[x] = 0;
+    for (int x = t; x < CP * NW; x += NT) cnt[x] = 0;
     int unsorted = pass == 0;
     uint32_t prev_digit = 0;
     if (pass > 0) prev_digit = base > 0 ? (sk[base - 1] >> shift) & 255u : 0u;
@@ -261,18 +261,17 @@ eval_sort_metrics_kernel(const uint32_t* __restrict__ keys, int64_t ldk, const i
       if (lane == 0) before = prev_digit;
       unsorted |= digit < before;
       prev_digit = __shfl_sync(0xffffffffu, digit, 31);
-      const unsigned same = __match_any_sync(0xffffffffu, digit);
-      if (lane == __ffs(same) - 1) cnt[digit * NW + warp] += __popc(same);
-      __syncwarp();
+      atomicAdd(&cnt[warp * CP + digit], 1);      // warp-private row: counting needs no order (the scatter below does)
     }
     if (!__syncthreads_or(unsorted)) continue;      // this digit is already in order everywhere: the pass is the identity
 
     // ---- B: exclusive scan of the counters in (digit, warp) order
     {
-      int* c8 = cnt + t * 8;
+      // thread t owns entries 8 t .. 8 t + 7 of the (digit, warp) order: digit (8 t) / NW, warps (8 t) % NW ..
+      int* c8 = cnt + ((8 * t) % NW) * CP + (8 * t) / NW;
       int v[8], s = 0;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = c8[e];
+      for (int e = 0; e < 8; ++e) v[e] = c8[e * CP];
 #pragma unroll
       for (int e = 0; e < 8; ++e) { const int x = v[e]; v[e] = s; s += x; }
       int incl = s;
@@ -295,7 +294,7 @@ eval_sort_metrics_kernel(const uint32_t* __restrict__ keys, int64_t ldk, const i
       __syncthreads();
       const int off = incl - s + (warp ? wtot[warp - 1] : 0);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) c8[e] = v[e] + off;
+      for (int e = 0; e < 8; ++e) c8[e * CP] = v[e] + off;
     }
     __syncthreads();
 
@@ -306,9 +305,9 @@ eval_sort_metrics_kernel(const uint32_t* __restrict__ keys, int64_t ldk, const i
       const uint32_t id = (it & 1) ? ip[it / 2] >> 16 : ip[it / 2] & 0xffffu;
       const uint32_t digit = (k >> shift) & 255u;
       const unsigned same = __match_any_sync(0xffffffffu, digit);
-      const int b = cnt[digit * NW + warp];
+      const int b = cnt[warp * CP + digit];
       __syncwarp();
-      if (lane == __ffs(same) - 1) cnt[digit * NW + warp] = b + __popc(same);
+      if (lane == __ffs(same) - 1) cnt[warp * CP + digit] = b + __popc(same);
       __syncwarp();
       const int pos = b + __popc(same & lt_mask);
       sk[pos] = k;
@@ -321,7 +320,7 @@ eval_sort_metrics_kernel(const uint32_t* __restrict__ keys, int64_t ldk, const i
                             out_depth, out_hist, out_rank);
 }
 
-static size_t sort_smem_bytes(int nt, int ipt, int C) { return size_t(nt) * ipt * 6 + size_t(256) * (nt / 32) * 4 + size_t(C) * 4; }
+static size_t sort_smem_bytes(int nt, int ipt, int C) { return size_t(nt) * ipt * 6 + size_t(257) * (nt / 32) * 4 + size_t(C) * 4; }
 
 template <int NT, int IPT>
 static int launch_sort(const uint32_t* keys, int64_t ldk, const int* labels, const int* cls, int N, int C, const int* queries, int nqb,
@@ -364,27 +363,44 @@ int launch_sort_metrics(const uint32_t* keys, int64_t ldk, const int* labels, co
 // ------------------------------------------------------------------------------------------ 3. confusion accumulation
 __global__ void __launch_bounds__(256)
 eval_confusion_kernel(const int* __restrict__ hist, const int* __restrict__ depth, const int* __restrict__ npos,
-                      const int* __restrict__ qcls, int nq, int C, float* __restrict__ cm, int* __restrict__ count) {
-  const int row = blockIdx.x;
-  for (int j0 = 0; j0 < C; j0 += blockDim.x) {
-    const int j = j0 + threadIdx.x;
+                      const int* __restrict__ qcls, int nq, int C, float* __restrict__ cm, int* __restrict__ count,
+                      int* __restrict__ lists /* [nq] scratch: the queries of each class, in query order */,
+                      const int* __restrict__ list_off /* [C] start of each class's list (all its queries would fit) */) {
+  __shared__ int wcnt[8];
+  __shared__ int s_total;
+  const int row = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  int* mine = lists + list_off[row];
+  // the queries of this class with at least one positive (src/utils.py:175-180 skips the others), in query order
+  int total = 0;
+  for (int base = 0; base < nq; base += 256) {
+    const int n = base + t;
+    const bool ok = n < nq && qcls[n] == row && npos[n] > 0;
+    const unsigned b = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) wcnt[warp] = __popc(b);
+    __syncthreads();
+    int off = total;
+    for (int w = 0; w < warp; ++w) off += wcnt[w];
+    if (ok) mine[off + __popc(b & ((1u << lane) - 1u))] = n;
+    for (int w = 0; w < 8; ++w) total += wcnt[w];
+    __syncthreads();
+  }
+  if (t == 0) { count[row] = total; s_total = total; }
+  __syncthreads();                                   // (also orders the list writes before the reads below: same block)
+  for (int j = t; j < C; j += 256) {
     float acc = 0.f;
-    int cnt = 0;
-    for (int n = 0; n < nq; ++n) {
-      if (qcls[n] != row || npos[n] <= 0) continue;        // queries without a positive are skipped (src/utils.py:175-180)
-      ++cnt;
-      if (j < C) acc = __fadd_rn(acc, float(double(hist[size_t(n) * C + j]) / double(depth[n])));   // int / int -> float64 -> float32 (:252,218)
+    for (int e = 0; e < total; ++e) {
+      const int n = mine[e];
+      acc = __fadd_rn(acc, float(double(hist[size_t(n) * C + j]) / double(depth[n])));   // int / int -> float64 -> float32 (:252,218)
     }
-    if (j < C) cm[size_t(row) * C + j] = acc;
-    if (j == 0) count[row] = cnt;
+    cm[size_t(row) * C + j] = acc;
   }
 }
 
 int confusion(const int* hist, const int* depth, const int* npos, const int* qcls, int64_t nq, int C, float* cm, int* count,
-              cudaStream_t s) {
-  MMSIM_REQUIRE(hist && depth && npos && qcls && cm && count, MMSIM_ERR_ARG, "evaluate_confusion: null pointer argument");
+              int* lists, const int* list_off, cudaStream_t s) {
+  MMSIM_REQUIRE(hist && depth && npos && qcls && cm && count && lists && list_off, MMSIM_ERR_ARG, "evaluate_confusion: null pointer argument");
   MMSIM_REQUIRE(nq >= 0 && nq < (int64_t(1) << 31) && C >= 1, MMSIM_ERR_ARG, "evaluate_confusion: bad sizes nq=%lld C=%d", (long long)nq, C);
-  eval_confusion_kernel<<<C, 256, 0, s>>>(hist, depth, npos, qcls, int(nq), C, cm, count);
+  eval_confusion_kernel<<<C, 256, 0, s>>>(hist, depth, npos, qcls, int(nq), C, cm, count, lists, list_off);
   MMSIM_CUDA_CHECK(::mmsim::launched());
   return MMSIM_OK;
 }

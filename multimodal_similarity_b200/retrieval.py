@@ -313,8 +313,12 @@ def _loo_records(embeddings, labels, normalize, standardize, alpha, aligned, wan
         queries_np = np.asarray(queries, dtype=np.int32)
     nq, C = int(queries_np.size), int(classes.size)
     qcls_np = cls_np[queries_np].astype(np.int32)
-    packed = torch.from_numpy(np.concatenate([lab_np, cls_np.astype(np.int32), queries_np, qcls_np])).to(dev)
-    lab, cls, queries, qcls = packed[:n], packed[n:2 * n], packed[2 * n:2 * n + nq], packed[2 * n + nq:]
+    list_off = np.cumsum(np.bincount(qcls_np, minlength=C))[:C].astype(np.int32)
+    list_off = np.r_[np.int32(0), list_off[:-1]].astype(np.int32)     # where each class's query list starts (confusion kernel)
+    packed = torch.from_numpy(np.concatenate([lab_np, cls_np.astype(np.int32), queries_np, qcls_np, list_off,
+                                              np.zeros(nq, np.int32)])).to(dev)
+    lab, cls, queries, qcls = packed[:n], packed[n:2 * n], packed[2 * n:2 * n + nq], packed[2 * n + nq:2 * n + 2 * nq]
+    list_off_d, lists_d = packed[2 * n + 2 * nq:2 * n + 2 * nq + C], packed[2 * n + 2 * nq + C:]
     ap = torch.empty(nq, dtype=torch.float64, device=dev)
     ints = torch.empty((4, max(nq, 1)), dtype=torch.int32, device=dev)          # npos, first, depth, hist[q, class of q]
     hist = torch.empty((max(nq, 1), C), dtype=torch.int32, device=dev)
@@ -343,7 +347,8 @@ def _loo_records(embeddings, labels, normalize, standardize, alpha, aligned, wan
             cm = torch.empty((C, C), dtype=torch.float32, device=dev)
             count = torch.empty(C, dtype=torch.int32, device=dev)
             _lib.check(lib.mmsim_evaluate_confusion_f32(hist.data_ptr(), ints[2].data_ptr(), ints[0].data_ptr(), qcls.data_ptr(),
-                                                        nq, C, cm.data_ptr(), count.data_ptr(), stream_handle(dev)),
+                                                        nq, C, cm.data_ptr(), count.data_ptr(), lists_d.data_ptr(),
+                                                        list_off_d.data_ptr(), stream_handle(dev)),
                        "mmsim_evaluate_confusion_f32")
             rec["cm"], rec["count"] = cm.cpu().numpy(), count.cpu().numpy()
     ints = ints.cpu().numpy()
