@@ -43,17 +43,32 @@ def parse():
     ap.add_argument("--gallery", type=int, default=WORKLOAD["gallery"])
     ap.add_argument("--dim", type=int, default=WORKLOAD["dim"])
     ap.add_argument("--k", type=int, default=WORKLOAD["k"])
+    ap.add_argument("--query-groups", default="auto",
+                    help="N > 1: query groups of the 2-D decomposition (ShardedGallery(query_groups=...)); 1 = every rank "
+                         "holds a different gallery shard and sweeps every query; auto = two gallery parts per group from 4 GPUs on")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / secondary configs (profiling runs)")
     ap.add_argument("--no-big", action="store_true", help="skip the 10M x 256-d single-GPU config among the secondary ones")
     return ap.parse_args()
 
 
-def config_of(a, n_gpus):
+def config_of(a, n_gpus, query_groups=1):
+    parts = n_gpus // query_groups
+    if n_gpus == 1:
+        par = "single GPU"
+    elif query_groups == 1:
+        par = (f"gallery-sharded x{n_gpus}, queries replicated, NCCL all-gather of pivot lists + all-to-all of candidate lists + "
+               "merge by query slice + all-gather")
+    else:
+        par = (f"{query_groups} query groups x {parts} gallery parts (ShardedGallery(query_groups={query_groups})): inside a group the "
+               f"gallery is sharded x{parts} (NCCL all-gather of pivot lists + all-to-all of candidate lists + merge by query "
+               f"slice), the groups split the queries, one all-gather over all {n_gpus} ranks assembles the result; every gallery "
+               f"row is resident on {query_groups} GPUs")
     return {"workload": f"sharded kNN: {a.queries} queries x {a.gallery} gallery, {a.dim}-d, top-{a.k} "
-                        f"(BASELINE configs[4] at the metric's 128-d), gallery rows split over {n_gpus} GPU(s)",
+                        f"(BASELINE configs[4] at the metric's 128-d), gallery rows split over {parts} GPU(s)"
+                        + (f" in each of {query_groups} query groups" if query_groups > 1 else ""),
             "queries": a.queries, "gallery": a.gallery, "dim": a.dim, "k": a.k,
             "l2": f"inputs larger than L2 (fp32 gallery {a.gallery * a.dim * 4 / 1e6:.0f} MB + fp16 copy, 126 MB L2)",
-            "parallelism": f"gallery-sharded x{n_gpus}, queries replicated, NCCL all-to-all of candidate lists + merge by query slice + all-gather" if n_gpus > 1 else "single GPU"}
+            "parallelism": par, "query_groups": query_groups, "gallery_parts": parts}
 
 
 # ----------------------------------------------------------------------------------------------- synthetic data
@@ -467,13 +482,18 @@ def main():
     mm.load()
 
     Q, G, D, k = a.queries, a.gallery, a.dim, a.k
-    lo, hi = shard_bounds(G, world, rank)
-    # identical synthetic data on every rank (seeded); each rank keeps its contiguous gallery block
+    from multimodal_similarity_b200.sharded import resolve_query_groups
+    qgroups = resolve_query_groups(a.query_groups if a.query_groups == "auto" else int(a.query_groups), world)
+    parts = world // qgroups
+    lo, hi = shard_bounds(G, parts, rank % parts)
+    # identical synthetic data on every rank (seeded); each rank keeps the contiguous gallery block of its part
     gallery_full = synth_torch(G, D, WORKLOAD["clusters"], SEED, dev)
     shard = gallery_full[lo:hi].clone()
+    e2e_lo, e2e_hi = shard_bounds(G, world, rank)          # the end-to-end arm uploads every gallery row once: 1-D sharding
+    shard_e2e_host = gallery_full[e2e_lo:e2e_hi].cpu().pin_memory() if world > 1 else None
     del gallery_full
     queries = synth_torch(Q, D, WORKLOAD["clusters"], SEED + 1, dev, centroid_seed=SEED)   # same mixture as the gallery
-    sg = ShardedGallery(shard, presharded=True, row_offset=lo, total_rows=G)
+    sg = ShardedGallery(shard, presharded=True, row_offset=lo, total_rows=G, query_groups=qgroups)
     torch.cuda.synchronize()
 
     statuses = []
@@ -534,7 +554,7 @@ def main():
 
     # ---- e2e: pinned host buffers in, host result out, every step
     q_host = queries.cpu().pin_memory()
-    g_host = sg.shard.cpu().pin_memory()
+    g_host = sg.shard.cpu().pin_memory() if world == 1 else shard_e2e_host
     if world == 1:
         res_d = torch.empty((Q, k), dtype=torch.float32).pin_memory()
         res_i = torch.empty((Q, k), dtype=out_i.dtype).pin_memory()
@@ -544,7 +564,8 @@ def main():
     if world > 1:
         # The shard of the end-to-end gallery object is a device STAGING buffer that persists across steps, like the
         # workspace: retrieve_host copies this rank's rows into it from pinned host memory every step.
-        sg_e2e = ShardedGallery(torch.empty_like(sg.shard), presharded=True, row_offset=lo, total_rows=G)
+        sg_e2e = ShardedGallery(torch.empty((e2e_hi - e2e_lo, D), dtype=torch.float32, device=dev), presharded=True,
+                                row_offset=e2e_lo, total_rows=G, query_groups=1)
         e2e_slice = [None]
 
     def step_e2e():
@@ -627,17 +648,19 @@ def main():
     else:
         # the reduced sharded protocol, stage by stage (same calls ShardedGallery.retrieve makes)
         from multimodal_similarity_b200.sharded import ReducedShard, merge_certified_slice, merge_pivots_into, reduced_kp, slice_rows
-        kp = reduced_kp(world, k)
+        kp = reduced_kp(parts, k)
         rs_ = ReducedShard(sg.shard, lo)
-        S = slice_rows(Q, world)
+        S, gq_lo, gq_hi = sg._my_queries(Q)
+        full_queries, queries = queries, queries[gq_lo:gq_hi]       # the queries of my group
+        Qg = gq_hi - gq_lo
         stride = S * (2 * kp + 1)
-        send = torch.empty((world, stride), dtype=torch.int32, device=dev)
+        send = torch.empty((parts, stride), dtype=torch.int32, device=dev)
         st_ = torch.empty(8, dtype=torch.int32, device=dev)
-        rows = -(-Q // 128) * 128
+        rows = -(-Qg // 128) * 128
         piv = rs_.stage1(queries, k, kp, send, st_)
-        allpiv = torch.empty((world * rows, 16), dtype=torch.float32, device=dev)
+        allpiv = torch.empty((parts * rows, 16), dtype=torch.float32, device=dev)
         recv = torch.empty_like(send)
-        mine = max(0, min(S, Q - rank * S))
+        mine = max(0, min(S, Qg - sg.part * S))
         bases = sg._bases(dev)
         flat = send.view(-1)
         views = (flat.view(torch.float32), flat[S * kp:], flat.view(torch.float32)[2 * S * kp:], st_)
@@ -647,11 +670,11 @@ def main():
         allmeta = torch.empty((world, S + 8), dtype=torch.int32, device=dev)
 
         def ag_piv():
-            dist.all_gather_into_tensor(allpiv, piv)
-            merge_pivots_into(allpiv.view(world, rows, 16), piv)
+            dist.all_gather_into_tensor(allpiv, piv, group=sg.sub_group)
+            merge_pivots_into(allpiv.view(parts, rows, 16), piv)
 
         def a2a_lists():
-            dist.all_to_all_single(recv.view(-1), send.view(-1))
+            dist.all_to_all_single(recv.view(-1), send.view(-1), group=sg.sub_group)
 
         def merge_slice():
             holder[0] = merge_certified_slice(recv, bases, mine, S, kp, k, True)
@@ -696,7 +719,7 @@ def main():
         traffic = ent["traffic_bytes"] if ent else None
     except (OSError, ValueError, KeyError):
         pass
-    flops = 2.0 * Q * (hi - lo) * D
+    flops = 2.0 * (Q if world == 1 else Qg) * (hi - lo) * D
     achieved = flops / (ms_tc / 1e3) / 1e12
     roofline = {"bound": "tensor", "kernel": "knn_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic,
@@ -708,7 +731,7 @@ def main():
     result = {
         "metric": "knn_queries_per_s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f16 tensor-core filter + f32 exact re-rank", "data": "synthetic", "config": config_of(a, world),
+        "dtype": "f16 tensor-core filter + f32 exact re-rank", "data": "synthetic", "config": config_of(a, world, qgroups),
         # counted, not estimated: libmmsim.so ticks a counter at every kernel launch (mmsim_kernel_launches); per step these
         # are the operand copies + norm packs, the query grouping (anchor index, tcgen05 assign pass, counting sort), the gallery
         # sample + tcgen05 pivot pre-pass, the ladder, the tcgen05 sweep, the re-rank, and the (idle) fallback kernels

@@ -19,6 +19,14 @@ single-GPU result:
                   compact lists are all-gathered and merged into those rows.  Only when more than ``FALLBACK_CAP``
                   queries are uncertified does the whole call repeat as ``exact-shards`` -- the result is always exact.
 
+``query_groups = R`` (2-D decomposition).  What does not shrink with the number of gallery shards is per-QUERY work -- operand
+copies and grouping of the replicated queries, the pivot pre-pass, candidate selection, the exchanges (a third of the step at
+8 shards).  With R > 1 the ranks form R groups of ``world / R``: the gallery is split over the ranks INSIDE a group (every
+group holds the whole gallery), the queries are split over the groups, each group runs the protocol above on its queries with
+collectives inside the group only, and ONE all-gather over all ranks assembles the result (every rank contributes the query
+slice it merged).  Per-query work and the sweep both shrink with the number of ranks.  ``"auto"`` keeps two gallery parts
+per group from 4 ranks on (memory: every row lives on R ranks).
+
 The training-loss kernels are not sharded (replicas only).
 """
 from __future__ import annotations
@@ -210,6 +218,16 @@ def patch_rows(out_d, out_i, allfb: torch.Tensor, bases: torch.Tensor, cap: int,
     _lib.check(rc, "mmsim_knn_merge_patch")
 
 
+def resolve_query_groups(query_groups, world: int) -> int:
+    """``"auto"``: two gallery parts per query group from 4 ranks on (R = world / 2), otherwise one group."""
+    if query_groups == "auto":
+        return world // 2 if world >= 4 and world % 2 == 0 else 1
+    r = int(query_groups)
+    if r < 1 or world % r:
+        raise ValueError(f"query_groups={query_groups} must divide the number of ranks ({world})")
+    return r
+
+
 class ShardedGallery:
     """``ShardedGallery(gallery, group).retrieve(queries, k)`` -> identical (dist, idx) on every rank.
 
@@ -217,25 +235,39 @@ class ShardedGallery:
                  rows together with ``row_offset`` / ``total_rows`` (the rows ``shard_bounds`` assigns to it)
     group        a torch.distributed process group (default: the world); without an initialised process group the
                  object degenerates to a single shard
+    query_groups R: the ranks form R groups of ``parts = world / R``; rank r holds gallery part ``r % parts`` (the rows
+                 ``shard_bounds(total_rows, parts, r % parts)``) and serves the queries of group ``r // parts``
+                 (see the module docstring); 1 = every rank holds a different shard and sees every query; ``"auto"``
     """
 
-    def __init__(self, gallery, group=None, *, presharded=False, row_offset=None, total_rows=None, device=None):
+    def __init__(self, gallery, group=None, *, presharded=False, row_offset=None, total_rows=None, device=None, query_groups=1):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.query_groups = resolve_query_groups(query_groups, self.world)
+        self.parts = self.world // self.query_groups       # gallery parts == ranks per query group
+        self.part = self.rank % self.parts
+        self.qgroup = self.rank // self.parts
+        self.sub_group = group                             # the ranks that share my queries (collectives of the protocols)
+        if self.query_groups > 1 and self.parts > 1:
+            members = dist.get_process_group_ranks(group) if group is not None else list(range(self.world))
+            for g_ in range(self.query_groups):            # every rank creates every group (torch.distributed contract)
+                sub = dist.new_group([members[g_ * self.parts + j] for j in range(self.parts)])
+                if g_ == self.qgroup:
+                    self.sub_group = sub
         if presharded:
             if row_offset is None or total_rows is None:
                 raise ValueError("presharded=True needs row_offset and total_rows")
             self.lo, self.total = int(row_offset), int(total_rows)
             shard = gallery
-            want = shard_bounds(self.total, self.world, self.rank)
+            want = shard_bounds(self.total, self.parts, self.part)
             if (self.lo, self.lo + int(gallery.shape[0])) != want:
-                # every rank derives the other shards' row offsets from (total_rows, world) alone -- see _bases()
+                # every rank derives the other shards' row offsets from (total_rows, parts) alone -- see _bases()
                 raise ValueError(f"presharded rows [{self.lo}, {self.lo + int(gallery.shape[0])}) of rank {self.rank} are not "
-                                 f"shard_bounds({self.total}, {self.world}, {self.rank}) = {want}")
+                                 f"shard_bounds({self.total}, {self.parts}, {self.part}) = {want}")
         else:
             self.total = int(gallery.shape[0])
-            self.lo, hi = shard_bounds(self.total, self.world, self.rank)
+            self.lo, hi = shard_bounds(self.total, self.parts, self.part)
             shard = gallery[self.lo:hi]
         self.shard = self._to_device(shard, device)
         self.hi = self.lo + int(self.shard.shape[0])
@@ -246,6 +278,13 @@ class ShardedGallery:
         self.last_protocol = None
         self.last_uncertified = None      # reduced protocol: device scalar, queries the global certificate did not prove
         self.last_repaired = 0            # ... and how many of them the last call repaired one by one
+
+    def _my_queries(self, nq: int):
+        """(S, q_lo, q_hi): rows per merge slice and the query range of my group.  Rank r merges the queries
+        [r S, (r + 1) S): group g serves [g parts S, (g + 1) parts S)."""
+        S = slice_rows(nq, self.world)
+        q_lo = min(nq, self.qgroup * self.parts * S)
+        return S, q_lo, min(nq, q_lo + self.parts * S)
 
     # -- steps of the exact-shards protocol; tests on CPU boxes replace them to exercise the sharding logic under gloo
     def _to_device(self, x, device):
@@ -267,14 +306,25 @@ class ShardedGallery:
         return merge_parts(gathered[:, 0].view(torch.float32), gathered[:, 1], bases, k)
 
     def _bases(self, device):
-        per = -(-self.total // self.world)
-        return torch.tensor([min(self.total, r * per) for r in range(self.world)], dtype=torch.int64, device=device)
+        per = -(-self.total // self.parts)
+        return torch.tensor([min(self.total, r * per) for r in range(self.parts)], dtype=torch.int64, device=device)
 
     def _retrieve_exact_shards(self, q, k, exclude_self, self_offset, check):
-        packed, status = self._local(q, k, exclude_self, self_offset)
+        nq = q.shape[0]
+        S, q_lo, q_hi = self._my_queries(nq)
+        if self.query_groups > 1:
+            q = q[q_lo:q_hi]
+        else:
+            q_lo = 0
+        if nq == 0:
+            dev = self.shard.device
+            return torch.empty((0, k), dtype=torch.float32, device=dev), torch.empty((0, k), dtype=torch.int64, device=dev)
+        packed, status = None, None
+        if q.shape[0] > 0:
+            packed, status = self._local(q, k, exclude_self, self_offset + q_lo)
         if check and self.world > 1:
-            # finish queued exact scans BEFORE the collective, and agree on the outcome: either every rank raises or none
-            err = torch.zeros(1, dtype=torch.int32, device=packed.device)
+            # finish queued exact scans BEFORE the collectives, and agree on the outcome: either every rank raises or none
+            err = torch.zeros(1, dtype=torch.int32, device=self.shard.device)
             try:
                 if status is not None:
                     check_status(status)
@@ -285,66 +335,94 @@ class ShardedGallery:
                 raise _lib.MmsimError("knn: the exact fallback failed on at least one gallery shard")
         elif check and status is not None:
             check_status(status)
-        if self.world > 1:
-            # dim-0 concatenation layout (accepted by both NCCL and gloo), viewed as [world, 2, Q, k] afterwards
-            flat = torch.empty((self.world * 2,) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
-            dist.all_gather_into_tensor(flat, packed, group=self.group)
-            gathered = flat.view((self.world,) + tuple(packed.shape))
-        else:
-            gathered = packed.unsqueeze(0)
-        return self._merge(gathered, self._bases(packed.device), k)
+        merged = None
+        if packed is not None:
+            if self.parts > 1:
+                # dim-0 concatenation layout (accepted by both NCCL and gloo), viewed as [parts, 2, Q, k] afterwards
+                flat = torch.empty((self.parts * 2,) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
+                dist.all_gather_into_tensor(flat, packed, group=self.sub_group)
+                gathered = flat.view((self.parts,) + tuple(packed.shape))
+            else:
+                gathered = packed.unsqueeze(0)
+            merged = self._merge(gathered, self._bases(packed.device), k)
+        if self.query_groups == 1:
+            return merged
+        # 2-D decomposition: every rank contributes the S rows of its group's result that it would merge in the reduced
+        # protocol; one all-gather over ALL ranks assembles the queries in order
+        dev = self.shard.device
+        my_d = torch.full((S, k), float("inf"), dtype=torch.float32, device=dev)
+        my_i = torch.full((S, k), -1, dtype=torch.int64, device=dev)
+        if merged is not None:
+            rows = merged[0][self.part * S:self.part * S + S]
+            my_d[:rows.shape[0]] = rows
+            my_i[:rows.shape[0]] = merged[1][self.part * S:self.part * S + S]
+        out_d = torch.empty((self.world * S, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((self.world * S, k), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out_d, my_d, group=self.group)
+        dist.all_gather_into_tensor(out_i, my_i, group=self.group)
+        return out_d[:nq], out_i[:nq]
 
-    def _reduced_slice(self, q, k, exclude_self, self_offset, rs=None, gallery_queued=False):
+    def _reduced_slice(self, q, k, exclude_self, self_offset, rs=None, gallery_queued=False, S=None):
         """Stages of the reduced protocol up to this rank's merged query slice: (dist [S, k], idx [S, k] global, meta).
+        ``q``: the queries of my group; ``S``: rows per merge slice (default: ceil(len(q) / parts)).
         ``rs``: the shard state to use (end-to-end path: one whose gallery rows come from the host; its gallery copies were
         queued by the caller already -- ``gallery_queued`` -- so only the query half of the preparation is left)."""
         nq = q.shape[0]
-        kp = reduced_kp(self.world, k)
+        kp = reduced_kp(self.parts, k)
         if rs is None:
             if self._reduced is None:
                 self._reduced = ReducedShard(self.shard, self.lo)
             rs = self._reduced
         dev = q.device
-        S = slice_rows(nq, self.world)
-        send = torch.empty((self.world, S * (2 * kp + 1)), dtype=torch.int32, device=dev)
+        if S is None:
+            S = slice_rows(nq, self.parts)
+        send = torch.empty((self.parts, S * (2 * kp + 1)), dtype=torch.int32, device=dev)
         status = torch.empty(8, dtype=torch.int32, device=dev)
         piv = rs.stage1(q, k, kp, send, status, phases=(PH_PREP_Q if gallery_queued else PH_PREP) | PH_PIVOT)
         rows = -(-nq // 128) * 128
         mine = piv if piv is not None else torch.full((rows, 16), float("inf"), device=dev)
-        allpiv = torch.empty((self.world * rows, 16), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(allpiv, mine, group=self.group)
+        allpiv = torch.empty((self.parts * rows, 16), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allpiv, mine, group=self.sub_group)
         if piv is not None:
-            merge_pivots_into(allpiv.view(self.world, rows, 16), piv)
+            merge_pivots_into(allpiv.view(self.parts, rows, 16), piv)
         rs.stage2(q, k, kp, exclude_self, self_offset, send, status, S)
         # merge by query slice: all-to-all of the candidate lists, merge + certify my slice
         recv = torch.empty_like(send)
-        dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
-        n_mine = max(0, min(S, nq - self.rank * S))
+        dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.sub_group)
+        n_mine = max(0, min(S, nq - self.part * S))
         return merge_certified_slice(recv, self._bases(dev), n_mine, S, kp, k, self.total < 2 ** 31) + (S,)
 
     def _repair(self, q, k, exclude_self, self_offset, out_d, out_i, flag, n_unc):
-        """Per-query repair of the rows the global certificate did not prove (identical decisions on every rank).
-        Returns False when the call has to be repeated as exact-shards."""
+        """Per-query repair of the rows of MY GROUP's queries the global certificate did not prove (``q``, ``out_d``,
+        ``out_i``, ``flag``: the group's rows; identical decisions on every rank of the group).  Returns False when the call
+        has to be repeated as exact-shards."""
         if n_unc > FALLBACK_CAP:
             return False
         dev = q.device
         fb = self._reduced.fallback(q, k, exclude_self, self_offset, flag, FALLBACK_CAP)
-        allfb = torch.empty((self.world, fb.numel()), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(allfb.view(-1), fb, group=self.group)
+        allfb = torch.empty((self.parts, fb.numel()), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allfb.view(-1), fb, group=self.sub_group)
         st = allfb[:, 2 * FALLBACK_CAP * k + FALLBACK_CAP:].cpu()
-        if bool((st[:, 1] > st[:, 2]).any()):         # a shard's streaming scan has queries left: identical view on every rank
+        if bool((st[:, 1] > st[:, 2]).any()):         # a shard's streaming scan has queries left: identical view in the group
             return False
         patch_rows(out_d, out_i, allfb, self._bases(dev), FALLBACK_CAP, k)
-        self.last_repaired = n_unc
         return True
 
     def _retrieve_reduced(self, q, k, exclude_self, self_offset, check):
         """Returns (dist, idx), or None when the call has to be repeated as exact-shards (more than FALLBACK_CAP
-        uncertified queries, or a shard's streaming scan still has queries queued)."""
+        uncertified queries in a group, or a shard's streaming scan still has queries queued)."""
         nq = q.shape[0]
         dev = q.device
-        my_d, my_i, meta, S = self._reduced_slice(q, k, exclude_self, self_offset)
-        # the merged slices go straight into the final arrays (three all-gathers, no repacking)
+        S, q_lo, q_hi = self._my_queries(nq)
+        idx_dtype = torch.int32 if self.total < 2 ** 31 else torch.int64
+        if q_hi > q_lo:
+            my_d, my_i, meta, _ = self._reduced_slice(q[q_lo:q_hi], k, exclude_self, self_offset + q_lo, S=S)
+        else:                                             # more query groups than slices with queries: nothing to do here
+            my_d = torch.full((S, k), float("inf"), dtype=torch.float32, device=dev)
+            my_i = torch.full((S, k), -1, dtype=idx_dtype, device=dev)
+            meta = torch.zeros(S + 8, dtype=torch.int32, device=dev)
+            meta[:S] = -1082130432
+        # the merged slices go straight into the final arrays (three all-gathers over ALL ranks, no repacking)
         out_d = torch.empty((self.world * S, k), dtype=torch.float32, device=dev)
         out_i = torch.empty((self.world * S, k), dtype=my_i.dtype, device=dev)
         allmeta = torch.empty((self.world, S + 8), dtype=torch.int32, device=dev)
@@ -358,12 +436,36 @@ class ShardedGallery:
         self.last_uncertified = uncertified           # device scalar, identical on every rank (part of the gathered buffer)
         if not check:
             return out_d, out_i                       # the caller inspects last_uncertified (bench.py does, after timing)
-        n_unc = int(uncertified)
+        per_rank = allmeta[:, S].cpu()
+        n_unc = int(per_rank.sum())
         if n_unc == 0:
             return out_d, out_i
-        flag = allmeta[:, :S].reshape(-1)[:nq].contiguous().view(torch.float32)
-        if not self._repair(q, k, exclude_self, self_offset, out_d, out_i, flag, n_unc):
+        per_group = per_rank.view(self.query_groups, self.parts).sum(1)
+        if int(per_group.max()) > FALLBACK_CAP:       # identical view on every rank: all of them repeat the call
             return None
+        flag = allmeta[:, :S].reshape(-1)[:nq].contiguous().view(torch.float32)
+        ok = True
+        if int(per_group[self.qgroup]) > 0:
+            ok = self._repair(q[q_lo:q_hi], k, exclude_self, self_offset + q_lo, out_d[q_lo:q_hi], out_i[q_lo:q_hi],
+                              flag[q_lo:q_hi].contiguous(), int(per_group[self.qgroup]))
+        if self.query_groups == 1:
+            if ok:
+                self.last_repaired = n_unc
+            return (out_d, out_i) if ok else None
+        # 2-D decomposition: a group repaired its own rows only; hand them to the other groups (and agree on failures)
+        rows = torch.nonzero(flag >= 0).view(-1)                                # all uncertified queries, ascending
+        mine = (rows >= q_lo) & (rows < q_hi)
+        pd = torch.where(mine[:, None], out_d[rows], torch.full_like(out_d[rows], float("-inf")))
+        pi = torch.where(mine[:, None], out_i[rows], torch.full_like(out_i[rows], -1))
+        bad = torch.tensor([0 if ok else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(pd, op=dist.ReduceOp.MAX, group=self.group)            # exactly one group owns each row
+        dist.all_reduce(pi, op=dist.ReduceOp.MAX, group=self.group)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self.group)
+        if int(bad):
+            return None
+        out_d[rows] = pd
+        out_i[rows] = pi
+        self.last_repaired = n_unc
         return out_d, out_i
 
     def retrieve_host(self, queries_host, k, *, gallery_host=None, exclude_self=False, self_offset=0):
@@ -380,6 +482,8 @@ class ShardedGallery:
         A query the global certificate cannot prove makes the call fall back to ``retrieve`` (every rank, same decision)."""
         if self.world == 1 or not self.shard.is_cuda:
             raise _lib.MmsimError("retrieve_host is the multi-GPU end-to-end path; use retrieval.retrieve_host on one GPU")
+        if self.query_groups != 1:
+            raise _lib.MmsimError("retrieve_host uploads every gallery row once: build the ShardedGallery with query_groups=1")
         k = int(k)
         dev = self.shard.device
         nq, d = queries_host.shape
@@ -440,7 +544,7 @@ class ShardedGallery:
         out = None
         self.last_protocol = "exact-shards"
         self.last_repaired = 0
-        if protocol != "exact-shards" and self.world > 1 and q.is_cuda and reduced_kp(self.world, k) < 128:
+        if protocol != "exact-shards" and self.parts > 1 and q.is_cuda and reduced_kp(self.parts, k) < 128:
             out = self._retrieve_reduced(q, k, exclude_self, self_offset, check)
             if out is not None:
                 self.last_protocol = "reduced"

@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, exclude_self, out_dir):
+def _worker(rank, world, port, exclude_self, out_dir, query_groups=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from multimodal_similarity_b200.sharded import ShardedGallery, shard_bounds
@@ -66,8 +66,10 @@ def _worker(rank, world, port, exclude_self, out_dir):
     rs = np.random.RandomState(7)
     x, _ = clustered(rs, 1001, 32, 6)
     q = x[:40] if exclude_self else clustered(rs, 40, 32, 6)[0]
-    sg = CpuShardedGallery(x)
-    assert (sg.lo, sg.hi) == shard_bounds(1001, world, rank)
+    sg = CpuShardedGallery(x, query_groups=query_groups)
+    parts = world // query_groups
+    assert (sg.parts, sg.part, sg.qgroup) == (parts, rank % parts, rank // parts)
+    assert (sg.lo, sg.hi) == shard_bounds(1001, parts, rank % parts)
     d, i = sg.retrieve(q, 15, exclude_self=exclude_self)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), d=d, i=i)
     dist.destroy_process_group()
@@ -84,6 +86,29 @@ def test_sharded_gallery_gloo(world, exclude_self, tmp_path):
     outs = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
     for o in outs:                                     # identical on every rank and equal to the unsharded result
         assert np.array_equal(o["d"], ref_d) and np.array_equal(o["i"], ref_i)
+
+
+@pytest.mark.parametrize("world,groups", [(2, 2), (4, 2), (4, 4)])
+@pytest.mark.parametrize("exclude_self", [False, True])
+def test_query_groups_gloo(world, groups, exclude_self, tmp_path):
+    """2-D decomposition: `groups` query groups of world / groups gallery parts each -- sub-group all-gather of the shard
+    lists, one world all-gather of the merged query slices; identical, unsharded-equal results on every rank."""
+    mp.spawn(_worker, args=(world, _free_port(), exclude_self, str(tmp_path), groups), nprocs=world, join=True)
+    rs = np.random.RandomState(7)
+    x, _ = clustered(rs, 1001, 32, 6)
+    q = x[:40] if exclude_self else clustered(rs, 40, 32, 6)[0]
+    ref_d, ref_i = O.knn(q, x, 15, exclude_self=exclude_self)
+    for r in range(world):
+        o = np.load(tmp_path / f"r{r}.npz")
+        assert np.array_equal(o["d"], ref_d) and np.array_equal(o["i"], ref_i), r
+
+
+def test_query_groups_resolution():
+    from multimodal_similarity_b200.sharded import resolve_query_groups
+    assert [resolve_query_groups("auto", w) for w in (1, 2, 3, 4, 6, 8)] == [1, 1, 1, 2, 3, 4]
+    assert resolve_query_groups(4, 8) == 4 and resolve_query_groups(1, 3) == 1
+    with pytest.raises(ValueError):
+        resolve_query_groups(3, 8)
 
 
 def test_shard_bounds_cover_and_partition():
