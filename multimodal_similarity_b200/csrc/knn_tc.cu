@@ -462,7 +462,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   }
   } else {
     // =============================================================== epilogue warps: TMEM -> candidates
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    if constexpr (NEPI >= 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");     // 8 warps: four 32-register accumulator buffers each
     const uint32_t q = warp & 3;              // TMEM lane quarter this warp may read
     const uint32_t h = (warp - 4) >> 2;       // which of the NH warps of this quarter
     const int row = q * 32 + lane;            // row of the CTA tile == TMEM lane
@@ -615,15 +616,18 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         // (Tried and dropped: accumulating a tile as two 128 x 128 halves with their own ready / drained barriers, four
         // half-accumulators in flight -- 29 ms instead of 20.6, gpurun_out/ablate_v6.log: N = 128 MMAs and twice the
         // barrier traffic cost more than the finer hand-off saves.)
-        float va[32], vb[32];
-        ptx::tmem_ld32(taddr, va);
-        ptx::tmem_ld32(taddr + NH * 32, vb);
+        // (Round 2, scripts/ubench/tmem_mma.cu: the hand-off itself costs ~130 cycles per tile whatever the waits look like;
+        // on top of it 16 warps with two loads in flight each run at ~1,350 cycles per tile, 8 warps with four at ~1,200.
+        // NB register buffers == loads in flight: four when a warp owns four or more chunks of a tile.)
+        constexpr int NB = CPW >= 4 ? 4 : 2;
+        float v[NB][32];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) ptx::tmem_ld32(taddr + b * NH * 32, v[b]);
 #pragma unroll 1
-        for (int cp = 0; cp < CPW; cp += 2) {
-          const int c0 = h + cp * NH, c1 = c0 + NH;
-          const bool last = cp + 2 >= CPW;
-          ptx::tmem_ld_wait(va);
-          ptx::tmem_ld_wait(vb);
+        for (int cp = 0; cp < CPW; cp += NB) {
+          const bool last = cp + NB >= CPW;
+#pragma unroll
+          for (int b = 0; b < NB; ++b) ptx::tmem_ld_wait(v[b]);
           if (last) {
             ptx::tc_fence_before();
             if (PAIR) {
@@ -635,10 +639,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             }
           }
           const float tau = SWEEP ? lds_f32(tau_addr) : pv_thr;
-          scan_chunk(va, c0, nrm, col0, tau);
-          if (!last) ptx::tmem_ld32(taddr + (cp + 2) * NH * 32, va);
-          scan_chunk(vb, c1, nrm, col0, SWEEP ? tau : pv_thr);
-          if (!last) ptx::tmem_ld32(taddr + (cp + 3) * NH * 32, vb);
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            scan_chunk(v[b], h + (cp + b) * NH, nrm, col0, SWEEP ? tau : pv_thr);
+            if (!last) ptx::tmem_ld32(taddr + (cp + NB + b) * NH * 32, v[b]);
+          }
         }
         if (MODE == MODE_SWEEP && h == (tc & (NH - 1))) {
           // tighten (the NH warps of a row take turns): once KPT logged entries lie below a pivot, the KPT smallest
@@ -1329,8 +1334,24 @@ static int launch_pair(int grid, const CUtensorMap& tq, const CUtensorMap& tg, c
   return MMSIM_OK;
 }
 
+// MMSIM_KNN_NEPI=8 (experiment switch, round 2): the product sweep with 8 epilogue warps and four TMEM loads in flight each
+static int sweep_nepi() {
+  const char* e = getenv("MMSIM_KNN_NEPI");
+  return e && atoi(e) == 8 ? 8 : NEPI_SWEEP;
+}
+
 template <int MODE, int ABL>
 static int launch_mode(int katoms, int grid, const CUtensorMap& tq, const CUtensorMap& tg, const SweepArgs& args, cudaStream_t s) {
+  if constexpr (MODE == MODE_SWEEP && ABL == 0) {
+    if (sweep_nepi() == 8) {
+      switch (katoms) {
+        case 1: return launch_tc<1, 8, MODE, ABL>(grid, tq, tg, args, s);
+        case 2: return launch_tc<2, 8, MODE, ABL>(grid, tq, tg, args, s);
+        case 3: return launch_tc<3, 8, MODE, ABL>(grid, tq, tg, args, s);
+        default: return launch_tc<4, 8, MODE, ABL>(grid, tq, tg, args, s);
+      }
+    }
+  }
   switch (katoms) {
     case 1: return launch_tc<1, NEPI_SWEEP, MODE, ABL>(grid, tq, tg, args, s);
     case 2: return launch_tc<2, NEPI_SWEEP, MODE, ABL>(grid, tq, tg, args, s);

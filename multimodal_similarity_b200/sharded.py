@@ -507,6 +507,9 @@ class ShardedGallery:
                 self._q_all[q_lo:q_hi].copy_(queries_host[q_lo:q_hi], non_blocking=True)
             ev_q.record()
         q = self._q_all[:nq]
+        # the query slice is on the critical path (exchange -> preparation -> pre-pass -> sweep) and shares the PCIe link with
+        # the shard: it goes first, alone -- the library's copy stream starts after everything queued on the caller's stream
+        main.wait_event(ev_q)
         if rs is not None and self.shard.shape[0] > 0:
             # queue the shard's host -> device copies now (sample first, then split by split: the library's copy stream);
             # they run under the query exchange, the query preparation and the sweeps of the earlier splits
@@ -514,7 +517,6 @@ class ShardedGallery:
             dummy = torch.empty(8, dtype=torch.int32, device=dev)
             rs._ws(nq, d, k)
             rs._call(q, k, kp, False, 0, PH_PREP_G, (dummy, dummy, dummy, dummy))
-        main.wait_event(ev_q)
         dist.all_gather_into_tensor(self._q_all, self._q_all[self.rank * S:self.rank * S + S], group=self.group)
         my_d, my_i, meta, S = self._reduced_slice(q, k, exclude_self, self_offset, rs=rs,
                                                    gallery_queued=rs is not None and self.shard.shape[0] > 0)

@@ -34,25 +34,44 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr) : "memory");
 }
+// wait flavours (round 2): 0 = mbarrier.try_wait with the library's 200 us suspend hint, 1 = pure test_wait spin,
+// 2 = try_wait without a hint (system default suspend time)
+__device__ int g_wait_mma = 0, g_wait_epi = 0;
+__device__ __forceinline__ void wait_as(int flavour, uint64_t* bar, uint32_t parity) {
+  if (flavour == 1) {
+    while (!ptx::mbar_test_wait(bar, parity)) {}
+  } else if (flavour == 2) {
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(ptx::smem_u32(bar)), "r"(parity) : "memory");
+  } else {
+    ptx::mbar_wait(bar, parity);
+  }
+}
 __device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// mode bits: 16 = the MMA warp commits per tile but never waits for a drained accumulator (cost of the commits alone; use
+// without bit 1), 32 = the epilogue warps take part in the hand-off but load nothing, 64 = ... load a quarter of the columns
 // mode bits: 1 = epilogue warps drain TMEM, 2 = MMA warp issues tiles, 4 = drain waits for the tile's MMA (pipelined
 // like the real kernel: 2 accumulator stages, tfull/tempty), 8 = min-tree over the loaded values (ALU work)
-template <int X>
-__global__ void __launch_bounds__(64 + 16 * 32, 1)
-bench_kernel(int mode, int nepi, int tiles, int katoms, int outstanding, long long* cycles, float* sink) {
+template <int X, int OUT = 2, int NT = 64 + 16 * 32>
+__global__ void __launch_bounds__(NT, 1)
+bench_kernel(int mode, int nepi, int tiles, int katoms, int outstanding, long long* cycles, float* sink, int dcols, int ns,
+             uint32_t idesc_in) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[8];
+  // dcols: 32-bit TMEM columns per accumulator (256: fp32 D; 128: fp16 D, two per column); ns: accumulator stages (<= 4)
+  __shared__ uint64_t bars[12];
   __shared__ uint32_t tmem_ptr;
-  uint64_t* tfull = bars;       // [2]
-  uint64_t* tempty = bars + 2;  // [2]
-  uint64_t* done = bars + 4;
+  uint64_t* tfull = bars;       // [ns]
+  uint64_t* tempty = bars + 4;  // [ns]
+  uint64_t* done = bars + 8;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // finite fp16 pattern in the operand tiles
   for (int i = threadIdx.x; i < (4 * A_BYTES + 4 * B_BYTES) / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003800u ^ ((i * 2654435761u) & 0x03ff03ffu);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], nepi * 32); }
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(&tfull[i], 1); ptx::mbar_init(&tempty[i], nepi * 32); }
     ptx::mbar_init(done, 1);
     ptx::fence_barrier_init();
   }
@@ -62,20 +81,21 @@ bench_kernel(int mode, int nepi, int tiles, int katoms, int outstanding, long lo
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_ptr;
+  const int wm = g_wait_mma, we = g_wait_epi;
   const long long t0 = clock64();
   if (warp == 1) {
     if (mode & 2) {
-      const uint32_t idesc = ptx::umma_idesc_f16(BM, BN);
+      const uint32_t idesc = idesc_in;
       const uint64_t ad0 = ptx::umma_desc_k128(ptx::smem_u32(smem));
       const uint64_t bd0 = ptx::umma_desc_k128(ptx::smem_u32(smem + 4 * A_BYTES));
       for (int t = 0; t < tiles; ++t) {
-        const uint32_t as = t & 1;
-        if (mode & 4) { ptx::mbar_wait(&tempty[as], ((t >> 1) & 1) ^ 1); ptx::tc_fence_after(); }
+        const uint32_t as = t % ns;
+        if ((mode & 4) && !(mode & 16)) { wait_as(wm, &tempty[as], ((t / ns) & 1) ^ 1); ptx::tc_fence_after(); }
         if (lane == 0) {
           for (int ka = 0; ka < katoms; ++ka)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              ptx::umma_f16(tmem_base + as * BN, ad0 + uint64_t(ka * (A_BYTES >> 4) + k * 2),
+              ptx::umma_f16(tmem_base + as * dcols, ad0 + uint64_t(ka * (A_BYTES >> 4) + k * 2),
                             bd0 + uint64_t(((t + ka) & 3) * (B_BYTES >> 4) + k * 2), idesc, (ka | k) != 0);
           if (mode & 4) ptx::umma_commit(&tfull[as]);
         }
@@ -88,47 +108,34 @@ bench_kernel(int mode, int nepi, int tiles, int katoms, int outstanding, long lo
   } else if (warp >= 2 && int(warp) < 2 + nepi && (mode & 1)) {
     const uint32_t q = warp & 3, h = (warp - 2) >> 2;
     const int nh = nepi / 4;
-    const int cpw = (BN / X) / nh;           // chunks per warp per tile
+    const int cpw = (mode & 32) ? 0 : ((mode & 64) ? (dcols / 4 / X) / nh : (dcols / X) / nh);   // chunks per warp per tile (32: none, 64: a quarter)
     float acc = 0.f;
-    uint32_t va[X], vb[X];
+    uint32_t v[OUT][X];
     for (int t = 0; t < tiles; ++t) {
-      const uint32_t as = t & 1;
-      if (mode & 4) { ptx::mbar_wait(&tfull[as], (t >> 1) & 1); ptx::tc_fence_after(); }
-      const uint32_t taddr = tmem_base + ((q * 32) << 16) + as * BN;
-      if (outstanding == 2) {
-        for (int c = 0; c < cpw; c += 2) {
-          tmem_ld<X>(taddr + (h + c * nh) * X, va);
-          tmem_ld<X>(taddr + (h + (c + 1) * nh) * X, vb);
-          ld_wait();
-          if (mode & 8) {
-            float m[4] = {1e30f, 1e30f, 1e30f, 1e30f};
+      const uint32_t as = t % ns;
+      if (mode & 4) { wait_as(we, &tfull[as], (t / ns) & 1); ptx::tc_fence_after(); }
+      const uint32_t taddr = tmem_base + ((q * 32) << 16) + as * dcols;
+      const int step = (outstanding >= OUT && cpw >= OUT) ? OUT : 1;
+      for (int c = 0; c < cpw; c += step) {
+        if (step == OUT) {
 #pragma unroll
-            for (int i = 0; i < X; i += 2) m[(i / 2) & 3] = fminf(fminf(m[(i / 2) & 3], __uint_as_float(va[i])), __uint_as_float(va[i + 1]));
-#pragma unroll
-            for (int i = 0; i < X; i += 2) m[(i / 2) & 3] = fminf(fminf(m[(i / 2) & 3], __uint_as_float(vb[i])), __uint_as_float(vb[i + 1]));
-            acc += fminf(fminf(m[0], m[1]), fminf(m[2], m[3]));
-          } else {
-            uint32_t x = 0;
-#pragma unroll
-            for (int i = 0; i < X; i += 2) x ^= va[i] ^ va[i + 1];
-#pragma unroll
-            for (int i = 0; i < X; i += 2) x ^= vb[i] ^ vb[i + 1];
-            acc += __uint_as_float(x);
-          }
+          for (int o = 0; o < OUT; ++o) tmem_ld<X>(taddr + (h + (c + o) * nh) * X, v[o]);
+        } else {
+          tmem_ld<X>(taddr + (h + c * nh) * X, v[0]);
         }
-      } else {
-        for (int c = 0; c < cpw; ++c) {
-          tmem_ld<X>(taddr + (h + c * nh) * X, va);
-          ld_wait();
+        ld_wait();
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) {
+          if (o >= step) break;
           if (mode & 8) {
             float m[4] = {1e30f, 1e30f, 1e30f, 1e30f};
 #pragma unroll
-            for (int i = 0; i < X; i += 2) m[(i / 2) & 3] = fminf(fminf(m[(i / 2) & 3], __uint_as_float(va[i])), __uint_as_float(va[i + 1]));
+            for (int i = 0; i < X; i += 2) m[(i / 2) & 3] = fminf(fminf(m[(i / 2) & 3], __uint_as_float(v[o][i])), __uint_as_float(v[o][i + 1]));
             acc += fminf(fminf(m[0], m[1]), fminf(m[2], m[3]));
           } else {
             uint32_t x = 0;
 #pragma unroll
-            for (int i = 0; i < X; i += 2) x ^= va[i] ^ va[i + 1];
+            for (int i = 0; i < X; i += 2) x ^= v[o][i] ^ v[o][i + 1];
             acc += __uint_as_float(x);
           }
         }
@@ -146,20 +153,21 @@ bench_kernel(int mode, int nepi, int tiles, int katoms, int outstanding, long lo
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-template <int X>
-void run(const char* name, int mode, int nepi, int tiles, int katoms, int outstanding) {
+template <int X, int OUT = 2, int NT = 64 + 16 * 32>
+void run(const char* name, int mode, int nepi, int tiles, int katoms, int outstanding, int dcols = 256, int ns = 2) {
+  const uint32_t idesc = dcols == 256 ? ptx::umma_idesc_f16(BM, BN) : (ptx::umma_idesc_f16(BM, BN) & ~(1u << 4));   // D = fp32 / fp16
   const int grid = 148;
   long long* cyc;
   float* sink;
   cudaMalloc(&cyc, 2 * grid * sizeof(long long));
   cudaMalloc(&sink, 4096);
   const int smem = 4 * A_BYTES + 4 * B_BYTES;
-  cudaFuncSetAttribute(bench_kernel<X>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(bench_kernel<X, OUT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  bench_kernel<X><<<grid, 64 + 16 * 32, smem>>>(mode, nepi, tiles / 4, katoms, outstanding, cyc, sink);
+  bench_kernel<X, OUT, NT><<<grid, NT, smem>>>(mode, nepi, tiles / 4, katoms, outstanding, cyc, sink, dcols, ns, idesc);
   cudaEventRecord(e0);
-  bench_kernel<X><<<grid, 64 + 16 * 32, smem>>>(mode, nepi, tiles, katoms, outstanding, cyc, sink);
+  bench_kernel<X, OUT, NT><<<grid, NT, smem>>>(mode, nepi, tiles, katoms, outstanding, cyc, sink, dcols, ns, idesc);
   cudaEventRecord(e1);
   cudaError_t err = cudaDeviceSynchronize();
   if (err != cudaSuccess) { printf("%s: CUDA error %s\n", name, cudaGetErrorString(err)); exit(1); }
@@ -171,15 +179,29 @@ void run(const char* name, int mode, int nepi, int tiles, int katoms, int outsta
   for (int i = 0; i < grid; ++i) { ce += h[i]; cm += h[grid + i]; }
   ce /= grid; cm /= grid;
   const double c = (mode & 1) ? ce : cm;
-  printf("%-44s x%-2d nepi=%2d out=%d katoms=%d: %8.1f cyc/tile  (%6.1f B/cyc TMEM->RF, %6.0f MAC/cyc)  %.3f ms -> %.0f MHz, %.0f TFLOP/s\n",
-         name, X, nepi, outstanding, katoms, c / tiles, (mode & 1) ? 131072.0 * tiles / c : 0.0,
+  printf("%-44s x%-2d nepi=%2d out=%d katoms=%d D=%s stages=%d: %8.1f cyc/tile  (%6.1f B/cyc TMEM->RF, %6.0f MAC/cyc)  %.3f ms -> %.0f MHz, %.0f TFLOP/s\n",
+         name, X, nepi, outstanding, katoms, dcols == 256 ? "f32" : "f16", ns, c / tiles, (mode & 1) ? 512.0 * dcols * tiles / c : 0.0,
          (mode & 2) ? double(BM) * BN * 64 * katoms * tiles / c : 0.0, ms, c / ms / 1e3,
          (mode & 2) ? 2.0 * BM * BN * 64 * katoms * tiles * grid / ms / 1e9 : 0.0);
   cudaFree(cyc); cudaFree(sink);
 }
 
-int main() {
+int main(int argc, char** argv) {
   const int T = 4000;
+  if (argc > 1 && argv[1][0] == 'h') {     // round 2: where do the ~150 cycles per tile between "mma only" and "pipelined" go?
+    run<32>("mma only", 2, 16, T, 2, 2);
+    run<32>("mma + commit per tile (no waits)", 2 | 4 | 16, 16, T, 2, 2);
+    for (int wm : {0, 1, 2})
+      for (int we : {0, 1, 2}) {
+        cudaMemcpyToSymbol(g_wait_mma, &wm, 4);
+        cudaMemcpyToSymbol(g_wait_epi, &we, 4);
+        printf("-- wait flavour: MMA warp %d, epilogue warps %d (0 try_wait + 200 us hint, 1 test_wait spin, 2 try_wait, no hint)\n", wm, we);
+        run<32>("pipelined, hand-off only (no loads)", 1 | 2 | 4 | 32, 16, T, 2, 2);
+        run<32>("pipelined, all columns loaded + min-tree", 1 | 2 | 4 | 8, 8, T, 2, 2);
+        run<32>("pipelined, all columns loaded + min-tree", 1 | 2 | 4 | 8, 16, T, 2, 2);
+      }
+    return 0;
+  }
   for (int nepi : {4, 8, 16}) {
     run<32>("drain only", 1, nepi, T, 2, 1);
     run<32>("drain only", 1, nepi, T, 2, 2);
