@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("MMSIM_LIB") or os.path.join(_HERE, "libmmsim.so")   #
 METRICS = {"squaredeuclidean": 0, "euclidean": 1, "l1": 2}
 LOSS_BATCH_HARD, LOSS_LIFTED = 0, 1
 KNN_MAX_K = 112
+KNN_MAX_D = 256            # widest embedding the tcgen05 sweep takes (4 K atoms); wider ones use the exact per-query path
 EVAL_SMEM_MAX_N = 16385     # largest N whose leave-one-out ranking fits the one-CTA-per-query kernel (csrc/eval.cu)
 
 # name -> (restype, argtypes); mirrors include/mmsim.h one to one (tests/test_abi.py checks the header against this)

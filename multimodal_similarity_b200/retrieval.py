@@ -148,13 +148,43 @@ def retrieve(queries, gallery, k, *, exclude_self=False, self_offset=0, queries2
         queries, gallery = late_fusion(queries, queries2), late_fusion(gallery, gallery2)
     q = to_cuda_f32(queries)
     g = q if gallery is queries else to_cuda_f32(gallery, q.device)
-    dist, idx, status = knn_raw(q, g, int(k), exclude_self, self_offset)
-    if check:
-        check_status(status)
-    idx = idx.to(torch.int64)
+    k = int(k)
+    if k > _lib.KNN_MAX_K - (1 if exclude_self else 0) or q.shape[1] > _lib.KNN_MAX_D:
+        dist, idx = _retrieve_exact_any(q, g, k, exclude_self, self_offset)
+    else:
+        dist, idx, status = knn_raw(q, g, k, exclude_self, self_offset)
+        if check:
+            check_status(status)
+        idx = idx.to(torch.int64)
     if as_numpy:
         return dist.cpu().numpy(), idx.cpu().numpy()
     return dist, idx
+
+
+def _retrieve_exact_any(q, g, k, exclude_self, self_offset):
+    """The shapes outside the tensor-core pipeline (k > 112 -- up to the reference's full argsort -- or D > 256): exact
+    distances in the reference's arithmetic (csrc/sqdist.cu, any D) for a block of queries at a time, IEEE square root, a
+    stable device sort by distance (ties by index, like every other path), the first k columns.  O(G log G) per query:
+    the per-query form of the reference (src/utils.py:73-74), not the fast path."""
+    from .distance import pairwise_distance
+    nq, ng = q.shape[0], g.shape[0]
+    if k < 1 or k > ng - (1 if exclude_self else 0):
+        raise ValueError(f"k={k} exceeds the {ng - (1 if exclude_self else 0)} gallery rows a query can be ranked against")
+    out_d = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+    block = max(1, min(nq, (1 << 27) // max(ng, 1)))            # <= 512 MB of distances at a time
+    for lo in range(0, nq, block):
+        hi = min(nq, lo + block)
+        d = torch.sqrt(pairwise_distance(q[lo:hi], g))
+        if exclude_self:
+            rows = torch.arange(lo, hi, device=q.device)
+            cols = rows + int(self_offset)
+            ok = (cols >= 0) & (cols < ng)
+            d[rows[ok] - lo, cols[ok]] = float("inf")
+        sd, si = torch.sort(d, dim=1, stable=True)
+        out_d[lo:hi] = sd[:, :k]
+        out_i[lo:hi] = si[:, :k]
+    return out_d, out_i
 
 
 def _as_host_f32(x) -> torch.Tensor:

@@ -134,8 +134,11 @@ def test_rejects_bad_arguments(rs):
         mm.retrieve(x, x, 113)
     with pytest.raises(ValueError):
         mm.retrieve(x, rs.randn(10, 64).astype(np.float32), 3)
-    with pytest.raises(mm.MmsimError):
-        mm.retrieve(rs.randn(4, 300).astype(np.float32), rs.randn(9, 300).astype(np.float32), 3)   # D > 256
+    with pytest.raises(ValueError):
+        mm.retrieve(rs.randn(4, 300).astype(np.float32), rs.randn(9, 200).astype(np.float32), 3)   # wide, and mismatched
+    from multimodal_similarity_b200.retrieval import knn_raw
+    with pytest.raises(mm.MmsimError):                                                           # the tensor-core call itself: D <= 256
+        knn_raw(torch.from_numpy(rs.randn(4, 300).astype(np.float32)).cuda(), torch.from_numpy(rs.randn(9, 300).astype(np.float32)).cuda(), 3)
 
 
 def test_random_shape_sweep(rs):
@@ -226,3 +229,15 @@ def test_grouped_queries_exclude_self_vs_oracle(rs):
     finally:
         del os.environ["MMSIM_KNN_GROUP"]
     assert np.array_equal(d0.cpu().numpy(), d) and np.array_equal(i0.cpu().numpy(), i)
+
+
+@pytest.mark.parametrize("n,d,k,excl", [(3000, 384, 10, False), (2500, 64, 500, True), (900, 1024, 899, True), (700, 32, 700, False)])
+def test_shapes_beyond_the_tensor_core_pipeline(n, d, k, excl, rs):
+    """k > 112 (up to the reference's full ranking) and D > 256 take the exact per-query path: same distances, same order."""
+    import multimodal_similarity_b200 as mm
+    x, _ = clustered(rs, n, d, 9)
+    q = x[:40] if excl else clustered(rs, 40, d, 9)[0]
+    dist, idx = mm.retrieve(q, x, k, exclude_self=excl)
+    ref_d, ref_i = O.knn(q, x, k, exclude_self=excl)
+    assert dist.dtype == np.float32 and idx.dtype == np.int64
+    assert np.array_equal(dist, ref_d) and np.array_equal(idx, ref_i)
