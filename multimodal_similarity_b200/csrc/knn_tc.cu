@@ -143,10 +143,15 @@ enum { MODE_PIVOT = 0, MODE_SWEEP = 1, MODE_ASSIGN = 2, MODE_RESWEEP = 3 };
 // Experiment counters (MMSIM_DEBUG_BUILD=1 builds only; scripts/sweep_debug.py): [5] 8-column groups handed to the
 // candidate path, [6] epilogue warp cycles (sum over warps), [7] 32-column warp chunks with a hit
 #ifdef MMSIM_SWEEP_DEBUG
-__device__ unsigned long long g_dbg[8];
+// Round 2, per-role cycle breakdown of the sweep (lane 0 of the MMA warp; lane 0 of epilogue warp 4): [0] MMA warp total,
+// [1] ... waiting for a drained accumulator, [2] ... waiting for a shared-memory stage, [3] epilogue warp waiting for a
+// ready accumulator, [4] ... from "ready" to "released" (its TMEM loads), [8] ... total, [9] tiles (MMA warp)
+__device__ unsigned long long g_dbg[16];
 #define DBG_ADD(i, v) atomicAdd(&g_dbg[i], (unsigned long long)(v))
+#define DBG_CLOCK() clock64()
 #else
 #define DBG_ADD(i, v) ((void)0)
+#define DBG_CLOCK() 0ll
 #endif
 
 struct SweepArgs {
@@ -420,6 +425,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     const uint64_t adesc0 = ptx::umma_desc_k128(ptx::smem_u32(smem_a));
     const uint64_t bdesc0 = ptx::umma_desc_k128(ptx::smem_u32(smem_b));
     uint32_t it = 0, tc = 0, ic = 0;
+    [[maybe_unused]] const long long t_mma0 = DBG_CLOCK();
     if (!PAIR || crank == 0) {
     for (int item = item0; item < n_items; item += item_step, ++ic) {
       int qb, split, t0, nt;
@@ -428,12 +434,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       ptx::tc_fence_after();
       for (int i = 0; i < nt; ++i, ++tc) {
         const uint32_t as = tc & 1;
+        [[maybe_unused]] const long long w0 = DBG_CLOCK();
         ptx::mbar_wait(&tempty[as], ((tc >> 1) & 1) ^ 1);   // (a spinning wait here is slower: 22.3 vs 21.2 ms)
         ptx::tc_fence_after();
+        if (MODE == MODE_SWEEP && lane == 0) { DBG_ADD(1, DBG_CLOCK() - w0); DBG_ADD(9, 1); }
         for (int ka = 0; ka < KATOMS; ++ka, ++it) {
           const uint32_t stage = it % NS, phase = (it / NS) & 1;
+          [[maybe_unused]] const long long w1 = DBG_CLOCK();
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
+          if (MODE == MODE_SWEEP && lane == 0) DBG_ADD(2, DBG_CLOCK() - w1);
           if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < KATOM / 16; ++k) {
@@ -458,6 +468,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       }
       __syncwarp();
     }
+    if (MODE == MODE_SWEEP && lane == 0) DBG_ADD(0, DBG_CLOCK() - t_mma0);
     }
   }
   } else {
@@ -603,8 +614,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       constexpr int CPW = (BN / 32) / NH;    // chunks per warp and tile (even)
       for (int i = 0; i < nt; ++i, ++tc) {
         const uint32_t as = tc & 1;
+        [[maybe_unused]] const long long e0 = DBG_CLOCK();
         ptx::mbar_wait(&tfull[as], (tc >> 1) & 1);
         ptx::tc_fence_after();
+        [[maybe_unused]] const long long e1 = DBG_CLOCK();
+        if (MODE == MODE_SWEEP && warp == 4 && lane == 0) DBG_ADD(3, e1 - e0);
         const uint32_t nrm = ring_u32 + (tc % NT) * NPACK * 4;
         const uint32_t taddr = taddr0 + as * BN;
         const int col0 = tile_of<MODE>(a, t0, i) * BN;
@@ -637,6 +651,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             } else {
               ptx::mbar_arrive(&tempty[as]);
             }
+            if (MODE == MODE_SWEEP && warp == 4 && lane == 0) DBG_ADD(4, DBG_CLOCK() - e1);
           }
           const float tau = SWEEP ? lds_f32(tau_addr) : pv_thr;
 #pragma unroll
@@ -714,6 +729,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     }
 #ifdef MMSIM_SWEEP_DEBUG
     if (lane == 0) DBG_ADD(6, clock64() - t_epi0);
+    if (MODE == MODE_SWEEP && warp == 4 && lane == 0) DBG_ADD(8, clock64() - t_epi0);
 #endif
   }
 
@@ -1872,12 +1888,12 @@ int merge_pivots(const float* parts, int nparts, int64_t part_stride, int64_t ro
 
 #ifdef MMSIM_SWEEP_DEBUG
 // experiment builds only (MMSIM_DEBUG_BUILD=1 python -m multimodal_similarity_b200.build --force); not part of the C-ABI
-extern "C" __attribute__((visibility("default"))) int mmsim_debug_counters(unsigned long long* out, int n, int reset) {
-  unsigned long long h[8] = {};
+extern "C" __attribute__((visibility("default"))) int mmsim_debug_counters(unsigned long long* out, int n, int reset) {  // n <= 16
+  unsigned long long h[16] = {};
   if (cudaMemcpyFromSymbol(h, mmsim::knn::g_dbg, sizeof(h)) != cudaSuccess) return -1;
-  for (int i = 0; i < n && i < 8; ++i) out[i] = h[i];
+  for (int i = 0; i < n && i < 16; ++i) out[i] = h[i];
   if (reset) {
-    unsigned long long z[8] = {};
+    unsigned long long z[16] = {};
     if (cudaMemcpyToSymbol(mmsim::knn::g_dbg, z, sizeof(z)) != cudaSuccess) return -1;
   }
   return 0;
