@@ -17,6 +17,7 @@ struct Plan {
   // query-streaming sweep (knn_sweepq.cuh; the default): one candidate log per query (n_splits == 1), work items are
   // (gallery tile, query chunk); host-buffer mode copies / sweeps the gallery in host_splits tile ranges
   int sweepq, host_splits;
+  int dual;                   // sweep with two query blocks resident per CTA (K <= 128): work items are PAIRS of query blocks
   size_t off_tau, off_state;
   int unc_cap;                // capacity of the uncertified-query lists (= nq: every query may take the exact fallback)
   int logcap, use_pivots;     // candidate log capacity per (query, split); pivot pre-pass used (gallery larger than a log)

@@ -157,6 +157,7 @@ __device__ unsigned long long g_dbg[16];
 struct SweepArgs {
   const float* gpack;        // [n_tiles][NPACK]
   int nq, n_qblocks, n_tiles;
+  int dual;                  // host side only: launch the DUAL instantiation (items = pairs of query blocks)
   // MODE_SWEEP: item = (split, query block); contiguous tile range per split
   int n_splits, tiles_per_split;
   int item_begin, item_end;  // MODE_SWEEP: this launch takes items [item_begin, item_end); item_end == 0: all of them
@@ -181,16 +182,18 @@ struct SweepArgs {
   long long dyn_budget;
 };
 
-template <int KATOMS>
+template <int KATOMS, bool DUAL = false>
 struct Smem {
-  static constexpr int NS = KATOMS <= 2 ? 5 : 4;               // gallery smem stages (one 32 KiB K atom of one tile each)
+  static constexpr int NA = DUAL ? 2 : 1;                      // query tiles resident (DUAL: two 128-query blocks per CTA)
+  static constexpr int NS = DUAL ? 4 : (KATOMS <= 2 ? 5 : 4);  // gallery smem stages (one 32 KiB K atom of one tile each)
   static constexpr int A_OFF = 0;
-  static constexpr int B_OFF = A_OFF + KATOMS * A_ATOM_BYTES;
+  static constexpr int B_OFF = A_OFF + NA * KATOMS * A_ATOM_BYTES;
   static constexpr int NORM_OFF = B_OFF + NS * B_STAGE_BYTES;
-  static constexpr int TAU_OFF = NORM_OFF + NT * NPACK * 4;   // float [BM]   current threshold of each row
-  static constexpr int CNT_OFF = TAU_OFF + BM * 4;            // u32   [BM]   packed log cursor + ladder counters
-  static constexpr int PV_OFF = CNT_OFF + BM * 4;             // float [4][NPSUB][BM] pivot pre-pass: per-warp sorted sub-lists
-  static constexpr int BAR_OFF = PV_OFF + 4 * NPSUB * BM * 4;
+  static constexpr int TAU_OFF = NORM_OFF + NT * NPACK * 4;   // float [NA][BM]   current threshold of each row
+  static constexpr int CNT_OFF = TAU_OFF + NA * BM * 4;       // u32   [NA][BM]   packed log cursor + ladder counters
+  static constexpr int RS_OFF = CNT_OFF + NA * BM * 4;        // float2 [NA][BM]  DUAL: ladder rungs of each row (piv0, piv1)
+  static constexpr int PV_OFF = RS_OFF + (DUAL ? NA * BM * 8 : 0);   // float [4][NPSUB][BM] pivot pre-pass: per-warp sorted sub-lists
+  static constexpr int BAR_OFF = PV_OFF + (DUAL ? 0 : 4 * NPSUB * BM * 4);
   static constexpr int NUM_BARS = 4 * NS + 2 + 2 + 2 + NT + NT;   // PAIR runs twice the stages (half the bytes each)
   static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
   static constexpr int TOTAL = TMEM_PTR_OFF + 8;
@@ -202,6 +205,11 @@ struct Smem {
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
@@ -283,10 +291,17 @@ __device__ __forceinline__ int tile_of(const SweepArgs& a, int t0, int i) {
 // shared memory and the pair's MMAs (issued by the leader CTA, M = 256) read both halves.  Per CTA and tile that halves
 // the TMA writes into shared memory and the L2 -> SM traffic; the 1-CTA kernel moves 160 KB through a 128 B/cycle shared
 // memory per 1,024-cycle tile (64 KB TMA writes + 96 KB operand reads), the pair 96 KB.
-template <int KATOMS, int NEPI, int MODE, int ABL, bool PAIR>
+// DUAL (round 2): a CTA keeps TWO 128-query blocks resident and multiplies every gallery tile with both before releasing its
+// shared-memory stage -- the sweep is bound by L2 -> SM bytes (782 query blocks each stream the fp16 gallery: 204 GB per
+// launch = the ~6,300 B/cycle the L2 delivers chip-wide, profiles/r2h_sweep_roles.txt), and this halves them.  The two
+// accumulators of a gallery tile are the two TMEM stages; everything per (query block, tile) is unchanged.  K <= 128 only
+// (two 32 KiB query tiles + a four-stage gallery ring fit in shared memory).
+template <int KATOMS, int NEPI, int MODE, int ABL, bool PAIR, bool DUAL = false>
 __global__ void __launch_bounds__(128 + NEPI * 32, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_g, const SweepArgs a) {
-  using S = Smem<KATOMS>;
+  static_assert(!DUAL || (!PAIR && KATOMS <= 2 && MODE == MODE_SWEEP), "DUAL: product sweep, K <= 128, single CTAs");
+  using S = Smem<KATOMS, DUAL>;
+  constexpr int NA = DUAL ? 2 : 1;
   constexpr int NS = PAIR ? 2 * S::NS : S::NS;   // PAIR: a stage holds half a tile's K atom (16 KiB), so twice as many fit
   constexpr int NH = NEPI / 4;            // epilogue warps per TMEM lane quarter; each takes every NH-th 32-column chunk
   constexpr int EPI_THREADS = NEPI * 32;
@@ -300,6 +315,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   float* norm_ring = reinterpret_cast<float*>(smem + S::NORM_OFF);
   float* s_tau = reinterpret_cast<float*>(smem + S::TAU_OFF);
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + S::CNT_OFF);
+  [[maybe_unused]] float2* s_rs = reinterpret_cast<float2*>(smem + S::RS_OFF);   // DUAL: (piv0, piv1) of every resident row
   float* s_pv = reinterpret_cast<float*>(smem + S::PV_OFF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* full = bars;                 // [NS]  TMA -> MMA
@@ -355,7 +371,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
   }
 
   // items: (split, query block) -- PAIR: (split, PAIR of query blocks), this CTA takes block 2 * pair + rank
-  const int n_qb_items = PAIR ? (n_qblocks + 1) / 2 : n_qblocks;
+  const int n_qb_items = (PAIR || DUAL) ? (n_qblocks + 1) / 2 : n_qblocks;   // DUAL: this CTA takes blocks 2 * item, 2 * item + 1
   const int n_items = SWEEP ? (a.item_end ? a.item_end : n_qb_items * n_splits) : n_qblocks;
   const int item0 = (MODE == MODE_SWEEP ? a.item_begin : 0) + (PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x));
   const int item_step = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
@@ -364,6 +380,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       split = item / n_qb_items;
       qb = item - split * n_qb_items;
       if (PAIR) qb = 2 * qb + int(crank);              // may be == n_qblocks (odd count): all rows invalid, loads zero-filled
+      if (DUAL) qb = 2 * qb;                           // ... and block qb + 1 (same remark)
       t0 = split * tiles_per_split;
       nt = min(a.n_tiles, t0 + tiles_per_split) - t0;
     } else {
@@ -383,9 +400,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
         item_range(item, qb, split, t0, nt);
         ptx::mbar_wait(aempty, (ic & 1) ^ 1);
         if (!PAIR) {
-          ptx::mbar_expect_tx(afull, KATOMS * A_ATOM_BYTES);
-          for (int ka = 0; ka < KATOMS; ++ka)
-            ptx::tma_load_2d(smem_a + ka * A_ATOM_BYTES, &tm_q, ka * KATOM, qb * BM, afull);
+          ptx::mbar_expect_tx(afull, NA * KATOMS * A_ATOM_BYTES);
+          for (int hb = 0; hb < NA; ++hb)
+            for (int ka = 0; ka < KATOMS; ++ka)
+              ptx::tma_load_2d(smem_a + (hb * KATOMS + ka) * A_ATOM_BYTES, &tm_q, ka * KATOM, (qb + hb) * BM, afull);
         } else {
           // both CTAs' query tiles are counted on the leader's barrier, which expects the bytes of the pair
           if (crank == 0) ptx::mbar_expect_tx(afull, 2 * KATOMS * A_ATOM_BYTES);
@@ -420,6 +438,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // =============================================================== MMA issuer (one thread issues, warp waits)
+    // (Round 2 tried TWO issuer warps, one per accumulator stage, to spread the issue path -- barrier waits, commits and the
+    // ~110 cycles every tcgen05.mma costs whatever its shape: 2-3% faster at 128-d when it worked, but two consumers of one
+    // mbarrier ring can fall a phase apart -- a parity wait only tells consecutive phases apart -- and it deadlocked at
+    // K = 256 and together with DUAL; removed.  profiles/r2i_sweep_dual_mma2.txt)
     // PAIR: only the leader CTA issues (M = 256 over both CTAs' query tiles); the peer's warp 1 just owns its TMEM
     const uint32_t idesc = ptx::umma_idesc_f16(PAIR ? 2 * BM : BM, BN);
     const uint64_t adesc0 = ptx::umma_desc_k128(ptx::smem_u32(smem_a));
@@ -432,22 +454,28 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       item_range(item, qb, split, t0, nt);
       ptx::mbar_wait(afull, ic & 1);
       ptx::tc_fence_after();
-      for (int i = 0; i < nt; ++i, ++tc) {
+      for (int i = 0; i < nt; ++i) {
+        const uint32_t it0 = it;
+#pragma unroll
+        for (int hb = 0; hb < NA; ++hb, ++tc) {          // DUAL: both query blocks against this gallery tile (tc counts MMA tiles)
         const uint32_t as = tc & 1;
         [[maybe_unused]] const long long w0 = DBG_CLOCK();
         ptx::mbar_wait(&tempty[as], ((tc >> 1) & 1) ^ 1);   // (a spinning wait here is slower: 22.3 vs 21.2 ms)
         ptx::tc_fence_after();
         if (MODE == MODE_SWEEP && lane == 0) { DBG_ADD(1, DBG_CLOCK() - w0); DBG_ADD(9, 1); }
+        it = it0;
         for (int ka = 0; ka < KATOMS; ++ka, ++it) {
           const uint32_t stage = it % NS, phase = (it / NS) & 1;
           [[maybe_unused]] const long long w1 = DBG_CLOCK();
-          ptx::mbar_wait(&full[stage], phase);
-          ptx::tc_fence_after();
+          if (hb == 0) {                                 // (the second block finds the stages this thread already waited for)
+            ptx::mbar_wait(&full[stage], phase);
+            ptx::tc_fence_after();
+          }
           if (MODE == MODE_SWEEP && lane == 0) DBG_ADD(2, DBG_CLOCK() - w1);
           if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < KATOM / 16; ++k) {
-              const uint64_t ad = adesc0 + uint64_t(ka * (A_ATOM_BYTES >> 4) + k * 2);
+              const uint64_t ad = adesc0 + uint64_t((hb * KATOMS + ka) * (A_ATOM_BYTES >> 4) + k * 2);
               const uint64_t bd = bdesc0 + uint64_t(stage * (B_BYTES >> 4) + k * 2);
               if (PAIR) ptx::umma_f16_pair(tmem_base + as * BN, ad, bd, idesc, (ka | k) != 0);
               else ptx::umma_f16(tmem_base + as * BN, ad, bd, idesc, (ka | k) != 0);
@@ -456,11 +484,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
               ptx::umma_commit_pair(&empty[stage]);                      // both CTAs' producers
               if (ka == KATOMS - 1) ptx::umma_commit_pair(&tfull[as]);   // both CTAs' epilogue warps
             } else {
-              ptx::umma_commit(&empty[stage]);                      // smem stage reusable once these MMAs retire
+              if (hb == NA - 1) ptx::umma_commit(&empty[stage]);    // smem stage reusable once these MMAs retire
               if (ka == KATOMS - 1) ptx::umma_commit(&tfull[as]);   // accumulator complete
             }
           }
           __syncwarp();
+        }
         }
       }
       if (lane == 0) {
@@ -496,9 +525,46 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
       float pv_thr = kInf;                              // MODE_PIVOT: current NPIV-th smallest sampled key of the row
       float as_best = kInf;                             // MODE_ASSIGN: smallest key of the row so far in this thread's chunks,
       int as_col = 0x7fffffff;                          //              and its column
-      const uint32_t tau_addr = ptx::smem_u32(s_tau + row), cnt_addr = ptx::smem_u32(s_cnt + row);
-      uint2* const mylog = a.log + (size_t(grow) * n_splits + split) * a.logcap;
+      // (DUAL: these follow the query block whose accumulator is being scanned -- set at the top of every MMA tile below)
+      uint32_t tau_addr = ptx::smem_u32(s_tau + row), cnt_addr = ptx::smem_u32(s_cnt + row);
+      uint2* mylog = a.log + (size_t(grow) * n_splits + split) * a.logcap;
+      [[maybe_unused]] const uint32_t tau_addr0 = tau_addr, cnt_addr0 = cnt_addr, rs_addr0 = ptx::smem_u32(s_rs + row);
+      [[maybe_unused]] uint2* const mylog0 = mylog;
+      [[maybe_unused]] const size_t log_half = size_t(BM) * n_splits * a.logcap;   // log entries between the two query blocks' rows
       const uint32_t pv_addr = ptx::smem_u32(s_pv + (h * NPSUB) * BM + row);
+      if constexpr (DUAL) {
+        static_assert(!DUAL || NH >= 2, "DUAL: warp h of a lane quarter prepares / publishes the rows of query block qb + h");
+        epi_bar_sync(EPI_THREADS);             // every epilogue warp is done with the previous item
+        if (h < 2) {
+          const int g = grow + int(h) * BM;
+          const bool ok = qb + int(h) < n_qblocks && g < nq;
+          float tau0 = kInf, p0 = -kInf, p1 = -kInf;
+          uint32_t cy = 0;
+          if (ok) {
+            if (a.use_pivots) {
+              const float4 pp = *reinterpret_cast<const float4*>(a.ladder + size_t(g) * 4);
+              p0 = pp.y; p1 = pp.z; tau0 = pp.w;
+            }
+            for (int s2 = 0; s2 < n_splits; ++s2) {   // thresholds and rung counters of the finished splits (see below)
+              if (s2 == split) continue;
+              const size_t o = size_t(g) * n_splits + s2;
+              uint32_t done;
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(a.split_done + o) : "memory");
+              if (done) {
+                tau0 = fminf(tau0, __ldcg(a.log_tau + o));
+                cy += done >> 1;
+              }
+            }
+            cy = min(cy & 0x7fffu, uint32_t(KPT)) | (min(cy >> 15, uint32_t(KPT)) << 15);
+          }
+          if (a.close_rows) tau0 = -kInf;
+          s_tau[h * BM + row] = ok ? tau0 : -kInf;
+          s_cnt[h * BM + row] = ((cy & 0x7fffu) << CN1_SHIFT) | ((cy >> 15) << CN0_SHIFT);
+          s_rs[h * BM + row] = make_float2(p0, p1);
+          carry = cy;                          // this warp publishes the row's counters when the item ends
+        }
+        epi_bar_sync(EPI_THREADS);
+      } else
       if (SWEEP) {
         float tau0 = kInf;
         if (a.use_pivots) {
@@ -612,14 +678,24 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
 
       const uint32_t taddr0 = tmem_base + ((q * 32) << 16) + h * 32;   // this warp's first chunk of accumulator stage 0
       constexpr int CPW = (BN / 32) / NH;    // chunks per warp and tile (even)
-      for (int i = 0; i < nt; ++i, ++tc) {
+      for (int i = 0; i < nt; ++i) {
+#pragma unroll 1
+      for (int hb = 0; hb < NA; ++hb, ++tc) {   // DUAL: the accumulators of query blocks qb, qb + 1 for this gallery tile
+        if constexpr (DUAL) {
+          tau_addr = tau_addr0 + hb * BM * 4;
+          cnt_addr = cnt_addr0 + hb * BM * 4;
+          mylog = mylog0 + size_t(hb) * log_half;
+          const float2 pp = lds_f32x2(rs_addr0 + hb * BM * 8);
+          piv0 = pp.x; piv1 = pp.y;
+        }
+        const uint32_t gtc = DUAL ? tc >> 1 : tc;   // gallery tiles seen (norm-pack ring, tightening turns)
         const uint32_t as = tc & 1;
         [[maybe_unused]] const long long e0 = DBG_CLOCK();
         ptx::mbar_wait(&tfull[as], (tc >> 1) & 1);
         ptx::tc_fence_after();
         [[maybe_unused]] const long long e1 = DBG_CLOCK();
         if (MODE == MODE_SWEEP && warp == 4 && lane == 0) DBG_ADD(3, e1 - e0);
-        const uint32_t nrm = ring_u32 + (tc % NT) * NPACK * 4;
+        const uint32_t nrm = ring_u32 + (gtc % NT) * NPACK * 4;
         const uint32_t taddr = taddr0 + as * BN;
         const int col0 = tile_of<MODE>(a, t0, i) * BN;
         // Two register buffers.  Both loads of a pair are issued before either chunk is scanned, and the TMEM stage is
@@ -660,20 +736,36 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ 
             if (!last) ptx::tmem_ld32(taddr + (cp + NB + b) * NH * 32, v[b]);
           }
         }
-        if (MODE == MODE_SWEEP && h == (tc & (NH - 1))) {
+        if (MODE == MODE_SWEEP && h == (gtc & (NH - 1))) {
           // tighten (the NH warps of a row take turns): once KPT logged entries lie below a pivot, the KPT smallest
           // keys all lie below it
-          const uint32_t cn = s_cnt[row];
-          const float ot = s_tau[row];
+          const int r_ = (DUAL ? hb * BM : 0) + row;
+          const uint32_t cn = s_cnt[r_];
+          const float ot = s_tau[r_];
           float nt_ = ot;
           if (((cn >> CN1_SHIFT) & 511u) >= KPT) nt_ = fminf(nt_, piv1);
           if (((cn >> CN0_SHIFT) & 511u) >= KPT) nt_ = fminf(nt_, piv0);
-          if (nt_ < ot) s_tau[row] = nt_;
+          if (nt_ < ot) s_tau[r_] = nt_;
         }
-        ptx::mbar_arrive(&nempty[tc % NT]);
+        if (!DUAL || hb == NA - 1) ptx::mbar_arrive(&nempty[gtc % NT]);
+      }
       }
 
-      if (SWEEP) {
+      if constexpr (DUAL) {
+        epi_bar_sync(EPI_THREADS);             // all appends of this item are done
+        if (h < 2 && qb + int(h) < n_qblocks) {
+          const size_t o = size_t(grow + int(h) * BM) * n_splits + split;
+          const uint32_t cn = s_cnt[h * BM + row];
+          a.log_cnt[o] = int(cn & CUR_MASK);
+          a.log_tau[o] = s_tau[h * BM + row];
+          if (n_splits > 1) {
+            const uint32_t own1 = ((cn >> CN1_SHIFT) & 511u) - (carry & 0x7fffu), own0 = ((cn >> CN0_SHIFT) & 511u) - (carry >> 15);
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.split_done + o), "r"(1u | (own1 << 1) | (own0 << 16))
+                         : "memory");
+          }
+        }
+      } else if (SWEEP) {
         epi_bar_sync(EPI_THREADS);             // all appends of this item are done
         if (h == 0 && qb_ok) {
           const size_t o = size_t(grow) * n_splits + split;
@@ -1178,12 +1270,27 @@ static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int Dp, in
   return MMSIM_OK;
 }
 
+static bool sweep_pairs();
+
 Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, bool host_mode) {
   Plan p{};
   p.Dp = int(align_up(size_t(D), KATOM));
   p.katoms = p.Dp / KATOM;
   p.n_qblocks = int((nq + BM - 1) / BM);
   p.n_tiles = int((ng + BN - 1) / BN);
+  // MMSIM_KNN_SWEEP=q: the query-streaming sweep (knn_sweepq.cuh; opt-in: faster pipeline, slower candidate path, no net gain)
+  {
+    const char* e = getenv("MMSIM_KNN_SWEEP");
+    p.sweepq = e && e[0] == 'q';
+  }
+  // DUAL sweep (two query blocks resident per CTA, half the L2 -> SM gallery bytes): K <= 128, at least two query blocks.
+  // Opt-in (MMSIM_KNN_DUAL=1): results identical, but halving the L2 traffic bought 0-2% at 128-d and lost 4% at 64-d
+  // (profiles/r2i_sweep_dual_mma2.txt) -- the L2 -> SM stream is not what binds the sweep.
+  {
+    const char* e = getenv("MMSIM_KNN_DUAL");
+    p.dual = p.katoms <= 2 && p.n_qblocks >= 2 && !p.sweepq && !sweep_pairs() && e && atoi(e) == 1;
+  }
+  const int q_items = p.dual ? (p.n_qblocks + 1) / 2 : p.n_qblocks;     // work items per gallery split
   // gallery splits: fill the persistent grid in whole waves without making sweeps too short
   int best_s = 1;
   double best_eff = 0;
@@ -1191,19 +1298,14 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, bool host_
     const int tps = (p.n_tiles + s - 1) / s;
     if (s > 1 && tps < 64) break;
     const int s_eff = (p.n_tiles + tps - 1) / tps;
-    const int64_t items = int64_t(p.n_qblocks) * s_eff;
+    const int64_t items = int64_t(q_items) * s_eff;
     const int64_t waves = (items + num_sms - 1) / num_sms;
     // cost model: waves * tiles per sweep, minus a penalty per extra split (every split restarts its threshold ladder)
-    const double eff = double(p.n_qblocks) * p.n_tiles / (double(waves) * num_sms * tps) - 0.02 * (s - 1);
+    const double eff = double(q_items) * p.n_tiles / (double(waves) * num_sms * tps) - 0.02 * (s - 1);
     if (eff > best_eff + 1e-9) {
       best_eff = eff;
       best_s = s_eff;
     }
-  }
-  // MMSIM_KNN_SWEEP=q: the query-streaming sweep (knn_sweepq.cuh; opt-in: faster pipeline, slower candidate path, no net gain)
-  {
-    const char* e = getenv("MMSIM_KNN_SWEEP");
-    p.sweepq = e && e[0] == 'q';
   }
   p.host_splits = int(std::max<int64_t>(1, std::min<int64_t>(8, p.n_tiles / 64)));
   if (host_mode) {
@@ -1223,7 +1325,7 @@ Plan make_plan(int64_t nq, int64_t ng, int64_t D, int k, int num_sms, bool host_
   p.n_splits = best_s;
   p.tiles_per_split = (p.n_tiles + p.n_splits - 1) / p.n_splits;
   p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.grid = int(std::min<int64_t>(num_sms, int64_t(p.n_qblocks) * p.n_splits));
+  p.grid = int(std::min<int64_t>(num_sms, int64_t(q_items) * p.n_splits));
   p.unc_cap = int(nq);
 
   // candidate log + pivot pre-pass.  Small galleries are logged whole (threshold +inf); otherwise a systematic sample of
@@ -1356,9 +1458,20 @@ static int sweep_nepi() {
   return e && atoi(e) == 8 ? 8 : NEPI_SWEEP;
 }
 
+template <int KATOMS>
+static int launch_dual(int grid, const CUtensorMap& tq, const CUtensorMap& tg, const SweepArgs& args, cudaStream_t stream) {
+  using S = Smem<KATOMS, true>;
+  auto kern = knn_tc_kernel<KATOMS, NEPI_SWEEP, MODE_SWEEP, 0, false, true>;
+  MMSIM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES));
+  kern<<<grid, 128 + NEPI_SWEEP * 32, S::DYN_BYTES, stream>>>(tq, tg, args);
+  MMSIM_CUDA_CHECK(::mmsim::launched());
+  return MMSIM_OK;
+}
+
 template <int MODE, int ABL>
 static int launch_mode(int katoms, int grid, const CUtensorMap& tq, const CUtensorMap& tg, const SweepArgs& args, cudaStream_t s) {
   if constexpr (MODE == MODE_SWEEP && ABL == 0) {
+    if (args.dual && katoms <= 2) return katoms == 1 ? launch_dual<1>(grid, tq, tg, args, s) : launch_dual<2>(grid, tq, tg, args, s);
     if (sweep_nepi() == 8) {
       switch (katoms) {
         case 1: return launch_tc<1, 8, MODE, ABL>(grid, tq, tg, args, s);
@@ -1718,6 +1831,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     SweepArgs args{};
     args.gpack = gpack;
     args.nq = int(nq); args.n_qblocks = p.n_qblocks; args.n_tiles = p.n_tiles;
+    args.dual = (p.dual && sweep_ablation() != 2 && sweep_ablation() != 4) ? 1 : 0;   // (the two ablation instantiations are single-block kernels)
     args.n_splits = p.n_splits; args.tiles_per_split = p.tiles_per_split;
     args.use_pivots = p.use_pivots;
     args.log = log; args.logcap = p.logcap; args.log_cnt = log_cnt; args.log_tau = log_tau; args.split_done = split_done;
@@ -1808,9 +1922,10 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
             rc = launch_q(int(t0), int(t1), x);
           } else {
             SweepArgs sa = args;
-            sa.item_begin = c * p.n_qblocks;
-            sa.item_end = (c + 1) * p.n_qblocks;
-            rc = launch_mode<MODE_SWEEP, 0>(p.katoms, std::min(num_sms, p.n_qblocks), tq, tg, sa, x);
+            const int q_items = sa.dual ? (p.n_qblocks + 1) / 2 : p.n_qblocks;
+            sa.item_begin = c * q_items;
+            sa.item_end = (c + 1) * q_items;
+            rc = launch_mode<MODE_SWEEP, 0>(p.katoms, std::min(num_sms, q_items), tq, tg, sa, x);
           }
           if (rc) return rc;
         }

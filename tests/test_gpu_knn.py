@@ -241,3 +241,24 @@ def test_shapes_beyond_the_tensor_core_pipeline(n, d, k, excl, rs):
     ref_d, ref_i = O.knn(q, x, k, exclude_self=excl)
     assert dist.dtype == np.float32 and idx.dtype == np.int64
     assert np.array_equal(dist, ref_d) and np.array_equal(idx, ref_i)
+
+
+def test_dual_query_block_sweep_matches(rs):
+    """MMSIM_KNN_DUAL=1 (opt-in): two query blocks resident per CTA, every gallery tile multiplied with both -- same logs
+    per query row, so bit-identical results (odd number of query blocks: the last CTA's second block is empty)."""
+    from multimodal_similarity_b200.retrieval import knn_raw, check_status
+    x, _ = clustered(rs, 70000, 128, 60)
+    g = torch.from_numpy(x).cuda()
+    q = torch.from_numpy(clustered(rs, 5 * 128 + 37, 128, 60)[0]).cuda()
+    d0, i0, st0 = knn_raw(q, g, 100)
+    check_status(st0)
+    d0, i0 = d0.clone(), i0.clone()
+    os.environ["MMSIM_KNN_DUAL"] = "1"
+    try:
+        d1, i1, st1 = knn_raw(q, g, 100)
+        check_status(st1)
+    finally:
+        del os.environ["MMSIM_KNN_DUAL"]
+    assert torch.equal(d0, d1) and torch.equal(i0, i1)
+    ref_d, ref_i = O.knn(q[:64].cpu().numpy(), x, 100)
+    assert np.array_equal(d1[:64].cpu().numpy(), ref_d)
