@@ -3,10 +3,10 @@
 mkdir -p gpurun_out
 for n in 1 2 4 8; do
   if [ $n -eq 1 ]; then
-    python bench.py --gpus 1 --steps 5 --warmup 3 --no-extras > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
+    python bench.py --gpus 1 --steps 10 --warmup 3 --no-extras > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
   else
     python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) \
-      bench.py --gpus $n --steps 5 --warmup 3 --no-extras > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
+      bench.py --gpus $n --steps 10 --warmup 3 --no-extras > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
   fi
   python - <<PY
 import json
