@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--query-groups", default="auto",
                     help="N > 1: query groups of the 2-D decomposition (ShardedGallery(query_groups=...)); 1 = every rank "
                          "holds a different gallery shard and sweeps every query; auto = two gallery parts per group from 4 GPUs on")
+    ap.add_argument("--graph", action="store_true",
+                    help="N > 1: time replays of the CUDA graph of one sharded step (ShardedGallery.graphed) instead of eager calls "
+                         "(opt-in: measured at N = 2 only this round, where a 14 ms step has no launch gaps to close)")
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / secondary configs (profiling runs)")
     ap.add_argument("--no-big", action="store_true", help="skip the 10M x 256-d single-GPU config among the secondary ones")
     return ap.parse_args()
@@ -680,12 +683,37 @@ def main():
     torch.cuda.synchronize()
 
     statuses = []
+    graphed, launch_how, launches_per_replay = None, "eager calls through the C-ABI", 0
+    if world > 1 and a.graph:
+        # the sharded step captured once as a CUDA graph (kernels + NCCL collectives) and replayed -- a public API of the
+        # product (ShardedGallery.graphed); checked against the eager call before it is timed.  All ranks agree on the outcome.
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            eager_d, eager_i = sg.retrieve(queries, k, check=False)
+            mm.load().mmsim_kernel_launches(1)
+            graphed = sg.graphed(queries, k)                    # two warm-up calls + the captured one
+            launches_per_replay = int(mm.load().mmsim_kernel_launches(1)) // 3
+            gd, gi = graphed()
+            torch.cuda.synchronize()
+            if not (torch.equal(gd, eager_d) and torch.equal(gi, eager_i)):
+                ok.zero_()
+            del eager_d, eager_i
+        except Exception as e:  # noqa: BLE001
+            print(f"bench: CUDA-graph capture of the sharded step failed on rank {rank}: {e!r}", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0:
+            graphed = None
+        else:
+            launch_how = "CUDA graph of one ShardedGallery.retrieve (kernels + NCCL collectives) captured once, replayed per step"
 
     def step():
         if world == 1:
             d_, i_, st = knn_raw(queries, sg.shard, k)
             statuses.append(st)
             return d_, i_
+        if graphed is not None:
+            return graphed()
         return sg.retrieve(queries, k, check=False)
 
     def barrier():
@@ -714,6 +742,8 @@ def main():
     with ClockSampler(local) as clk:
         ms, (out_d, out_i) = timed(step, a.steps)
         gpu_launches = int(lib.mmsim_kernel_launches(1))     # kernels of libmmsim.so launched inside the timed region
+        if graphed is not None:      # replays do not pass through the library's launch path: kernels per captured call x steps
+            gpu_launches = launches_per_replay * a.steps
         # the timed region can be shorter than nvidia-smi's sampling period (K steps of a few ms at N = 8): keep the SAME
         # load running, untimed, until the sampler has a few rows (every rank takes the same number of extra steps)
         extra = 0
@@ -732,7 +762,8 @@ def main():
     if statuses:
         fell_back = check_status(statuses[-1])
     else:       # sharded: queries the global certificate did not prove (the timed steps run check=False and do not repair them)
-        fell_back = int(sg.last_uncertified) if sg.last_uncertified is not None else 0
+        unc = graphed.uncertified if graphed is not None else sg.last_uncertified
+        fell_back = int(unc) if unc is not None else 0
     value = Q * a.steps / (ms / 1e3)
 
     # ---- e2e: pinned host buffers in, host result out, every step
@@ -924,7 +955,7 @@ def main():
         # sample + tcgen05 pivot pre-pass, the ladder, the tcgen05 sweep, the re-rank, and the (idle) fallback kernels
         "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "gpu_launches_per_step": gpu_launches / a.steps,
         "roofline": roofline,
-        "exact_fallback_queries": fell_back, "protocol": sg.last_protocol if world > 1 else "single",
+        "exact_fallback_queries": fell_back, "protocol": sg.last_protocol if world > 1 else "single", "launch": launch_how,
     }
 
     if rank == 0 and world == 1 and not a.no_extras:
@@ -958,8 +989,12 @@ def main():
             if key in sec and "value" in sec[key]:
                 result[name] = sec[key]["value"]
     if rank == 0:
-        print(json.dumps(result))
+        print(json.dumps(result), flush=True)
     if world > 1:
+        if graphed is not None:      # a live graph holds NCCL kernels: release it before the communicator goes away
+            graphed.close()
+            graphed = None
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

@@ -223,6 +223,42 @@ def patch_rows(out_d, out_i, allfb: torch.Tensor, bases: torch.Tensor, cap: int,
     _lib.check(rc, "mmsim_knn_merge_patch")
 
 
+class GraphedRetrieve:
+    """See ``ShardedGallery.graphed``."""
+
+    def __init__(self, sg, queries, k, exclude_self, self_offset):
+        if not (torch.is_tensor(queries) and queries.is_cuda):
+            raise ValueError("graphed() needs the queries as a CUDA tensor (the captured buffer)")
+        self.sg, self.queries = sg, to_cuda_f32(queries, sg.shard.device)
+        dev = self.queries.device
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):           # warm-up outside the capture: workspaces, kernel attributes, NCCL channels
+            for _ in range(2):
+                sg.retrieve(self.queries, k, exclude_self=exclude_self, self_offset=self_offset, check=False)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = sg.retrieve(self.queries, k, exclude_self=exclude_self, self_offset=self_offset, check=False)
+            self.uncertified = sg.last_uncertified if sg.last_uncertified is not None else torch.zeros((), dtype=torch.int32, device=dev)
+        self.protocol = sg.last_protocol
+
+    def __call__(self, queries=None):
+        if queries is not None:
+            self.queries.copy_(queries, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+    def close(self):
+        """Release the captured graph (it holds NCCL kernels): call this on every rank BEFORE ``destroy_process_group`` --
+        tearing the communicator down under a live graph hung a 2-GPU run of this round in its teardown."""
+        torch.cuda.synchronize(self.queries.device)
+        self.out = self.uncertified = None
+        self.graph = None
+
+
 def resolve_query_groups(query_groups, world: int) -> int:
     """``"auto"``: two gallery parts per query group from 4 ranks on (R = world / 2), otherwise one group."""
     if query_groups == "auto":
@@ -311,8 +347,22 @@ class ShardedGallery:
         return merge_parts(gathered[:, 0].view(torch.float32), gathered[:, 1], bases, k)
 
     def _bases(self, device):
-        per = -(-self.total // self.parts)
-        return torch.tensor([min(self.total, r * per) for r in range(self.parts)], dtype=torch.int64, device=device)
+        """First gallery row of every part of my group (cached: a host -> device copy cannot be captured in a CUDA graph)."""
+        key = str(device)
+        if getattr(self, "_bases_cache", None) is None or self._bases_cache[0] != key:
+            per = -(-self.total // self.parts)
+            self._bases_cache = (key, torch.tensor([min(self.total, r * per) for r in range(self.parts)], dtype=torch.int64,
+                                                   device=device))
+        return self._bases_cache[1]
+
+    def graphed(self, queries, k, *, exclude_self=False, self_offset=0):
+        """``retrieve`` for a FIXED query buffer captured once as a CUDA graph (kernels + NCCL collectives) and replayed:
+        ``g = sg.graphed(q, k); dist, idx = g()`` (``g(new_queries)`` copies them into the captured buffer first).  At 8 GPUs a
+        100k-query step is ~4 ms made of ~30 kernels and 6 collectives issued from Python; replaying the graph removes the
+        launch gaps between them.  Every rank must capture and replay in step (the collectives are part of the graph).
+        The replay does not repair uncertified queries: ``g.uncertified`` (device scalar) says how many the last replay had --
+        call ``retrieve`` when it is not zero."""
+        return GraphedRetrieve(self, queries, int(k), exclude_self, self_offset)
 
     def _retrieve_exact_shards(self, q, k, exclude_self, self_offset, check):
         nq = q.shape[0]
