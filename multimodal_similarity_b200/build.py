@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "-cudart", "static"]
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "-cudart", "static", "-ldl"]      # -ldl: header-only NVTX 3
     subprocess.run(cmd, check=True)
     return LIB
 

@@ -5,6 +5,8 @@
 #include <cstdint>
 #include <cstdio>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/mmsim.h"
 
 namespace mmsim {
@@ -31,6 +33,18 @@ cudaError_t launched();
       return (code);                     \
     }                                    \
   } while (0)
+
+// NVTX range over the host-side enqueue of an entry point or a phase (header-only NVTX 3: a no-op costing one indirect call
+// unless a tool -- nsys, ncu --nvtx -- injected itself); the kernels launched inside inherit it in the tool's timeline.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define MMSIM_CAT2(a, b) a##b
+#define MMSIM_CAT(a, b) MMSIM_CAT2(a, b)
+#define MMSIM_RANGE(name) ::mmsim::NvtxRange MMSIM_CAT(_mmsim_range_, __LINE__)(name)
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

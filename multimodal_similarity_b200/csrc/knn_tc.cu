@@ -1720,6 +1720,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   // queries while the gallery shard is still on its way from the host)
   const bool prep_g = (phases & (kPhasePrep | kPhasePrepG)) != 0, prep_q = (phases & (kPhasePrep | kPhasePrepQ)) != 0;
   if (prep_g) {
+    MMSIM_RANGE("knn: gallery operand copies");
     MMSIM_CUDA_CHECK(cudaMemsetAsync(gstats, 0, 64, stream));
     if (host) {
       // host-buffer mode: EVERY host -> device copy of the call is queued here, on the copy stream, in the order the
@@ -1774,6 +1775,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     }
   }
   if (prep_q) {
+    MMSIM_RANGE("knn: query operand copies + grouping");
     const unsigned qb = unsigned(std::min<int64_t>((nq + warps_per_block - 1) / warps_per_block, cap));
     prep<<<qb, PREP_THREADS, 0, stream>>>(Q, nq, nq, int(D), p.Dp, -2.0f, qh, qnorm, qerr, 0, nullptr, nullptr);
     MMSIM_CUDA_CHECK(::mmsim::launched());
@@ -1843,6 +1845,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
       MMSIM_CUDA_CHECK(::mmsim::launched());
     }
     if ((phases & kPhasePivot) && p.use_pivots) {
+      MMSIM_RANGE("knn: pivot pre-pass");
       // The pre-pass sweeps a compact block holding the sampled gallery rows (sample_row(): every sample_div-th row).
       // Device-resident call: the operand-copy kernel gathers them from G.  Host-buffer call: they come over first, as
       // one strided 2-D copy per segment, so the pre-pass (and with it the first sweep) does not wait for the gallery.
@@ -1875,6 +1878,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
       MMSIM_CUDA_CHECK(::mmsim::launched());
     }
     if (phases & kPhaseTensor) {
+      MMSIM_RANGE("knn: tcgen05 sweep");
       if (p.n_splits > 1)
         MMSIM_CUDA_CHECK(cudaMemsetAsync(split_done, 0, size_t(p.n_qblocks) * BM * p.n_splits * 4, stream));
       const int abl = sweep_ablation();
@@ -1964,6 +1968,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   //    key = |g|^2 - 2 q.g: (Dp + 8) roundings of relative size 2^-24, on terms bounded by (|q|^2 + |g|^2), 4x safety.
   if (phases & kPhaseRerank) {
     const float delta_coeff = delta_coeff_of(p.Dp);
+    MMSIM_RANGE("knn: select + exact re-rank + certificate");
     const int blocks = int((nq + RR_WARPS - 1) / RR_WARPS);
     const int scratch_words = RR_STAGE;               // per-warp scratch: the staged keys of the selection
     const size_t smem = size_t(RR_WARPS) * (size_t(D) + 2 * KP + scratch_words) * 4;
@@ -1980,6 +1985,7 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
   // 4. exact fallback for the uncertified queries (knn_fallback.cuh; the count lives on the device: when it is zero the
   //    kernels below find nothing to do)
   if (((phases & kPhaseFallback) && !shard_kp) || (phases & kPhaseFinish)) {
+    MMSIM_RANGE("knn: exact fallback of uncertified queries");
     if ((phases & kPhaseFallback) && !(phases & kPhaseRerank))      // phase-by-phase timing: restart the tier-2 queue
       MMSIM_CUDA_CHECK(cudaMemsetAsync(status + 1, 0, 2 * sizeof(int), stream));
     FbLists L{status, unc_query, unc_bound, reinterpret_cast<int*>(w + p.off_fb2_list), status, p.unc_cap};
