@@ -1003,6 +1003,7 @@ constexpr int RR_STAGE = 1024;             // logged keys per query staged in sh
 __device__ __forceinline__ uint32_t sortable(uint32_t fbits) { return (fbits & 0x80000000u) ? ~fbits : (fbits | 0x80000000u); }
 __device__ __forceinline__ float unsortable(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 
+template <bool VEC>
 __global__ void __launch_bounds__(RR_WARPS * 32)
 knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int nq, int64_t ng, int D,
                   const uint2* __restrict__ log, int logcap, const int* __restrict__ log_cnt, const float* __restrict__ log_tau,
@@ -1016,10 +1017,11 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
                   int slice_rows, int64_t slice_stride /* gallery-shard mode, slice_rows > 0: query qo's outputs go to block
                   qo / slice_rows (blocks slice_stride words apart) at row qo % slice_rows -- the layout the all-to-all of the
                   candidate lists sends, written directly */) {
+  // VEC: 8 | D <= 256 and 16-byte aligned gallery rows -- 128-bit gathers, two lanes per candidate (below)
   // kp <= KP candidates are re-ranked.  out_lb == nullptr: emit the top-k and certify locally (k <= kp).
   // out_lb != nullptr (gallery-shard mode): emit all kp re-ranked candidates (k == kp) plus the lower bound on the
   // true distance of every row of this shard that is NOT among them; the certificate is evaluated after the merge.
-  extern __shared__ float rr_smem[];
+  extern __shared__ __align__(16) float rr_smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qi = blockIdx.x * RR_WARPS + warp;       // position in the sweep's order: logs, norms
   if (qi >= nq) return;
@@ -1130,7 +1132,60 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
 
   // ---- exact distances (reference arithmetic): 8 lanes per candidate, 4 candidates per round
   const int self = exclude_self ? int(self_offset + qo) : -1;
-  {
+  if constexpr (VEC) {
+    // 128-bit form (8 | D <= 256): TWO lanes per candidate, lane h = lane & 1 owns NumPy's accumulators r[4h .. 4h + 3] -- one
+    // float4 of every 8-element step -- so a row goes through a quarter of the load instructions of the 8-lane form below
+    // and 32 candidates (two per lane pair) are in flight per round.  Same operations in the same order per accumulator,
+    // the same combine ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) (the second operand comes from the partner lane; fp32 addition
+    // commutes), the same two-leaf split above 128 elements (exact.cuh): every bit as before.
+    const int h = lane & 1, pr = lane >> 1;
+    const int n2 = D <= 128 ? D : (D / 2 - (D / 2) % 8);      // first leaf [0, n2), second leaf [n2, D): multiples of 8, <= 128
+    const float4* q4 = reinterpret_cast<const float4*>(qs) + h;
+#pragma unroll 1
+    for (int r0 = 0; r0 < KP; r0 += 32) {
+      if (r0 >= kp) break;                      // slots >= kp hold the (+inf, -1) padding
+      const int ia = sv[r0 + pr], ib = sv[r0 + 16 + pr];
+      const bool la = ia >= 0 && ia != self, lb = ib >= 0 && ib != self;
+      const float4* ga = reinterpret_cast<const float4*>(G + size_t(la ? ia : 0) * D) + h;
+      const float4* gb = reinterpret_cast<const float4*>(G + size_t(lb ? ib : 0) * D) + h;
+      float sa = 0.f, sb = 0.f;
+      for (int e0 = 0; e0 < D;) {
+        const int e1 = e0 == 0 ? n2 : D;
+        const int j0 = e0 >> 2, j1 = e1 >> 2;   // in float4 units; this lane's float4s are j0, j0 + 2, ... (+ h in the pointers)
+        float4 x = __ldg(ga + j0), y = __ldg(gb + j0), q = q4[j0];
+        float a0 = exact_term<kSquaredEuclidean>(q.x, x.x), a1 = exact_term<kSquaredEuclidean>(q.y, x.y);
+        float a2 = exact_term<kSquaredEuclidean>(q.z, x.z), a3 = exact_term<kSquaredEuclidean>(q.w, x.w);
+        float b0 = exact_term<kSquaredEuclidean>(q.x, y.x), b1 = exact_term<kSquaredEuclidean>(q.y, y.y);
+        float b2 = exact_term<kSquaredEuclidean>(q.z, y.z), b3 = exact_term<kSquaredEuclidean>(q.w, y.w);
+#pragma unroll 4
+        for (int j = j0 + 2; j < j1; j += 2) {
+          x = __ldg(ga + j); y = __ldg(gb + j); q = q4[j];
+          a0 = __fadd_rn(a0, exact_term<kSquaredEuclidean>(q.x, x.x));
+          a1 = __fadd_rn(a1, exact_term<kSquaredEuclidean>(q.y, x.y));
+          a2 = __fadd_rn(a2, exact_term<kSquaredEuclidean>(q.z, x.z));
+          a3 = __fadd_rn(a3, exact_term<kSquaredEuclidean>(q.w, x.w));
+          b0 = __fadd_rn(b0, exact_term<kSquaredEuclidean>(q.x, y.x));
+          b1 = __fadd_rn(b1, exact_term<kSquaredEuclidean>(q.y, y.y));
+          b2 = __fadd_rn(b2, exact_term<kSquaredEuclidean>(q.z, y.z));
+          b3 = __fadd_rn(b3, exact_term<kSquaredEuclidean>(q.w, y.w));
+        }
+        float ta = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+        float tb = __fadd_rn(__fadd_rn(b0, b1), __fadd_rn(b2, b3));
+        ta = __fadd_rn(ta, __shfl_xor_sync(0xffffffffu, ta, 1));
+        tb = __fadd_rn(tb, __shfl_xor_sync(0xffffffffu, tb, 1));
+        sa = e0 == 0 ? ta : __fadd_rn(sa, ta);
+        sb = e0 == 0 ? tb : __fadd_rn(sb, tb);
+        e0 = e1;
+      }
+      __syncwarp();
+      if (h == 0) {
+        sk[r0 + pr] = la ? __fsqrt_rn(sa) : kInf;
+        sv[r0 + pr] = la ? ia : 0x7fffffff;
+        sk[r0 + 16 + pr] = lb ? __fsqrt_rn(sb) : kInf;
+        sv[r0 + 16 + pr] = lb ? ib : 0x7fffffff;
+      }
+    }
+  } else {
     // (Round 2 tried gathering the rows with 16-byte cp.async into shared memory, eight rows per batch, double-buffered: a
     // whole 512-byte row per instruction and far more bytes in flight per warp -- and it was SLOWER, 2.9 vs 2.25 ms: the row
     // buffers halve the resident warps, and reducing from shared memory adds an LDS per element.  gpurun_out/r2_s_bench*.json)
@@ -1182,6 +1237,36 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
 
   // ---- bitonic sort of the candidate slots (padded to a power of two >= kp) in shared memory by (distance, index)
   const int SP = kp <= 32 ? 32 : (kp <= 64 ? 64 : KP);
+  // VEC: the slots are packed first -- (distance bits << 32 | index) in one 64-bit word over the sk | sv arrays -- so that a
+  // compare-exchange is two 64-bit loads, one unsigned comparison and two stores instead of four loads, a two-level comparison
+  // and four stores (the sort was a sixth of this kernel's instructions).  Distances are non-negative floats or +inf and
+  // indices non-negative, so the unsigned order of the words is the (distance, index) order.
+  unsigned long long* pk = reinterpret_cast<unsigned long long*>(sk);
+  if constexpr (VEC) {
+    unsigned long long e[KP / 32];
+#pragma unroll
+    for (int r = 0; r < KP / 32; ++r)
+      e[r] = (static_cast<unsigned long long>(__float_as_uint(sk[lane + 32 * r])) << 32) | static_cast<uint32_t>(sv[lane + 32 * r]);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < KP / 32; ++r) pk[lane + 32 * r] = e[r];
+    __syncwarp();
+    for (int size = 2; size <= SP; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = lane; t < SP / 2; t += 32) {
+          const int lo = 2 * t - (t & (stride - 1));
+          const int hi = lo + stride;
+          const bool asc = (lo & size) == 0;
+          const unsigned long long a = pk[lo], b = pk[hi];
+          if ((a > b) == asc) {
+            pk[lo] = b;
+            pk[hi] = a;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else
   for (int size = 2; size <= SP; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int t = lane; t < SP / 2; t += 32) {
@@ -1202,9 +1287,9 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
 
   const size_t o_row = slice_rows > 0 ? size_t(qo / slice_rows) * size_t(slice_stride) + size_t(qo % slice_rows) * k : size_t(qo) * k;
   for (int r = lane; r < k; r += 32) {
-    const float d = sk[r];
+    const float d = VEC ? __uint_as_float(uint32_t(pk[r] >> 32)) : sk[r];
     out_dist[o_row + r] = d;
-    out_idx[o_row + r] = (d < kInf) ? sv[r] : -1;
+    out_idx[o_row + r] = (d < kInf) ? (VEC ? int(uint32_t(pk[r])) : sv[r]) : -1;
   }
 
   // ---- certificate: lower bound on the true distance of every row that is not a candidate
@@ -1226,7 +1311,7 @@ knn_rerank_kernel(const float* __restrict__ Q, const float* __restrict__ G, int 
     if (out_lb) {
       out_lb[slice_rows > 0 ? size_t(qo / slice_rows) * size_t(slice_stride) + size_t(qo % slice_rows) : size_t(qo)] = lb;
     } else {
-      const float dk = sk[k - 1];
+      const float dk = VEC ? __uint_as_float(uint32_t(pk[k - 1] >> 32)) : sk[k - 1];
       if (!(dk < lb)) {
         const int slot = atomicAdd(&status[0], 1);     // unc_cap == nq: every query has a slot
         if (slot < unc_cap) {
@@ -1972,8 +2057,16 @@ int run(const float* Q, int64_t nq, const float* G, int64_t ng, int64_t D, int k
     const int blocks = int((nq + RR_WARPS - 1) / RR_WARPS);
     const int scratch_words = RR_STAGE;               // per-warp scratch: the staged keys of the selection
     const size_t smem = size_t(RR_WARPS) * (size_t(D) + 2 * KP + scratch_words) * 4;
-    MMSIM_CUDA_CHECK(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    knn_rerank_kernel<<<blocks, RR_WARPS * 32, smem, stream>>>(Q, G, int(nq), ng, int(D), log, p.logcap, log_cnt, log_tau,
+    // MMSIM_RR_VEC=1 (opt-in, experiment): 128-bit gathers + packed 64-bit sort where the width and the alignment allow.
+    // Bit-identical (tests/test_gpu_zz_graphed.py) and SLOWER on B200 -- re-rank phase 3.12 against 2.35 ms at 100k x 1M x 128
+    // (profiles/r2x_rerank_vec.txt): 16 rows per load instruction instead of 4 and 36 instead of 40 resident warps lose more
+    // than the 30% fewer instructions win, like the cp.async row gather before it.  The default stays the 8-lane form.
+    const char* rr_env = getenv("MMSIM_RR_VEC");
+    const bool rr_vec = (D % 8 == 0 && D >= 8 && D <= 256 && (reinterpret_cast<uintptr_t>(G) & 15) == 0 &&
+                        rr_env && rr_env[0] == '1');
+    auto rerank = rr_vec ? knn_rerank_kernel<true> : knn_rerank_kernel<false>;
+    MMSIM_CUDA_CHECK(cudaFuncSetAttribute(rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    rerank<<<blocks, RR_WARPS * 32, smem, stream>>>(Q, G, int(nq), ng, int(D), log, p.logcap, log_cnt, log_tau,
                                                                p.n_splits, qnorm, qerr, gstats, delta_coeff, shard_kp ? shard_kp : k,
                                                                shard_kp ? shard_kp : KP, exclude_self, self_offset, out_dist,
                                                                out_idx, shard_kp ? out_lb : nullptr, status, unc_query,

@@ -39,3 +39,23 @@ def test_graphed_needs_device_queries(rs):
     sg = mm.ShardedGallery(x)
     with pytest.raises(ValueError):
         sg.graphed(x[:10], 5)
+
+
+def test_rerank_gather_forms_agree(rs, monkeypatch):
+    """The re-rank kernel's opt-in 128-bit gather form (MMSIM_RR_VEC=1: two lanes per candidate, packed 64-bit sort; 8 | D <= 256)
+    and its default 8-lane form return the same bits -- one- and two-leaf summation trees, ties (duplicated gallery rows),
+    leave-one-out -- and both equal the oracle."""
+    import multimodal_similarity_b200 as mm
+    for ng, nq, d, k, excl in ((40000, 700, 128, 100, False), (30000, 500, 256, 50, False), (20000, 400, 200, 30, False),
+                               (9000, 600, 64, 20, True), (5000, 200, 8, 10, False)):
+        x = clustered(rs, ng, d, 30)[0]
+        x[1::7] = x[0:-1:7][: len(x[1::7])]                        # exact duplicates: ties on (distance), broken by index
+        g = torch.from_numpy(x).cuda()
+        q = g[:nq].clone() if excl else torch.from_numpy(clustered(rs, nq, d, 30)[0]).cuda()
+        monkeypatch.setenv("MMSIM_RR_VEC", "1")
+        d1, i1 = mm.retrieve(q, g, k, exclude_self=excl)
+        monkeypatch.delenv("MMSIM_RR_VEC", raising=False)
+        d0, i0 = mm.retrieve(q, g, k, exclude_self=excl)
+        assert torch.equal(d0, d1) and torch.equal(i0, i1), (ng, nq, d, k)
+        ref_d, _ = O.knn(q[:64].cpu().numpy(), x, k, exclude_self=excl)
+        assert np.array_equal(d1[:64].cpu().numpy(), ref_d)
