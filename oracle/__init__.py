@@ -17,8 +17,17 @@ Parity pin status
   container and committed their outputs as ``tests/golden/*.npz``;
   ``tests/test_oracle_golden.py`` checks this restatement against them
   bit-for-bit.
-* TensorFlow half (cdist_tf, batch_hard, lifted_loss): PARITY UNPINNED --
-  TensorFlow is not installable here, the reference has no tests or golden
-  vectors.  The restatement follows the TF graph op for op and is pinned only
-  by the hand-checked known-answer tests of SURVEY.md Appendix B.
+* TensorFlow half (cdist_tf, batch_hard, lifted_loss): TensorFlow is not
+  installable here and the reference has no tests or golden vectors, so
+  TensorFlow's own kernels are never executed.  The restatement
+  (``oracle/losses_torch.py``) follows the TF graph op for op and is pinned by
+  (a) the hand-checked known-answer tests of SURVEY.md Appendix B and (b) the
+  reference's OWN functions executed unmodified under a torch-backed stand-in
+  for the ``tf.*`` calls they make (``oracle/tf_shim.py``,
+  ``oracle/make_golden_losses.py`` -> ``tests/golden/loss_*.npz``,
+  ``tests/test_oracle_losses_golden.py``).  That pins the reference's source
+  as executed code; the stand-in's reading of TF semantics (even tie split of
+  reduce_max/min gradients, reducers of empty tensors) is stated in its header.
+* tf.contrib triplet_semihard_loss / lifted_struct_loss: third-party source
+  absent from /root/reference -- PARITY UNPINNED.
 """

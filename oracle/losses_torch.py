@@ -1,11 +1,15 @@
 """torch-CPU restatement of the reference's TensorFlow loss graph.
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED by the
-reference (TensorFlow cannot run here and the reference ships no tests): this
-file follows src/utils.py:302-311,343-360 and src/networks.py:797-870 op for
-op, in the reference's materialising form ([N,N,D] difference tensor), and is
-pinned only by the hand-checked known-answer tests of SURVEY.md Appendix B
-(tests/test_oracle_kat.py).  Gradients come from torch autograd through the
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  TensorFlow cannot run here
+and the reference ships no tests, so TensorFlow's own kernels are never
+executed: this file follows src/utils.py:302-311,343-360 and
+src/networks.py:797-870 op for op, in the reference's materialising form
+([N,N,D] difference tensor), and is pinned by the hand-checked known-answer
+tests of SURVEY.md Appendix B (tests/test_oracle_kat.py) and by the outputs of
+the reference's own functions executed unmodified under oracle/tf_shim.py
+(tests/golden/loss_*.npz, tests/test_oracle_losses_golden.py).  The tf.contrib
+section at the end has no reference source to execute: PARITY UNPINNED.
+Gradients come from torch autograd through the
 same ops; ``amax``/``amin`` split the gradient evenly among ties exactly like
 TF's ``_MinOrMaxGrad``.
 
